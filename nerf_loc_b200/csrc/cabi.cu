@@ -1,0 +1,254 @@
+// extern "C" surface of libnerfloc_b200.so (declared in include/nerfloc_b200.h).
+#include <stdio.h>
+#include <string.h>
+#include "../../include/nerfloc_b200.h"
+#include "match_kernels.h"
+#include "nlb_internal.h"
+#include "render_kernels.h"
+
+namespace nlb {
+
+static thread_local char g_err[512] = "";
+
+int set_error(const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg ? msg : "unknown error");
+  return 1;
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return 0;
+  char buf[480];
+  snprintf(buf, sizeof(buf), "%s: %s", what, cudaGetErrorString(e));
+  return set_error(buf);
+}
+
+static SceneDev to_dev(const nlb_scene* s) {
+  SceneDev d{};
+  d.V = s->V; d.H = s->H; d.W = s->W; d.h = s->h; d.w = s->w;
+  d.images = s->images; d.feat = s->featmaps; d.vis = s->vis_maps; d.cams = s->cams;
+  d.near_ = s->near_plane; d.far_ = s->far_plane;
+  d.M = s->M; d.sup_pre = s->sup_pre; d.sup_geo = s->sup_geo; d.knn = s->knn_index;
+  d.qc[0] = s->query_center[0]; d.qc[1] = s->query_center[1]; d.qc[2] = s->query_center[2];
+  return d;
+}
+
+static int check_scene(const nlb_scene* s, bool need_support = true) {
+  if (!s) return set_error("scene is NULL");
+  if (!s->images || !s->featmaps || !s->vis_maps || !s->cams) return set_error("scene: NULL map / camera pointer");
+  if (need_support && (!s->sup_pre || !s->sup_geo || !s->knn_index || s->M < 1))
+    return set_error("scene: support points not prepared");
+  if (s->V < 1 || s->V > 16) return set_error("scene: number of reference views must be in 1..16");
+  if (s->H < 2 || s->W < 2 || s->h < 2 || s->w < 2) return set_error("scene: maps must be at least 2x2");
+  return 0;
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+struct Carver {
+  char* p;
+  size_t left;
+  bool ok = true;
+  template <class T>
+  T* take(size_t n) {
+    const size_t b = align256(n * sizeof(T));
+    if (b > left) { ok = false; return nullptr; }
+    T* r = reinterpret_cast<T*>(p);
+    p += b; left -= b;
+    return r;
+  }
+};
+
+}  // namespace nlb
+
+using namespace nlb;
+
+extern "C" {
+
+const char* nlb_last_error(void) { return g_err; }
+int nlb_version(void) { return 100; }
+
+size_t nlb_knn_index_bytes(int64_t M) { return knn_index_bytes(M); }
+
+int nlb_knn_build(const float* p2, int64_t M, void* index, size_t index_bytes, void* stream) {
+  if (!p2 || !index) return set_error("nlb_knn_build: NULL pointer");
+  return knn_build(p2, M, index, index_bytes, (cudaStream_t)stream);
+}
+
+int nlb_knn_query(const void* index, const float* p1, int64_t N, int K, int64_t* idx, float* dist2, void* stream) {
+  if (!index || (N > 0 && (!p1 || !idx || !dist2))) return set_error("nlb_knn_query: NULL pointer");
+  return knn_query(index, p1, N, K, idx, nullptr, dist2, (cudaStream_t)stream);
+}
+
+int nlb_render_param_count(void) { return 100; }
+size_t nlb_render_weights_floats(int S) { return render_weights_floats(S); }
+
+int nlb_render_pack_weights(const float* const* params, int n_params, int S, float* packed, size_t packed_floats,
+                            void* stream) {
+  if (!params || !packed) return set_error("nlb_render_pack_weights: NULL pointer");
+  return render_weights_pack(params, n_params, S, packed, packed_floats, (cudaStream_t)stream);
+}
+
+int nlb_support_prepare(const float* packed_weights, int S, const float* xyz, const float* feature,
+                        const float* confidence, const float* direction, int64_t M, float* sup_pre, float* sup_geo,
+                        void* stream) {
+  if (!packed_weights || !xyz || !feature || !confidence || !direction || !sup_pre || !sup_geo)
+    return set_error("nlb_support_prepare: NULL pointer");
+  const RenderW w = render_weights_view(packed_weights, S);
+  if (launch_linear(feature, M, C_RGBF, C_RGBF, w.w1a, w.b1, W_HID, 0, sup_pre, W_HID, (cudaStream_t)stream)) return 1;
+  return launch_sup_geo(xyz, direction, confidence, M, sup_geo, (cudaStream_t)stream);
+}
+
+size_t nlb_query_scratch_bytes(int64_t N, int K) {
+  if (N < 1) N = 1;
+  return align256((size_t)N * K * 4) + align256((size_t)N * K * 4) + align256((size_t)N * W_HID * 4) + 1024;
+}
+
+int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S, const float* xyz,
+                     const float* direction, int64_t N, int K, float* feature_agg, float* feature, float* weights,
+                     float* mv_feature, float* mv_visibility, float* aggregated, int32_t* knn_idx, float* knn_d2,
+                     void* scratch, size_t scratch_bytes, void* stream) {
+  if (check_scene(scene)) return 1;
+  if (N <= 0) return 0;
+  if (!packed_weights || !xyz || !feature_agg) return set_error("nlb_query_points: NULL pointer");
+  if (K != 1 && K != 2 && K != 4 && K != 8) return set_error("nlb_query_points: K must be 1, 2, 4 or 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  Carver c{(char*)scratch, scratch_bytes};
+  int* idx = knn_idx ? knn_idx : c.take<int>((size_t)N * K);
+  float* d2 = knn_d2 ? knn_d2 : c.take<float>((size_t)N * K);
+  float* agg = aggregated ? aggregated : c.take<float>((size_t)N * W_HID);
+  if (!c.ok) return set_error("nlb_query_points: scratch too small (see nlb_query_scratch_bytes)");
+  const SceneDev sc = to_dev(scene);
+  const RenderW w = render_weights_view(packed_weights, S);
+  PointSrc ps{xyz, direction, nullptr, nullptr, nullptr, 1};
+  if (knn_query(sc.knn, xyz, N, K, nullptr, idx, d2, st)) return 1;
+  if (launch_aggregate(sc, w, ps, N, 0, agg, nullptr, nullptr, nullptr, mv_feature, mv_visibility, st)) return 1;
+  return launch_neighbor(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, st);
+}
+
+int nlb_aggregate_points(const nlb_scene* scene, const float* packed_weights, int S, const float* xyz, int64_t N,
+                         float* aggregated, float* mv_feature, float* mv_visibility, void* stream) {
+  if (check_scene(scene, false)) return 1;
+  if (N <= 0) return 0;
+  if (!packed_weights || !xyz || !aggregated) return set_error("nlb_aggregate_points: NULL pointer");
+  const SceneDev sc = to_dev(scene);
+  const RenderW w = render_weights_view(packed_weights, S);
+  PointSrc ps{xyz, nullptr, nullptr, nullptr, nullptr, 1};
+  return launch_aggregate(sc, w, ps, N, 0, aggregated, nullptr, nullptr, nullptr, mv_feature, mv_visibility,
+                          (cudaStream_t)stream);
+}
+
+int nlb_descriptor_head(const float* packed_weights, int S, int level, const float* x, int64_t N, float* out,
+                        void* stream) {
+  if (!packed_weights || !x || !out) return set_error("nlb_descriptor_head: NULL pointer");
+  const RenderW w = render_weights_view(packed_weights, S);
+  return launch_linear(x, N, 323, 323, level == 0 ? w.pj_c : w.pj_f, level == 0 ? w.pj_c_b : w.pj_f_b, 192, 0, out, 192,
+                       (cudaStream_t)stream);
+}
+
+int nlb_confidence_head(const float* packed_weights, int S, const float* aggregated, int64_t N, float* conf,
+                        float* scratch, void* stream) {
+  if (!packed_weights || !aggregated || !conf || !scratch) return set_error("nlb_confidence_head: NULL pointer");
+  const RenderW w = render_weights_view(packed_weights, S);
+  if (launch_linear(aggregated, N, W_HID, W_HID, w.cf1, w.cf1_b, 64, 1, scratch, 64, (cudaStream_t)stream)) return 1;
+  return launch_rowdot_sigmoid(scratch, N, 64, w.cf2, w.cf2_b, conf, (cudaStream_t)stream);
+}
+
+size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
+  const size_t n = (size_t)(chunk_rays < 1 ? 1 : chunk_rays) * S;
+  return align256(n * KNN_K * 4) * 2 + align256(n * W_HID * 4) * 2 + align256(n * V * 32 * 4) + align256(n * V * 16) +
+         align256(n) + 2048;
+}
+
+int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays) {
+  if (R <= 0) return 0;
+  if (chunk_rays < 1) chunk_rays = R;
+  return 4 * ((R + chunk_rays - 1) / chunk_rays);
+}
+
+int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
+                    const float* rays_d, const float* z_vals, int64_t R, int white_bkgd, int64_t chunk_rays,
+                    float* rgb, float* depth, float* weights, uint8_t* mask, float* depth_uncertainty, float* feat,
+                    float* dbg_feature_agg, float* dbg_sigma, void* scratch, size_t scratch_bytes, void* stream) {
+  if (check_scene(scene)) return 1;
+  if (R <= 0) return 0;
+  if (!packed_weights || !rays_o || !rays_d || !z_vals || !rgb || !depth || !weights || !mask || !depth_uncertainty)
+    return set_error("nlb_render_rays: NULL pointer");
+  if (S % 8 != 0 || S < 8 || S > 128) return set_error("nlb_render_rays: S must be a multiple of 8 in [8, 128]");
+  if (chunk_rays < 1) chunk_rays = R;
+  if (chunk_rays > R) chunk_rays = R;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int V = scene->V;
+  const size_t n = (size_t)chunk_rays * S;
+  Carver c{(char*)scratch, scratch_bytes};
+  int* idx = c.take<int>(n * KNN_K);
+  float* d2 = c.take<float>(n * KNN_K);
+  float* agg = c.take<float>(n * W_HID);
+  float* fagg = c.take<float>(n * W_HID);
+  float* partial = c.take<float>(n * V * 32);
+  float* rgbvis = c.take<float>(n * V * 4);
+  unsigned char* nvalid = c.take<unsigned char>(n);
+  if (!c.ok) return set_error("nlb_render_rays: scratch too small (see nlb_render_scratch_bytes)");
+  const SceneDev sc = to_dev(scene);
+  const RenderW w = render_weights_view(packed_weights, S);
+  for (int64_t r0 = 0; r0 < R; r0 += chunk_rays) {
+    const int64_t rc = (R - r0) < chunk_rays ? (R - r0) : chunk_rays;
+    const int64_t nc = rc * S;
+    const float* ro = rays_o + r0 * 3;
+    const float* rd = rays_d + r0 * 3;
+    PointSrc ps{nullptr, nullptr, ro, rd, z_vals, S};
+    float* fa = dbg_feature_agg ? dbg_feature_agg + r0 * S * W_HID : fagg;
+    if (knn_query_rays(sc.knn, ro, rd, z_vals, rc, S, idx, d2, st)) return 1;
+    if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, st)) return 1;
+    if (launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)) return 1;
+    if (launch_ray(sc, w, z_vals, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
+                   weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
+                   dbg_sigma ? dbg_sigma + r0 * S : nullptr, st))
+      return 1;
+  }
+  return 0;
+}
+
+size_t nlb_match_weights_floats(int C) { return match_weights_floats(C); }
+
+int nlb_match_pack_weights(const float* const* params, int n_params, int C, float* packed, size_t packed_floats,
+                           void* stream) {
+  if (!params || !packed) return set_error("nlb_match_pack_weights: NULL pointer");
+  return match_weights_pack(params, n_params, C, packed, packed_floats, (cudaStream_t)stream);
+}
+
+int nlb_s2d_scores(const float* packed, int C, const float* desc0, const float* desc1, int64_t N, int64_t M,
+                   float* score, void* stream) {
+  if (N <= 0 || M <= 0) return set_error("nlb_s2d_scores: both descriptor sets must be non-empty (sparse_to_dense.py:123)");
+  if (!packed || !desc0 || !desc1 || !score) return set_error("nlb_s2d_scores: NULL pointer");
+  return launch_s2d(match_weights_view(packed, C), desc0, desc1, N, M, score, (cudaStream_t)stream);
+}
+
+size_t nlb_mutual_scratch_bytes(int64_t N, int64_t M) {
+  return align256((size_t)(N < 1 ? 1 : N) * 8) + align256((size_t)(M < 1 ? 1 : M) * 4) + 1024;
+}
+
+int nlb_mutual_matches(const float* score, int64_t N, int64_t M, float thr, int64_t* i_ids, int64_t* j_ids,
+                       int32_t* count, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!score || !i_ids || !j_ids || !count || !scratch) return set_error("nlb_mutual_matches: NULL pointer");
+  if (N <= 0 || M <= 0) return set_error("nlb_mutual_matches: empty score matrix");
+  if (scratch_bytes < nlb_mutual_scratch_bytes(N, M)) return set_error("nlb_mutual_matches: scratch too small");
+  return launch_mutual(score, N, M, thr, i_ids, j_ids, count, scratch, (cudaStream_t)stream);
+}
+
+int nlb_fine_windows(const float* packed, int C, const float* feat_fine, int h, int w, int stride, int coarse_w,
+                     const int64_t* j_ids, int64_t Mm, float* out, void* stream) {
+  if (Mm <= 0) return 0;
+  if (!packed || !feat_fine || !j_ids || !out) return set_error("nlb_fine_windows: NULL pointer");
+  return launch_fine_windows(match_weights_view(packed, C), feat_fine, h, w, C, stride, coarse_w, j_ids, Mm, out,
+                             (cudaStream_t)stream);
+}
+
+int nlb_fine_match(const float* packed, int C, const float* f0, const float* f1, int64_t Mm, const float* mkps2d_c,
+                   float* expec_f, float* mkps2d_f, void* stream) {
+  if (Mm <= 0) return 0;
+  if (!packed || !f0 || !f1 || !mkps2d_c || !expec_f || !mkps2d_f) return set_error("nlb_fine_match: NULL pointer");
+  return launch_fine_match(match_weights_view(packed, C), f0, f1, Mm, mkps2d_c, expec_f, mkps2d_f, (cudaStream_t)stream);
+}
+
+}  // extern "C"

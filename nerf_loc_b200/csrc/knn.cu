@@ -1,0 +1,404 @@
+// Exact K-nearest-neighbour search over the support neural points (sm_100a).
+//
+// Replaces the reference's brute-force KNN (nerf_loc/models/ops/knn/src/knn.cu:131-241, the vendored pytorch3d
+// kernels selected for D=3, K=8 / K=1 at conditional_nerf/model.py:289,318,377) with an exact search over a
+// bounding-volume hierarchy that is rebuilt once per frame:
+//   * support points are sorted along a 30-bit Morton curve (cub radix sort, per-frame setup);
+//   * leaves hold LEAF consecutive sorted points, inner levels group FAN consecutive children; every node
+//     stores its AABB as two float4;
+//   * one thread per query walks the tree with a small stack, nearest child first, pruning a node only when
+//     its box distance is STRICTLY larger than the current K-th distance.
+// Results are identical to the reference definition: the K smallest squared distances by (distance, index),
+// ascending, with the squared distance accumulated as ((dx*dx + dy*dy) + dz*dz) with one rounding per
+// operation (no FMA), exactly like knn_cpu.cpp:43-47.  The box distance is evaluated with the same operation
+// order, so by monotonicity of rounding it is a true lower bound of every contained point's distance and the
+// pruning is exact, ties included.
+#include <cub/cub.cuh>
+#include <float.h>
+#include "nlb_internal.h"
+
+namespace nlb {
+
+constexpr int LEAF = 8;
+constexpr int FAN = 8;
+
+// ---- index layout inside the caller-provided buffer -------------------------------------------------------
+// header (KnnHeader) | sorted points float4[M] (xyz, original index bits) | level 0 boxes | level 1 boxes ...
+struct KnnHeader {
+  int64_t M;
+  int n_levels;
+  int level_count[12];
+  int64_t level_off[12];  // float4 offsets (2 float4 per box) from the start of the box area
+  int64_t pts_off;        // byte offsets from buffer start
+  int64_t box_off;
+  int64_t keys_off, vals_off, keys2_off, vals2_off, bbox_off, cub_off;
+  int64_t cub_bytes;
+  int64_t total_bytes;
+};
+
+static void knn_layout(int64_t M, KnnHeader& h) {
+  h.M = M;
+  int64_t n = (M + LEAF - 1) / LEAF;
+  int L = 0;
+  int64_t boxes = 0;
+  while (true) {
+    h.level_count[L] = (int)n;
+    h.level_off[L] = boxes * 2;
+    boxes += n;
+    ++L;
+    if (n <= FAN || L >= 12) break;
+    n = (n + FAN - 1) / FAN;
+  }
+  h.n_levels = L;
+  auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
+  int64_t o = align(sizeof(KnnHeader));
+  h.pts_off = o; o = align(o + M * 16);
+  h.box_off = o; o = align(o + boxes * 32);
+  h.keys_off = o; o = align(o + M * 4);
+  h.vals_off = o; o = align(o + M * 4);
+  h.keys2_off = o; o = align(o + M * 4);
+  h.vals2_off = o; o = align(o + M * 4);
+  h.bbox_off = o; o = align(o + 64);
+  size_t cub_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)M, 0, 30);
+  h.cub_off = o; h.cub_bytes = (int64_t)cub_bytes; o = align(o + cub_bytes);
+  h.total_bytes = o;
+}
+
+size_t knn_index_bytes(int64_t M) {
+  KnnHeader h;
+  knn_layout(M < 1 ? 1 : M, h);
+  return (size_t)h.total_bytes;
+}
+
+// ---- build kernels ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned f2ord(float f) {
+  unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void knn_bbox_init(unsigned* bb) {
+  if (threadIdx.x < 3) bb[threadIdx.x] = 0xffffffffu;
+  else if (threadIdx.x < 6) bb[threadIdx.x] = 0u;
+}
+
+__global__ void knn_bbox_kernel(const float* __restrict__ xyz, int64_t M, unsigned* bb) {
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float v = xyz[i * 3 + c];
+      lo[c] = fminf(lo[c], v);
+      hi[c] = fmaxf(hi[c], v);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+      hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(&bb[c], f2ord(lo[c]));
+      atomicMax(&bb[3 + c], f2ord(hi[c]));
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned spread3(unsigned v) {
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void knn_morton_kernel(const float* __restrict__ xyz, int64_t M, const unsigned* __restrict__ bb,
+                                  uint32_t* keys, uint32_t* vals) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  unsigned q[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float lo = ord2f(bb[c]), hi = ord2f(bb[3 + c]);
+    float e = fmaxf(hi - lo, 1e-20f);
+    float t = (xyz[i * 3 + c] - lo) / e * 1023.f;
+    t = fminf(fmaxf(t, 0.f), 1023.f);
+    q[c] = (unsigned)t;
+  }
+  keys[i] = (spread3(q[0]) << 2) | (spread3(q[1]) << 1) | spread3(q[2]);
+  vals[i] = (uint32_t)i;
+}
+
+__global__ void knn_gather_kernel(const float* __restrict__ xyz, int64_t M, const uint32_t* __restrict__ order,
+                                  float4* pts) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  uint32_t j = order[i];
+  pts[i] = make_float4(xyz[(int64_t)j * 3], xyz[(int64_t)j * 3 + 1], xyz[(int64_t)j * 3 + 2], __uint_as_float(j));
+}
+
+__global__ void knn_leaf_boxes(const float4* __restrict__ pts, int64_t M, float4* boxes, int n) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int k = 0; k < LEAF; ++k) {
+    int64_t i = (int64_t)b * LEAF + k;
+    if (i >= M) break;
+    float4 p = pts[i];
+    lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+    lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+    lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+  }
+  boxes[2 * b] = make_float4(lo[0], lo[1], lo[2], 0.f);
+  boxes[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+}
+
+__global__ void knn_inner_boxes(const float4* __restrict__ child, int n_child, float4* boxes, int n) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n) return;
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int k = 0; k < FAN; ++k) {
+    int c = b * FAN + k;
+    if (c >= n_child) break;
+    float4 a = child[2 * c], z = child[2 * c + 1];
+    lo[0] = fminf(lo[0], a.x); lo[1] = fminf(lo[1], a.y); lo[2] = fminf(lo[2], a.z);
+    hi[0] = fmaxf(hi[0], z.x); hi[1] = fmaxf(hi[1], z.y); hi[2] = fmaxf(hi[2], z.z);
+  }
+  boxes[2 * b] = make_float4(lo[0], lo[1], lo[2], 0.f);
+  boxes[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+}
+
+int knn_build(const float* xyz, int64_t M, void* buf, size_t bytes, cudaStream_t st) {
+  if (M < 1) return set_error("knn_build: empty support set");
+  if (M >= (1ll << 31)) return set_error("knn_build: too many points");
+  KnnHeader h;
+  knn_layout(M, h);
+  if (bytes < (size_t)h.total_bytes) return set_error("knn_build: index buffer too small");
+  char* base = (char*)buf;
+  unsigned* bb = (unsigned*)(base + h.bbox_off);
+  uint32_t* keys = (uint32_t*)(base + h.keys_off);
+  uint32_t* vals = (uint32_t*)(base + h.vals_off);
+  uint32_t* keys2 = (uint32_t*)(base + h.keys2_off);
+  uint32_t* vals2 = (uint32_t*)(base + h.vals2_off);
+  float4* pts = (float4*)(base + h.pts_off);
+  float4* boxes = (float4*)(base + h.box_off);
+  const int T = 256;
+  const int G = (int)((M + T - 1) / T);
+  knn_bbox_init<<<1, 32, 0, st>>>(bb);
+  knn_bbox_kernel<<<G < 592 ? G : 592, T, 0, st>>>(xyz, M, bb);
+  knn_morton_kernel<<<G, T, 0, st>>>(xyz, M, bb, keys, vals);
+  size_t cub_bytes = (size_t)h.cub_bytes;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(base + h.cub_off, cub_bytes, keys, keys2, vals, vals2, (int)M, 0, 30, st);
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  knn_gather_kernel<<<G, T, 0, st>>>(xyz, M, vals2, pts);
+  knn_leaf_boxes<<<(h.level_count[0] + T - 1) / T, T, 0, st>>>(pts, M, boxes + h.level_off[0], h.level_count[0]);
+  for (int l = 1; l < h.n_levels; ++l)
+    knn_inner_boxes<<<(h.level_count[l] + T - 1) / T, T, 0, st>>>(boxes + h.level_off[l - 1], h.level_count[l - 1],
+                                                               boxes + h.level_off[l], h.level_count[l]);
+  e = cudaMemcpyAsync(buf, &h, sizeof(h), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  // the header is read back from pageable host memory: make sure the copy has consumed it
+  e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  return 0;
+}
+
+// ---- query -------------------------------------------------------------------------------------------------
+struct KnnTree {
+  const float4* pts;
+  const float4* boxes;
+  int64_t M;
+  int n_levels;
+  int level_count[12];
+  int64_t level_off[12];
+};
+
+__device__ __forceinline__ float d2_exact(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = __fsub_rn(ax, bx), dy = __fsub_rn(ay, by), dz = __fsub_rn(az, bz);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+__device__ __forceinline__ float box_d2(float qx, float qy, float qz, float4 lo, float4 hi) {
+  // per-axis gap, written so that for a point on the face the value equals |q - p| bit for bit
+  const float dx = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.f);
+  const float dy = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
+  const float dz = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
+  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+template <int K>
+struct TopK {
+  float d[K];
+  int id[K];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int i = 0; i < K; ++i) { d[i] = FLT_MAX; id[i] = 0x7fffffff; }
+  }
+  __device__ __forceinline__ float worst() const { return d[K - 1]; }
+  // keep ascending by (dist, index)
+  __device__ __forceinline__ void push(float dist, int idx) {
+    if (!(dist < d[K - 1] || (dist == d[K - 1] && idx < id[K - 1]))) return;
+    d[K - 1] = dist; id[K - 1] = idx;
+#pragma unroll
+    for (int i = K - 1; i > 0; --i) {
+      const bool sw = d[i] < d[i - 1] || (d[i] == d[i - 1] && id[i] < id[i - 1]);
+      if (sw) {
+        float td = d[i]; d[i] = d[i - 1]; d[i - 1] = td;
+        int ti = id[i]; id[i] = id[i - 1]; id[i - 1] = ti;
+      }
+    }
+  }
+};
+
+template <int K>
+__device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy, float qz, TopK<K>& best) {
+  constexpr int STACK = 12 * FAN;
+  unsigned stk_node[STACK];
+  float stk_d[STACK];
+  int sp = 0;
+  const int top = t.n_levels - 1;
+  // push the top level (<= FAN nodes unless the level cap was hit), farthest first
+  for (int n = t.level_count[top] - 1; n >= 0; --n) {
+    const float4 lo = t.boxes[t.level_off[top] + 2 * n], hi = t.boxes[t.level_off[top] + 2 * n + 1];
+    if (sp < STACK) { stk_node[sp] = ((unsigned)top << 28) | (unsigned)n; stk_d[sp] = box_d2(qx, qy, qz, lo, hi); ++sp; }
+  }
+  while (sp > 0) {
+    --sp;
+    const float nd = stk_d[sp];
+    if (nd > best.worst()) continue;  // strict: equal distance may still hide a smaller index
+    const unsigned code = stk_node[sp];
+    const int lvl = code >> 28;
+    const int node = code & 0x0fffffffu;
+    if (lvl == 0) {
+      const int64_t p0 = (int64_t)node * LEAF;
+#pragma unroll
+      for (int k = 0; k < LEAF; ++k) {
+        if (p0 + k < t.M) {
+          const float4 p = t.pts[p0 + k];
+          best.push(d2_exact(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+        }
+      }
+    } else {
+      const int cl = lvl - 1;
+      const int c0 = node * FAN;
+      const int nc = min(FAN, t.level_count[cl] - c0);
+      float cd[FAN];
+      int nearest = -1;
+      float nearest_d = FLT_MAX;
+#pragma unroll
+      for (int k = 0; k < FAN; ++k) {
+        cd[k] = FLT_MAX;
+        if (k < nc) {
+          const float4 lo = t.boxes[t.level_off[cl] + 2 * (c0 + k)], hi = t.boxes[t.level_off[cl] + 2 * (c0 + k) + 1];
+          cd[k] = box_d2(qx, qy, qz, lo, hi);
+          if (cd[k] < nearest_d) { nearest_d = cd[k]; nearest = k; }
+        }
+      }
+      const float w = best.worst();
+#pragma unroll
+      for (int k = 0; k < FAN; ++k) {
+        if (k < nc && k != nearest && cd[k] <= w && sp < STACK) {
+          stk_node[sp] = ((unsigned)cl << 28) | (unsigned)(c0 + k); stk_d[sp] = cd[k]; ++sp;
+        }
+      }
+      if (nearest >= 0 && nearest_d <= w && sp < STACK) {
+        stk_node[sp] = ((unsigned)cl << 28) | (unsigned)(c0 + nearest); stk_d[sp] = nearest_d; ++sp;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ KnnTree load_tree(const void* index) {
+  const KnnHeader* h = (const KnnHeader*)index;
+  KnnTree t;
+  t.M = h->M;
+  t.n_levels = h->n_levels;
+  t.pts = (const float4*)((const char*)index + h->pts_off);
+  t.boxes = (const float4*)((const char*)index + h->box_off);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { t.level_count[i] = h->level_count[i]; t.level_off[i] = h->level_off[i]; }
+  return t;
+}
+
+// Generic query: p1 [N,3] -> idx (int64 [N,K]) and/or idx32 (int32 [N,K]), dist2 [N,K].
+template <int K>
+__global__ void __launch_bounds__(128) knn_query_kernel(const void* __restrict__ index, const float* __restrict__ p1, int64_t N,
+                                                        int64_t* idx64, int* idx32, float* dist2) {
+  __shared__ KnnTree tree;
+  if (threadIdx.x == 0) tree = load_tree(index);
+  __syncthreads();
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float qx = p1[i * 3], qy = p1[i * 3 + 1], qz = p1[i * 3 + 2];
+  TopK<K> best;
+  best.init();
+  knn_search<K>(tree, qx, qy, qz, best);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const bool ok = best.id[k] != 0x7fffffff;  // fewer than K support points: pad with zeros like the reference
+    if (idx64) idx64[i * K + k] = ok ? best.id[k] : 0;
+    if (idx32) idx32[i * K + k] = ok ? best.id[k] : 0;
+    if (dist2) dist2[i * K + k] = ok ? best.d[k] : 0.f;
+  }
+}
+
+// Ray-sample query used by the render path: sample n = r*S + s sits at o_r + d_r * z_s, computed with the
+// reference's operation order (one rounding per multiply/add, conditional_nerf/model.py:498).
+template <int K>
+__global__ void __launch_bounds__(128) knn_query_rays_kernel(const void* __restrict__ index, const float* __restrict__ rays_o,
+                                                             const float* __restrict__ rays_d, const float* __restrict__ z_vals,
+                                                             int64_t R, int S, int* idx32, float* dist2) {
+  __shared__ KnnTree tree;
+  if (threadIdx.x == 0) tree = load_tree(index);
+  __syncthreads();
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= R * S) return;
+  const int64_t r = i / S;
+  const int s = (int)(i - r * S);
+  const float z = z_vals[s];
+  const float qx = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(rays_d[r * 3 + 0], z));
+  const float qy = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(rays_d[r * 3 + 1], z));
+  const float qz = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(rays_d[r * 3 + 2], z));
+  TopK<K> best;
+  best.init();
+  knn_search<K>(tree, qx, qy, qz, best);
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const bool ok = best.id[k] != 0x7fffffff;
+    idx32[i * K + k] = ok ? best.id[k] : 0;
+    dist2[i * K + k] = ok ? best.d[k] : 0.f;
+  }
+}
+
+int knn_query(const void* index, const float* p1, int64_t N, int K, int64_t* idx64, int* idx32, float* dist2,
+              cudaStream_t st) {
+  if (N <= 0) return 0;
+  const int T = 128;
+  const unsigned G = (unsigned)((N + T - 1) / T);
+  switch (K) {
+    case 1: knn_query_kernel<1><<<G, T, 0, st>>>(index, p1, N, idx64, idx32, dist2); break;
+    case 2: knn_query_kernel<2><<<G, T, 0, st>>>(index, p1, N, idx64, idx32, dist2); break;
+    case 4: knn_query_kernel<4><<<G, T, 0, st>>>(index, p1, N, idx64, idx32, dist2); break;
+    case 8: knn_query_kernel<8><<<G, T, 0, st>>>(index, p1, N, idx64, idx32, dist2); break;
+    case 16: knn_query_kernel<16><<<G, T, 0, st>>>(index, p1, N, idx64, idx32, dist2); break;
+    default: return set_error("knn_query: K must be one of 1,2,4,8,16");
+  }
+  return check_launch("knn_query");
+}
+
+int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, int64_t R, int S,
+                   int* idx32, float* dist2, cudaStream_t st) {
+  const int64_t N = R * S;
+  if (N <= 0) return 0;
+  const int T = 128;
+  knn_query_rays_kernel<8><<<(unsigned)((N + T - 1) / T), T, 0, st>>>(index, rays_o, rays_d, z_vals, R, S, idx32, dist2);
+  return check_launch("knn_query_rays");
+}
+
+}  // namespace nlb

@@ -1,0 +1,8 @@
+// Single translation unit of libnerfloc_b200.so: the kernels share __global__ helpers (pack kernels) and inline
+// device code, so they are compiled together instead of with relocatable device code.
+#include "pack.cu"
+#include "knn.cu"
+#include "render_point.cu"
+#include "render_ray.cu"
+#include "match.cu"
+#include "cabi.cu"

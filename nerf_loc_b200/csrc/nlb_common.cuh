@@ -1,0 +1,199 @@
+// Shared device helpers for the NeRF-Loc B200 kernels (sm_100a).
+//
+// Everything on the render path is a chain of small dense layers whose activations never leave shared
+// memory.  The workhorse is `tile_gemm`: C[rows x COLS] = A[rows x K] * Wt[K x COLS] where
+//   * A lives in shared memory, row-major with a padded leading dimension (ld % 32 == 4 keeps the float4
+//     fragment loads conflict free), optionally addressed through conv "taps" (row shift per K-block) so a
+//     Conv1d / ConvTranspose1d along the ray is the same code path as a Linear layer;
+//   * Wt is the pre-transposed, zero-padded weight in global memory (L2 resident, packed once per model by
+//     pack.cu) and is streamed through a double-buffered cp.async staging ring;
+//   * accumulation is fp32 FFMA with a TM x TN register micro-tile per thread (MMA mode "fp32-FFMA" in
+//     the parity bar of 1e-4 rules out single-pass bf16/tf32 operands).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nlb {
+
+constexpr int NT = 256;  // threads per CTA for all tile kernels
+constexpr int KT = 32;   // K-tile of the weight staging ring
+constexpr int STAGE_FLOATS = 2 * KT * 128;  // two stages of [KT][<=128]
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
+__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expm1f(x); }
+__device__ __forceinline__ float softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Block-wide sum over NT threads; `red` is >= 8 floats of shared scratch.  All threads get the result.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < NT / 32; ++i) t += red[i];
+  return t;
+}
+
+// A-operand addressing.  For K-tile kt (KT consecutive k) the fragment of logical row r starts at
+//   base + (r + off[tap]) * ld + (kt*KT - tap*cin),  tap = (kt*KT) / cin.
+// A plain Linear layer has cin >= K and off[0] = 0.  cin must be a multiple of KT.
+struct ASrc {
+  const float* base;
+  int ld;
+  int cin;
+  int off0, off1, off2;
+};
+__device__ __forceinline__ ASrc plainA(const float* base, int ld) { return ASrc{base, ld, 1 << 30, 0, 0, 0}; }
+
+// Core of the tile GEMM: acc[TM][TN] (+)= A[r0.., :] * Wt for the calling thread's micro-tile.
+//   Wt: global, row k at Wt + k*ldb (column offset already applied by the caller), K % KT == 0.
+//   sB: shared staging, 2*KT*COLS floats.
+//   kscale (SCALE only): shared/global array of K factors; staged row k of Wt is multiplied by kscale[k] by the
+//   thread that copied it, i.e. the GEMM computes A * (diag(kscale) Wt) - the S2D "fold a_n into layer 1" form.
+template <int TM, int TN, int COLS, bool SCALE>
+__device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const bool active, const float* __restrict__ Wt,
+                                          const int ldb, const int K, float* sB, const float* kscale,
+                                          float (&acc)[TM][TN]) {
+  static_assert(TN % 4 == 0 && COLS % TN == 0, "bad tile");
+  constexpr int TC = COLS / TN;  // column groups
+  constexpr int NG = TN / 4;     // float4 column groups per thread
+  constexpr int GSTRIDE = COLS / NG;
+  static_assert(NT % TC == 0, "bad tile");
+  constexpr int CHUNKS = KT * COLS / 4;  // 16-byte chunks per stage
+  const int tid = threadIdx.x;
+  const int tc = tid % TC;
+  const int nkt = K / KT;
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  __syncthreads();  // previous users of sB (and producers of A) are done
+  for (int c = tid; c < CHUNKS; c += NT) {
+    const int k = c / (COLS / 4), n4 = c % (COLS / 4);
+    cp_async16(sB + k * COLS + n4 * 4, Wt + (size_t)k * ldb + n4 * 4);
+  }
+  cp_async_commit();
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    cp_async_wait<0>();
+    if (SCALE) {
+      float* cur = sB + (kt & 1) * (KT * COLS);
+      for (int c = tid; c < CHUNKS; c += NT) {
+        const int k = c / (COLS / 4), n4 = c % (COLS / 4);
+        const float sc = kscale[kt * KT + k];
+        float4* p = reinterpret_cast<float4*>(cur + k * COLS + n4 * 4);
+        float4 v = *p;
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        *p = v;
+      }
+    }
+    __syncthreads();
+    if (kt + 1 < nkt) {
+      float* dst = sB + ((kt + 1) & 1) * (KT * COLS);
+      const float* src = Wt + (size_t)(kt + 1) * KT * ldb;
+      for (int c = tid; c < CHUNKS; c += NT) {
+        const int k = c / (COLS / 4), n4 = c % (COLS / 4);
+        cp_async16(dst + k * COLS + n4 * 4, src + (size_t)k * ldb + n4 * 4);
+      }
+      cp_async_commit();
+    }
+    if (active) {
+      const int k0 = kt * KT;
+      const int tap = k0 / A.cin;
+      const int roff = tap == 0 ? A.off0 : (tap == 1 ? A.off1 : A.off2);
+      const float* arow = A.base + (r0 + roff) * A.ld + (k0 - tap * A.cin);
+      const float* bt = sB + (kt & 1) * (KT * COLS) + tc * 4;
+#pragma unroll
+      for (int kk = 0; kk < KT; kk += 4) {
+        float4 a[TM];
+#pragma unroll
+        for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(arow + i * A.ld + kk);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          float b[TN];
+#pragma unroll
+          for (int g = 0; g < NG; ++g) {
+            const float4 bv = *reinterpret_cast<const float4*>(bt + (kk + k4) * COLS + g * GSTRIDE);
+            b[g * 4 + 0] = bv.x; b[g * 4 + 1] = bv.y; b[g * 4 + 2] = bv.z; b[g * 4 + 3] = bv.w;
+          }
+#pragma unroll
+          for (int i = 0; i < TM; ++i) {
+            const float av = k4 == 0 ? a[i].x : (k4 == 1 ? a[i].y : (k4 == 2 ? a[i].z : a[i].w));
+#pragma unroll
+            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av, b[j], acc[i][j]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// C = A * Wt (+ epilogue).  rows: runtime; threads whose rows fall outside are idle but still help staging.
+//   epi(row, col, value) is called once per output element by its owning thread.
+// If SYNC_BEFORE_EPI, a __syncthreads() separates the last A read from the first epilogue write (in-place use).
+template <int TM, int TN, int COLS, bool SYNC_BEFORE_EPI, class Epi>
+__device__ __forceinline__ void tile_gemm(const ASrc A, const int rows, const float* __restrict__ Wt, const int ldb,
+                                          const int K, float* sB, Epi epi) {
+  constexpr int TC = COLS / TN;
+  constexpr int TR = NT / TC;  // row groups per pass
+  constexpr int NG = TN / 4;
+  constexpr int GSTRIDE = COLS / NG;
+  const int tc = threadIdx.x % TC, tr = threadIdx.x / TC;
+  for (int rb = 0; rb < rows; rb += TR * TM) {
+    const int r0 = rb + tr * TM;
+    const bool active = r0 < rows;
+    float acc[TM][TN];
+    gemm_core<TM, TN, COLS, false>(A, r0, active, Wt, ldb, K, sB, nullptr, acc);
+    if (SYNC_BEFORE_EPI) __syncthreads();
+    if (active) {
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int g = 0; g < NG; ++g)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) epi(r0 + i, g * GSTRIDE + tc * 4 + j, acc[i][g * 4 + j]);
+    }
+  }
+}
+
+// Variant that leaves the accumulators with the caller (single pass: rows <= TR*TM).  Used where a LayerNorm
+// over the whole output slab, or a reduction over the columns, has to happen before anything is written.
+template <int TM, int TN, int COLS>
+struct Frag {
+  float acc[TM][TN];
+  int r0;
+  bool active;
+  static constexpr int TC = COLS / TN;
+  static constexpr int NG = TN / 4;
+  static constexpr int GSTRIDE = COLS / NG;
+  __device__ __forceinline__ int col(int j) const { return (j / 4) * GSTRIDE + (threadIdx.x % TC) * 4 + (j % 4); }
+};
+
+template <int TM, int TN, int COLS, bool SCALE = false>
+__device__ __forceinline__ void tile_gemm_frag(const ASrc A, const int rows, const float* __restrict__ Wt, const int ldb,
+                                               const int K, float* sB, Frag<TM, TN, COLS>& f,
+                                               const float* kscale = nullptr) {
+  constexpr int TC = COLS / TN;
+  f.r0 = (threadIdx.x / TC) * TM;
+  f.active = f.r0 < rows;
+  gemm_core<TM, TN, COLS, SCALE>(A, f.r0, f.active, Wt, ldb, K, sB, kscale, f.acc);
+}
+
+}  // namespace nlb

@@ -1,0 +1,89 @@
+// Internal (C++) declarations shared by the translation units of libnerfloc_b200.so.
+// The public surface is include/nerfloc_b200.h; nothing here is exported.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace nlb {
+
+int set_error(const char* msg);           // records the message, returns a non-zero code
+int check_launch(const char* what);       // cudaGetLastError() -> set_error
+
+// ---- exact KNN (knn.cu) ------------------------------------------------------------------------------------
+size_t knn_index_bytes(int64_t M);
+int knn_build(const float* xyz, int64_t M, void* buf, size_t bytes, cudaStream_t st);
+int knn_query(const void* index, const float* p1, int64_t N, int K, int64_t* idx64, int* idx32, float* dist2,
+              cudaStream_t st);
+int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, int64_t R, int S,
+                   int* idx32, float* dist2, cudaStream_t st);
+
+// ---- packed weights of the render path (pack.cu) ------------------------------------------------------------
+// All matrices are stored transposed ("Wt": row = input feature k, column = output feature n), zero padded so
+// that K is a multiple of 32, as the tile GEMM wants them.  Offsets are in floats from the buffer start.
+constexpr int C_FEAT = 192;   // backbone2d_fpn_dim
+constexpr int C_RGBF = 195;   // rgb + feature
+constexpr int W_HID = 128;    // model_3d_hidden_dim
+constexpr int C_VIS = 32;     // DepthFusionNet output channels
+constexpr int KNN_K = 8;
+
+struct UnetLayer {
+  const float* w;      // conv: [3*Cin][Cout]; transposed conv: even [Cin][Cout] followed by odd [2*Cin][Cout]
+  const float* b;      // [Cout]
+  const float* g;      // LayerNorm gain, transposed to [S_level][Cout]
+  const float* be;     // LayerNorm bias,  transposed to [S_level][Cout]
+};
+
+struct RenderW {
+  int S;  // samples per ray the RayUnet LayerNorms were built for (0: no RayUnet packed)
+  // aggregator (multiview_aggregator.py, visibility_decoder.py)
+  const float *dec1, *dec1_b;   // [32][128] (heads mean|var|aw|vis), [128]
+  const float *dec2, *dec2_b;   // 4 x [32][32], [128]
+  const float *dec3, *dec3_b;   // [6][32] natural (mean0,mean1,var0,var1,aw,vis), [6]
+  const float *fc1, *fc1_b;     // [416][64], [64]
+  const float *fc2, *fc2_b;     // [64][128], [128]
+  // colour blend (model.py:90-96)
+  const float *bl1v, *bl1_b;    // per-view part [224][32]: rows 0..194 rgb_feat, 195 vis, 196..199 ray_diff; bias [32]
+  const float *bl1a;            // feature_agg part [128][32]
+  const float *bl2, *bl2_b;     // [16][32] natural, [16]
+  const float *bl3, *bl3_b;     // [16], [1]
+  // neighbour MLP (model.py:36-39,63-77)
+  const float *w1a, *b1;        // [224][128] support-feature part of base_mlp.0 (+bias) -> per-frame precompute
+  const float *rd1, *rd1_b;     // [16][4] natural, [16]
+  const float *rd2, *rd2_b;     // [27][16] natural, [27]
+  const float *w1b;             // [96][128]: rows 0..62 PE, 63..89 ray_diff_fc
+  const float *w2, *b2, *w3, *b3;  // [128][128], [128]
+  const float *wq, *wk, *wv, *wfc; // wq^T, wk natural ([h*32+j][c]), wv^T, wfc^T; all [128][128]
+  const float *ln_g, *ln_b;     // [128]
+  // ray stage
+  UnetLayer u[7];               // conv1, conv2, conv3, trans_conv3, trans_conv2, trans_conv1, conv_out
+  const float *sig_w, *sig_b;   // [128], [1]
+  const float *ft1, *ft1_b;     // [128][128], [128]
+  const float *ft2, *ft2_b;     // [128][192], [192]
+  // per-frame setup / descriptor heads
+  const float *cf1, *cf1_b, *cf2, *cf2_b;   // confidence_mlp: [128][64], [64], [64], [1]
+  const float *pj_c, *pj_c_b, *pj_f, *pj_f_b;  // proj_layer_3d_*: [352][192] (rows 0..127 feature_agg, 128..322 feature), [192]
+};
+
+size_t render_weights_floats(int S);
+// params: host array of device pointers in the order of nerf_loc_b200/params.py::conditional_nerf_shapes(S)
+int render_weights_pack(const float* const* params, int n_params, int S, float* packed, size_t packed_floats,
+                        cudaStream_t st);
+RenderW render_weights_view(const float* packed, int S);
+
+// ---- scene (per-frame) -----------------------------------------------------------------------------------------
+struct SceneDev {
+  int V, H, W, h, w;
+  const float* images;   // [V][H][W][4]  rgb + pad
+  const float* feat;     // [V][h][w][192]
+  const float* vis;      // [V][h][w][32]
+  const float* cams;     // [V][32]: P=K_hom*w2c rows 0..2 (12) | K*Rt (12) | camera centre (3) | pad
+  float near_, far_;
+  int64_t M;             // support points
+  const float* sup_pre;  // [M][128]
+  const float* sup_geo;  // [M][8]: xyz, dir, conf, pad
+  const void* knn;       // KNN index
+  float qc[3];           // query camera centre (colour-blend ray_diff); unused by query()
+};
+
+}  // namespace nlb

@@ -1,0 +1,29 @@
+// Launchers of the render-path kernels (internal).
+#pragma once
+#include "nlb_internal.h"
+
+namespace nlb {
+
+// Where the sample points come from: an explicit list (query API) or rays x depth samples (render API).
+struct PointSrc {
+  const float* xyz;     // [N][3] or null
+  const float* dirs;    // [N][3] viewing direction per point, or null
+  const float* rays_o;  // [R][3]
+  const float* rays_d;  // [R][3]
+  const float* z;       // [S]
+  int S;
+};
+
+int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int with_blend, float* agg,
+                     float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, cudaStream_t st);
+int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
+                    const float* d2, const float* agg, float* fagg, float* feature, float* weights, cudaStream_t st);
+int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,
+                  float* out, int ldo, cudaStream_t st);
+int launch_sup_geo(const float* xyz, const float* dir, const float* conf, int64_t M, float* out, cudaStream_t st);
+int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t R, int S, int white_bkgd,
+               const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
+               float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
+               cudaStream_t st);
+
+}  // namespace nlb

@@ -1,0 +1,651 @@
+// Per-sample stage of the conditional-NeRF render / query path (sm_100a).
+//
+//   aggregate_kernel  - MultiviewFeatureAggregator.forward (conditional_nerf/multiview_aggregator.py:156-222):
+//                       two projections per (sample, view) (IBRNet convention ibrnet/ibrnet.py:169-231 and NeuRay
+//                       convention conditional_nerf/depth_fusion.py:78-147), bilinear fetches from the reference
+//                       views, the mixture-of-logistics visibility decoder (visibility_decoder.py:62-148),
+//                       visibility-weighted mean/variance over views and the 393->64->128 MLP.  It also emits the
+//                       per-view half of the colour-blend MLP's first layer (model.py:532-535), which is linear in
+//                       its concatenated input, so the 195-channel per-view features never leave the SM.
+//   neighbor_kernel   - the K=8 support-point MLP + attention of ConditionalNeRF.query (model.py:371-427).
+//
+// One CTA owns a tile of samples; activations stay in shared memory between layers (row-major, padded ld), weights
+// are streamed from L2 by nlb::tile_gemm.  Two exact algebraic rewrites are used (DESIGN.md "rewrites"):
+//   (1) base_mlp layer 1 is split into the support-feature part, precomputed once per frame per support point
+//       (sup_pre = W1[:, :195] f + b1), and the per-pair part (positional encoding + ray difference);
+//   (2) in base_mlp_attn the query is the same vector for all K positions (model.py:413-414), so the K and V
+//       projections are folded onto the query / context side and `feature` has one distinct row per sample.
+#include <float.h>
+#include "nlb_common.cuh"
+#include "nlb_internal.h"
+#include "render_kernels.h"
+
+namespace nlb {
+
+// ------------------------------------------------------------------------------------------------------------------
+// shared geometry helpers
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_point(const PointSrc& ps, int64_t n, float& x, float& y, float& z) {
+  if (ps.xyz) {
+    x = ps.xyz[n * 3]; y = ps.xyz[n * 3 + 1]; z = ps.xyz[n * 3 + 2];
+  } else {
+    // xyz = rays_o + rays_d * z, one rounding per op (model.py:498)
+    const int64_t r = n / ps.S;
+    const float t = ps.z[n - r * ps.S];
+    x = __fadd_rn(ps.rays_o[r * 3 + 0], __fmul_rn(ps.rays_d[r * 3 + 0], t));
+    y = __fadd_rn(ps.rays_o[r * 3 + 1], __fmul_rn(ps.rays_d[r * 3 + 1], t));
+    z = __fadd_rn(ps.rays_o[r * 3 + 2], __fmul_rn(ps.rays_d[r * 3 + 2], t));
+  }
+}
+
+struct Taps {  // bilinear footprint: 4 taps, weight 0 marks a skipped (out of range) tap
+  int x0, y0;
+  float w[4];  // nw, ne, sw, se
+};
+
+// torch grid_sample, bilinear.  `zeros`: padding_mode='zeros' (taps outside contribute nothing);
+// otherwise 'border' (coordinate clipped first).
+__device__ __forceinline__ Taps make_taps(float ix, float iy, int w, int h, bool zeros) {
+  if (!zeros) {
+    ix = fminf((float)(w - 1), fmaxf(ix, 0.f));
+    iy = fminf((float)(h - 1), fmaxf(iy, 0.f));
+  }
+  const float fx = floorf(ix), fy = floorf(iy);
+  Taps t;
+  // keep the int conversion well defined for far-away projections (weights are zero there anyway)
+  t.x0 = (int)fminf(fmaxf(fx, -2.f), (float)w);
+  t.y0 = (int)fminf(fmaxf(fy, -2.f), (float)h);
+  const float ex = (fx + 1.f) - ix, ey = (fy + 1.f) - iy;  // ix_se - ix, iy_se - iy
+  const float wx = ix - fx, wy = iy - fy;
+  t.w[0] = ex * ey; t.w[1] = wx * ey; t.w[2] = ex * wy; t.w[3] = wx * wy;
+  const bool inx0 = fx >= 0.f && fx <= (float)(w - 1), inx1 = fx + 1.f >= 0.f && fx + 1.f <= (float)(w - 1);
+  const bool iny0 = fy >= 0.f && fy <= (float)(h - 1), iny1 = fy + 1.f >= 0.f && fy + 1.f <= (float)(h - 1);
+  if (!(inx0 && iny0)) t.w[0] = 0.f;
+  if (!(inx1 && iny0)) t.w[1] = 0.f;
+  if (!(inx0 && iny1)) t.w[2] = 0.f;
+  if (!(inx1 && iny1)) t.w[3] = 0.f;
+  // NaN coordinates: every comparison above is false -> all weights zero
+  return t;
+}
+
+// row info slots
+enum { RI_FX = 0, RI_FY, RI_IX, RI_IY, RI_VX, RI_VY, RI_DEPTH, RI_VALID, RI_MASK, RI_VIS, RI_DD, RI_W, RI_N };
+
+constexpr int LDF = 228;   // rgb_feat rows: 195 + vis + ray_diff(4) + zero pad to 224 (+4)
+constexpr int LDH = 132;
+constexpr int LDX = 36;
+constexpr int LDG = 420;   // 393 -> 416 (+4)
+constexpr int TP_MAX = 16;
+
+constexpr int AGG_SMEM_FLOATS = STAGE_FLOATS + 128 * LDF + TP_MAX * LDG + TP_MAX * 68 + 128 * RI_N + 128 * 8 + TP_MAX * 4;
+
+__global__ void __launch_bounds__(NT, 1)
+aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int with_blend,
+                 float* __restrict__ agg_out, float* __restrict__ partial_out, float* __restrict__ rgbvis_out,
+                 unsigned char* __restrict__ nvalid_out, float* __restrict__ mvf_out, float* __restrict__ mvv_out) {
+  extern __shared__ __align__(16) float smem[];
+  float* sB = smem;
+  float* arena = sB + STAGE_FLOATS;
+  float* sG = arena + 128 * LDF;
+  float* sO1 = sG + TP_MAX * LDG;
+  float* sRI = sO1 + TP_MAX * 68;
+  float* sDec = sRI + 128 * RI_N;
+  float* sPt = sDec + 128 * 8;
+  float* sX = arena;               // [128][LDX]
+  float* sH = arena + 128 * LDX;   // [128][LDH]
+  float* sF = arena;               // [128][LDF] (after the decoder is done)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int V = sc.V;
+  const int TP = min(TP_MAX, 128 / V);
+  const int64_t n0 = (int64_t)blockIdx.x * TP;
+  const int np = (int)min((int64_t)TP, N - n0);
+  const int rows = np * V;
+  const float near_ = sc.near_, far_ = sc.far_;
+
+  // ---- phase 1: projections, one thread per (sample, view) row -----------------------------------------------
+  if (tid < 128) {
+    float* ri = sRI + tid * RI_N;
+    if (tid < rows) {
+      const int p = tid / V, v = tid - p * V;
+      float x, y, z;
+      load_point(ps, n0 + p, x, y, z);
+      if (v == 0) { sPt[p * 4] = x; sPt[p * 4 + 1] = y; sPt[p * 4 + 2] = z; }
+      const float* cam = sc.cams + v * 32;
+      // IBRNet convention
+      const float ph0 = fmaf(cam[2], z, fmaf(cam[1], y, cam[0] * x)) + cam[3];
+      const float ph1 = fmaf(cam[6], z, fmaf(cam[5], y, cam[4] * x)) + cam[7];
+      const float ph2 = fmaf(cam[10], z, fmaf(cam[9], y, cam[8] * x)) + cam[11];
+      const float zc = fmaxf(ph2, 1e-8f);
+      float px = ph0 / zc, py = ph1 / zc;
+      px = fminf(fmaxf(px, -1e6f), 1e6f);
+      py = fminf(fmaxf(py, -1e6f), 1e6f);
+      const bool inb = px <= (float)(sc.W - 1) && px >= 0.f && py <= (float)(sc.H - 1) && py >= 0.f;
+      ri[RI_MASK] = (inb && ph2 > 0.f) ? 1.f : 0.f;
+      const float gx = 2.f * px / (float)(sc.W - 1) - 1.f, gy = 2.f * py / (float)(sc.H - 1) - 1.f;
+      ri[RI_IX] = ((gx + 1.f) / 2.f) * (float)(sc.W - 1);
+      ri[RI_IY] = ((gy + 1.f) / 2.f) * (float)(sc.H - 1);
+      ri[RI_FX] = ((gx + 1.f) / 2.f) * (float)(sc.w - 1);
+      ri[RI_FY] = ((gy + 1.f) / 2.f) * (float)(sc.h - 1);
+      // NeuRay convention
+      const float* kr = cam + 12;
+      const float c0 = fmaf(kr[2], z, fmaf(kr[1], y, kr[0] * x)) + kr[3];
+      const float c1 = fmaf(kr[6], z, fmaf(kr[5], y, kr[4] * x)) + kr[7];
+      float dep = fmaf(kr[10], z, fmaf(kr[9], y, kr[8] * x)) + kr[11];
+      const bool bad = fabsf(dep) < 1e-4f;
+      if (bad) dep = 1e-3f;
+      const float qx = c0 / dep, qy = c1 / dep;
+      const bool outside = qx < -0.5f || qx >= (float)sc.W - 0.5f || qy < -0.5f || qy >= (float)sc.H - 0.5f;
+      ri[RI_VALID] = (!bad && !outside) ? 1.f : 0.f;
+      ri[RI_DEPTH] = dep;
+      const float xn = qx / (float)(sc.W - 1) * 2.f - 1.f, yn = qy / (float)(sc.H - 1) * 2.f - 1.f;
+      if (sc.h == sc.H && sc.w == sc.W) {  // align_corners=True only when the map has the image size
+        ri[RI_VX] = ((xn + 1.f) / 2.f) * (float)(sc.w - 1);
+        ri[RI_VY] = ((yn + 1.f) / 2.f) * (float)(sc.h - 1);
+      } else {
+        ri[RI_VX] = ((xn + 1.f) * (float)sc.w - 1.f) / 2.f;
+        ri[RI_VY] = ((yn + 1.f) * (float)sc.h - 1.f) / 2.f;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < RI_N; ++i) ri[i] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: 32-channel visibility features (border padding), one warp per row ------------------------------
+  for (int r = warp; r < 128; r += NT / 32) {
+    float val = 0.f;
+    if (r < rows) {
+      const float* ri = sRI + r * RI_N;
+      const int v = r % V;
+      const Taps t = make_taps(ri[RI_VX], ri[RI_VY], sc.w, sc.h, false);
+      const float* base = sc.vis + ((size_t)v * sc.h * sc.w) * C_VIS + lane;
+      float a = 0.f;
+      if (t.w[0] != 0.f) a = __ldg(base + ((size_t)t.y0 * sc.w + t.x0) * C_VIS) * t.w[0];
+      if (t.w[1] != 0.f) a += __ldg(base + ((size_t)t.y0 * sc.w + t.x0 + 1) * C_VIS) * t.w[1];
+      if (t.w[2] != 0.f) a += __ldg(base + ((size_t)(t.y0 + 1) * sc.w + t.x0) * C_VIS) * t.w[2];
+      if (t.w[3] != 0.f) a += __ldg(base + ((size_t)(t.y0 + 1) * sc.w + t.x0 + 1) * C_VIS) * t.w[3];
+      val = a * ri[RI_VALID];
+    }
+    sX[r * LDX + lane] = val;
+  }
+  // (tile_gemm starts with a __syncthreads)
+
+  // ---- phase 3: visibility decoder ------------------------------------------------------------------------------
+  tile_gemm<8, 8, 128, false>(plainA(sX, LDX), 128, w.dec1, 128, 32, sB,
+                              [&](int r, int c, float v) { sH[r * LDH + c] = elu(v + __ldg(w.dec1_b + c)); });
+  for (int hd = 0; hd < 4; ++hd) {
+    tile_gemm<4, 4, 32, true>(plainA(sH + 32 * hd, LDH), 128, w.dec2 + 1024 * hd, 32, 32, sB, [&](int r, int c, float v) {
+      sH[r * LDH + 32 * hd + c] = elu(v + __ldg(w.dec2_b + 32 * hd + c));
+    });
+  }
+  __syncthreads();
+  if (tid < rows) {
+    const float* hrow = sH + tid * LDH;
+    float o[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      const int hd = j < 2 ? 0 : (j < 4 ? 1 : (j == 4 ? 2 : 3));
+      float a = 0.f;
+      for (int k = 0; k < 32; ++k) a = fmaf(__ldg(w.dec3 + j * 32 + k), hrow[32 * hd + k], a);
+      o[j] = a + __ldg(w.dec3_b + j);
+    }
+    const float m0 = softplus(o[0]), m1 = softplus(o[1]);
+    const float v0 = softplus(o[2]) + 0.05f, v1 = softplus(o[3]) + 0.05f;
+    const float aw = sigmoidf(o[4]), vs = sigmoidf(o[5]);
+    float* ri = sRI + tid * RI_N;
+    const float dep = ri[RI_DEPTH];
+    const float near_inv = -1.f / near_, far_inv = -1.f / far_;
+    float refd = -1.f / (m0 * (far_inv - near_inv) + near_inv);
+    refd = fminf(fmaxf(refd, near_), far_);
+    ri[RI_DD] = fabsf(dep - refd) / (far_ - near_);
+    const float dn = (-1.f / fmaxf(dep, 1e-5f) - near_inv) / (far_inv - near_inv);
+    const float cdf0 = (0.5f + 0.5f * tanhf((dn - m0) * v0)) * vs;
+    const float cdf1 = (0.5f + 0.5f * tanhf((dn - m1) * v1)) * vs;
+    const float vis = (1.f - cdf0) * aw + (1.f - cdf1) * (1.f - aw);
+    ri[RI_VIS] = vis * ri[RI_VALID];
+  }
+  __syncthreads();
+
+  // ---- phase 4: per-sample view weights --------------------------------------------------------------------------
+  if (tid < np) {
+    float sum = 0.f;
+    for (int v = 0; v < V; ++v) sum += sRI[(tid * V + v) * RI_N + RI_VIS];
+    const float den = sum + 1e-8f;
+    float ddm = 0.f, wsum = 0.f;
+    int nval = 0;
+    for (int v = 0; v < V; ++v) {
+      float* ri = sRI + (tid * V + v) * RI_N;
+      const float wv = ri[RI_VIS] / den;
+      ri[RI_W] = wv;
+      ddm += ri[RI_DD] * wv;
+      wsum += wv;
+      nval += ri[RI_MASK] != 0.f;
+    }
+    float ddv = 0.f;
+    for (int v = 0; v < V; ++v) {
+      const float* ri = sRI + (tid * V + v) * RI_N;
+      const float d = ri[RI_DD] - ddm;
+      ddv += ri[RI_W] * (d * d);
+    }
+    float* g = sG + tid * LDG;
+    g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
+    for (int k = 393; k < 416; ++k) g[k] = 0.f;
+    if (nvalid_out) nvalid_out[n0 + tid] = (unsigned char)nval;
+  }
+  __syncthreads();  // sH (arena) is dead from here on
+
+  // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
+  for (int r = warp; r < 128; r += NT / 32) {
+    float* frow = sF + r * LDF;
+    if (r < rows) {
+      const float* ri = sRI + r * RI_N;
+      const int p = r / V, v = r - p * V;
+      const Taps tf = make_taps(ri[RI_FX], ri[RI_FY], sc.w, sc.h, true);
+      const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
+      float2 acc[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (tf.w[t] != 0.f) {
+          const float* tp = fb + ((size_t)(tf.y0 + (t >> 1)) * sc.w + tf.x0 + (t & 1)) * C_FEAT;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float2 q = __ldg(reinterpret_cast<const float2*>(tp + j * 64));
+            acc[j].x = fmaf(q.x, tf.w[t], acc[j].x);
+            acc[j].y = fmaf(q.y, tf.w[t], acc[j].y);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        frow[3 + j * 64 + lane * 2] = acc[j].x;
+        frow[3 + j * 64 + lane * 2 + 1] = acc[j].y;
+      }
+      // rgb: lanes 0..3 fetch one tap each
+      const Taps ti = make_taps(ri[RI_IX], ri[RI_IY], sc.W, sc.H, true);
+      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lane < 4 && ti.w[lane] != 0.f) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(
+            sc.images + (((size_t)v * sc.H + ti.y0 + (lane >> 1)) * sc.W + ti.x0 + (lane & 1)) * 4));
+        c.x = q.x * ti.w[lane]; c.y = q.y * ti.w[lane]; c.z = q.z * ti.w[lane];
+      }
+      c.x += __shfl_xor_sync(0xffffffffu, c.x, 1); c.y += __shfl_xor_sync(0xffffffffu, c.y, 1); c.z += __shfl_xor_sync(0xffffffffu, c.z, 1);
+      c.x += __shfl_xor_sync(0xffffffffu, c.x, 2); c.y += __shfl_xor_sync(0xffffffffu, c.y, 2); c.z += __shfl_xor_sync(0xffffffffu, c.z, 2);
+      if (lane == 0) {
+        frow[0] = c.x; frow[1] = c.y; frow[2] = c.z;
+        frow[195] = ri[RI_VIS];
+        // colour-blend ray difference (ibrnet.py:144-167) between the query camera and view v
+        const float x = sPt[p * 4], y = sPt[p * 4 + 1], z = sPt[p * 4 + 2];
+        const float* cc = sc.cams + v * 32 + 24;
+        float ax = sc.qc[0] - x, ay = sc.qc[1] - y, az = sc.qc[2] - z;
+        float an = sqrtf(ax * ax + ay * ay + az * az) + 1e-6f;
+        ax /= an; ay /= an; az /= an;
+        float bx = cc[0] - x, by = cc[1] - y, bz = cc[2] - z;
+        float bn = sqrtf(bx * bx + by * by + bz * bz) + 1e-6f;
+        bx /= bn; by /= bn; bz /= bn;
+        const float dx = ax - bx, dy = ay - by, dz = az - bz;
+        const float dn = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);
+        frow[196] = dx / dn; frow[197] = dy / dn; frow[198] = dz / dn;
+        frow[199] = ax * bx + ay * by + az * bz;
+        if (rgbvis_out) {
+          float4 o = make_float4(c.x, c.y, c.z, ri[RI_VIS]);
+          *reinterpret_cast<float4*>(rgbvis_out + ((n0 + p) * V + v) * 4) = o;
+        }
+        if (mvv_out) mvv_out[(n0 + p) * V + v] = ri[RI_VIS];
+      }
+      if (lane < 28) frow[200 + lane] = 0.f;
+    } else {
+      for (int k = lane; k < LDF; k += 32) frow[k] = 0.f;
+    }
+  }
+  __syncthreads();
+  if (mvf_out) {
+    for (int i = tid; i < rows * C_RGBF; i += NT) {
+      const int r = i / C_RGBF, c = i - r * C_RGBF;
+      mvf_out[(n0 * V + r) * C_RGBF + c] = sF[r * LDF + c];
+    }
+  }
+
+  // ---- phase 6: visibility-weighted mean / variance over views (ibrnet.py:8-12) ---------------------------------
+  for (int i = tid; i < np * C_RGBF; i += NT) {
+    const int p = i / C_RGBF, c = i - p * C_RGBF;
+    float m = 0.f;
+    for (int v = 0; v < V; ++v) m += sF[(p * V + v) * LDF + c] * sRI[(p * V + v) * RI_N + RI_W];
+    float var = 0.f;
+    for (int v = 0; v < V; ++v) {
+      const float d = sF[(p * V + v) * LDF + c] - m;
+      var += sRI[(p * V + v) * RI_N + RI_W] * (d * d);
+    }
+    sG[p * LDG + c] = m;
+    sG[p * LDG + C_RGBF + c] = var;
+  }
+  for (int i = tid; i < (TP_MAX - np) * LDG; i += NT) sG[np * LDG + i] = 0.f;
+
+  // ---- phase 7: out_fc 393 -> 64 -> 128 (ELU) --------------------------------------------------------------------
+  tile_gemm<1, 4, 64, false>(plainA(sG, LDG), TP_MAX, w.fc1, 64, 416, sB,
+                             [&](int r, int c, float v) { sO1[r * 68 + c] = elu(v + __ldg(w.fc1_b + c)); });
+  tile_gemm<1, 8, 128, false>(plainA(sO1, 68), TP_MAX, w.fc2, 128, 64, sB, [&](int r, int c, float v) {
+    if (r < np) agg_out[(n0 + r) * W_HID + c] = elu(v + __ldg(w.fc2_b + c));
+  });
+
+  // ---- phase 8: per-view half of the colour-blend first layer ----------------------------------------------------
+  if (with_blend) {
+    tile_gemm<4, 4, 32, false>(plainA(sF, LDF), 128, w.bl1v, 32, 224, sB, [&](int r, int c, float v) {
+      if (r < rows) partial_out[(n0 * V + r) * 32 + c] = v + __ldg(w.bl1_b + c);
+    });
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// neighbour MLP + attention
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int LDP = 100;  // PE(63) + ray_diff_fc(27) -> 96 (+4)
+constexpr int NBR_SMEM_FLOATS = STAGE_FLOATS + 128 * LDH + 128 * LDP + 3 * TP_MAX * LDH + 512 + 128 * 2 + TP_MAX * 4;
+
+__global__ void __launch_bounds__(NT, 1)
+neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int K,
+                const int* __restrict__ knn_idx, const float* __restrict__ knn_d2, const float* __restrict__ agg_in,
+                float* __restrict__ fagg_out, float* __restrict__ feature_out, float* __restrict__ weights_out) {
+  extern __shared__ __align__(16) float smem[];
+  float* sB = smem;
+  float* sA = sB + STAGE_FLOATS;        // [128][LDH]  neighbour activations
+  float* sX = sA + 128 * LDH;           // [128][LDP]  PE | ray_diff_fc ; later q~ / context [64][LDH]
+  float* sAgg = sX + 128 * LDP;         // [16][LDH]
+  float* sQ = sAgg + TP_MAX * LDH;      // [16][LDH]
+  float* sO = sQ + TP_MAX * LDH;        // [16][LDH]
+  float* sSc = sO + TP_MAX * LDH;       // [16][4][8]
+  float* sD = sSc + 512;                // [128] sqrt-dist, [128] conf
+  float* sWs = sD + 256;                // [16][4]
+  float* sQT = sX;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n0 = (int64_t)blockIdx.x * TP_MAX;
+  const int np = (int)min((int64_t)TP_MAX, N - n0);
+  const float inv_range = sc.far_ - sc.near_;
+
+  // ---- phase 0: per (sample, neighbour) geometry: positional encoding and ray difference -------------------------
+  if (tid < 128) {
+    const int p = tid >> 3, k = tid & 7;
+    float* xr = sX + tid * LDP;
+    if (p < np && k < K) {
+      const int64_t n = n0 + p;
+      const int id = knn_idx[n * K + k];
+      sD[tid] = knn_d2[n * K + k];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8 + 4));
+      sD[128 + tid] = g1.z;  // confidence
+      float x, y, z;
+      load_point(ps, n, x, y, z);
+      float dx, dy, dz;
+      if (ps.dirs) {
+        dx = ps.dirs[n * 3]; dy = ps.dirs[n * 3 + 1]; dz = ps.dirs[n * 3 + 2];
+      } else if (ps.rays_d && !ps.xyz) {
+        const int64_t r = n / ps.S;
+        dx = ps.rays_d[r * 3]; dy = ps.rays_d[r * 3 + 1]; dz = ps.rays_d[r * 3 + 2];
+      } else {  // direction=None: the nearest neighbour's own direction (model.py:391-392)
+        const int id0 = knn_idx[n * K];
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8));
+        const float4 h1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8 + 4));
+        dx = h0.w; dy = h1.x; dz = h1.y;
+      }
+      const float off[3] = {__fdiv_rn(__fsub_rn(x, g0.x), inv_range), __fdiv_rn(__fsub_rn(y, g0.y), inv_range),
+                            __fdiv_rn(__fsub_rn(z, g0.z), inv_range)};
+      xr[0] = off[0]; xr[1] = off[1]; xr[2] = off[2];
+      float f = 1.f;
+#pragma unroll
+      for (int i = 0; i < 10; ++i) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float s, co;
+          sincosf(off[c] * f, &s, &co);
+          xr[3 + i * 6 + c] = s;
+          xr[3 + i * 6 + 3 + c] = co;
+        }
+        f *= 2.f;
+      }
+      // ray difference (model.py:396-399) and ray_diff_fc (4 -> 16 -> 27, LeakyReLU)
+      const float nx = g0.w, ny = g1.x, nz = g1.y;
+      float rx = dx - nx, ry = dy - ny, rz = dz - nz;
+      const float rn = sqrtf(rx * rx + ry * ry + rz * rz) + 1e-8f;
+      const float rd[4] = {rx / rn, ry / rn, rz / rn, dx * nx + dy * ny + dz * nz};
+      float h1[16];
+#pragma unroll
+      for (int o = 0; o < 16; ++o) {
+        float a = __ldg(w.rd1_b + o);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) a = fmaf(__ldg(w.rd1 + o * 4 + c), rd[c], a);
+        h1[o] = leaky(a);
+      }
+      for (int o = 0; o < 27; ++o) {
+        float a = __ldg(w.rd2_b + o);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) a = fmaf(__ldg(w.rd2 + o * 16 + c), h1[c], a);
+        xr[63 + o] = leaky(a);
+      }
+#pragma unroll
+      for (int c = 90; c < 96; ++c) xr[c] = 0.f;
+    } else {
+      for (int c = 0; c < 96; ++c) xr[c] = 0.f;
+      sD[tid] = 1.f; sD[128 + tid] = 0.f;
+    }
+  }
+  // ---- phase 1: gather the per-frame precomputed support part of layer 1 ------------------------------------------
+  for (int r = warp; r < 128; r += NT / 32) {
+    const int p = r >> 3, k = r & 7;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p < np && k < K) {
+      const int id = knn_idx[(n0 + p) * K + k];
+      v = __ldg(reinterpret_cast<const float4*>(sc.sup_pre + (size_t)id * W_HID + lane * 4));
+    }
+    *reinterpret_cast<float4*>(sA + r * LDH + lane * 4) = v;
+  }
+  for (int i = tid; i < TP_MAX * W_HID; i += NT) {
+    const int p = i >> 7, c = i & 127;
+    sAgg[p * LDH + c] = p < np ? agg_in[(n0 + p) * W_HID + c] : 0.f;
+  }
+  // ---- phase 2/3: base_mlp ------------------------------------------------------------------------------------------
+  tile_gemm<8, 8, 128, false>(plainA(sX, LDP), 128, w.w1b, 128, 96, sB,
+                              [&](int r, int c, float v) { sA[r * LDH + c] = leaky(v + sA[r * LDH + c]); });
+  tile_gemm<8, 8, 128, true>(plainA(sA, LDH), 128, w.w2, 128, 128, sB,
+                             [&](int r, int c, float v) { sA[r * LDH + c] = leaky(v + __ldg(w.b2 + c)); });
+  tile_gemm<8, 8, 128, true>(plainA(sA, LDH), 128, w.w3, 128, 128, sB,
+                             [&](int r, int c, float v) { sA[r * LDH + c] = leaky(v + __ldg(w.b3 + c)); });
+  // ---- phase 4: q = Wq agg ; phase 5: q~_h = Wk_h^T q_h -------------------------------------------------------------
+  tile_gemm<1, 8, 128, false>(plainA(sAgg, LDH), TP_MAX, w.wq, 128, 128, sB,
+                              [&](int r, int c, float v) { sQ[r * LDH + c] = v; });
+  for (int hd = 0; hd < 4; ++hd)
+    tile_gemm<1, 8, 128, false>(plainA(sQ + 32 * hd, LDH), TP_MAX, w.wk + 32 * hd * 128, 128, 32, sB,
+                                [&](int r, int c, float v) { sQT[(r * 4 + hd) * LDH + c] = v; });
+  __syncthreads();
+  // ---- phase 6: attention scores + softmax over the K neighbours ----------------------------------------------------
+  for (int it = 0; it < 2; ++it) {
+    const int i = tid + it * NT;  // (p, h, k), k fastest
+    const int p = i >> 5, hd = (i >> 3) & 3, k = i & 7;
+    const float* qv = sQT + (p * 4 + hd) * LDH;
+    const float* kv = sA + (p * 8 + k) * LDH;
+    float a = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < 128; c += 4) {
+      const float4 q4 = *reinterpret_cast<const float4*>(qv + c);
+      const float4 k4 = *reinterpret_cast<const float4*>(kv + c);
+      a = fmaf(q4.x, k4.x, a); a = fmaf(q4.y, k4.y, a); a = fmaf(q4.z, k4.z, a); a = fmaf(q4.w, k4.w, a);
+    }
+    a *= 0.17677669529663687f;  // 1/sqrt(d_k = 32)
+    if (k >= K) a = -FLT_MAX;
+    float m = a;
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+    const float e = k < K ? expf(a - m) : 0.f;
+    float s = e;
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    sSc[i] = e / s;
+  }
+  __syncthreads();
+  // ---- phase 7: per-head context = sum_k a_k * point_feature_k (overwrites q~) --------------------------------------
+  {
+    const int ph = tid >> 2, c0 = (tid & 3) * 32;
+    const int p = ph >> 2;
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (int k = 0; k < 8; ++k) {
+      const float a = sSc[ph * 8 + k];
+      const float* kv = sA + (p * 8 + k) * LDH + c0;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const float4 v4 = *reinterpret_cast<const float4*>(kv + c);
+        acc[c] = fmaf(a, v4.x, acc[c]); acc[c + 1] = fmaf(a, v4.y, acc[c + 1]);
+        acc[c + 2] = fmaf(a, v4.z, acc[c + 2]); acc[c + 3] = fmaf(a, v4.w, acc[c + 3]);
+      }
+    }
+    __syncthreads();  // every score has been consumed from sQT's neighbours; q~ itself is dead
+#pragma unroll
+    for (int c = 0; c < 32; ++c) sQT[ph * LDH + c0 + c] = acc[c];
+  }
+  // ---- phase 8: o_h = Wv_h ctx_h ; phase 9: fc + residual ------------------------------------------------------------
+  for (int hd = 0; hd < 4; ++hd)
+    tile_gemm<1, 4, 32, false>(plainA(sQT + hd * LDH, 4 * LDH), TP_MAX, w.wv + 32 * hd, 128, 128, sB,
+                               [&](int r, int c, float v) { sO[r * LDH + 32 * hd + c] = v; });
+  tile_gemm<1, 8, 128, false>(plainA(sO, LDH), TP_MAX, w.wfc, 128, 128, sB,
+                              [&](int r, int c, float v) { sQ[r * LDH + c] = v + sAgg[r * LDH + c]; });
+  __syncthreads();
+  // ---- phase 10: LayerNorm(eps 1e-6), neighbour weights, weighted sum -------------------------------------------------
+  if (tid < TP_MAX) {
+    // weights = (1/clamp(dist)) * softmax_K(corr) * conf, normalised (model.py:415-426); corr rows are identical
+    // across K, so softmax_K(corr) is exactly 1/K.
+    float wk[8], s = 0.f;
+    const float corr = 1.f / (float)K;
+    for (int k = 0; k < 8; ++k) {
+      float v = 0.f;
+      if (k < K) {
+        v = 1.f / fmaxf(sqrtf(sD[tid * 8 + k]), 1e-8f);
+        v *= corr;
+        v *= sD[128 + tid * 8 + k];
+      }
+      wk[k] = v; s += v;
+    }
+    s = fmaxf(s, 1e-8f);
+    for (int k = 0; k < 8; ++k) {
+      wk[k] = wk[k] / s;
+      sSc[tid * 8 + k] = wk[k];
+      if (weights_out && tid < np && k < K) weights_out[(n0 + tid) * K + k] = wk[k];
+    }
+  }
+  for (int p = warp; p < TP_MAX; p += NT / 32) {
+    const float4 y = *reinterpret_cast<const float4*>(sQ + p * LDH + lane * 4);
+    const float mean = warp_sum(y.x + y.y + y.z + y.w) * (1.f / 128.f);
+    const float d0 = y.x - mean, d1 = y.y - mean, d2 = y.z - mean, d3 = y.w - mean;
+    const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / 128.f);
+    const float rstd = 1.f / sqrtf(var + 1e-6f);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(w.ln_g + lane * 4));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(w.ln_b + lane * 4));
+    float4 f;
+    f.x = d0 * rstd * g.x + b.x; f.y = d1 * rstd * g.y + b.y; f.z = d2 * rstd * g.z + b.z; f.w = d3 * rstd * g.w + b.w;
+    *reinterpret_cast<float4*>(sO + p * LDH + lane * 4) = f;
+  }
+  __syncthreads();
+  for (int i = tid; i < np * W_HID; i += NT) {
+    const int p = i >> 7, c = i & 127;
+    const float f = sO[p * LDH + c];
+    float a = 0.f;
+    for (int k = 0; k < K; ++k) a += f * sSc[p * 8 + k];
+    fagg_out[(n0 + p) * W_HID + c] = a;
+    if (feature_out) feature_out[(n0 + p) * W_HID + c] = f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// generic row-tile Linear: out[n][0..Nout) = act(A[n][0..K) Wt + b), Wt [Kp][Nout] (Kp = K rounded up to 32)
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NT, 1)
+linear_kernel(const float* __restrict__ A, const int64_t N, const int K, const int lda, const float* __restrict__ Wt,
+              const float* __restrict__ bias, const int Nout, const int act, float* __restrict__ out, const int ldo) {
+  extern __shared__ __align__(16) float smem[];
+  float* sB = smem;
+  float* sA = sB + STAGE_FLOATS;
+  const int Kp = (K + 31) / 32 * 32;
+  const int ld = Kp + 4;
+  const int64_t n0 = (int64_t)blockIdx.x * 128;
+  const int nr = (int)min((int64_t)128, N - n0);
+  for (int i = threadIdx.x; i < 128 * Kp; i += NT) {
+    const int r = i / Kp, k = i - r * Kp;
+    sA[r * ld + k] = (r < nr && k < K) ? A[(n0 + r) * lda + k] : 0.f;
+  }
+  for (int c0 = 0; c0 < Nout; c0 += 64) {
+    tile_gemm<4, 8, 64, false>(plainA(sA, ld), 128, Wt + c0, Nout, Kp, sB, [&](int r, int c, float v) {
+      if (r < nr) {
+        float o = v + (bias ? __ldg(bias + c0 + c) : 0.f);
+        if (act == 1) o = leaky(o);
+        else if (act == 2) o = 1.f / (1.f + expf(-o));
+        out[(n0 + r) * ldo + c0 + c] = o;
+      }
+    });
+  }
+}
+
+// support-point geometry pack: [M][8] = xyz, direction(3), confidence, 0
+__global__ void sup_geo_kernel(const float* __restrict__ xyz, const float* __restrict__ dir, const float* __restrict__ conf,
+                               int64_t M, float* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  float4 a = make_float4(xyz[i * 3], xyz[i * 3 + 1], xyz[i * 3 + 2], dir[i * 4]);
+  float4 b = make_float4(dir[i * 4 + 1], dir[i * 4 + 2], conf[i], 0.f);
+  *reinterpret_cast<float4*>(out + i * 8) = a;
+  *reinterpret_cast<float4*>(out + i * 8 + 4) = b;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------------------------
+template <class Kern>
+static int set_smem(Kern k, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  return e == cudaSuccess ? 0 : set_error(cudaGetErrorString(e));
+}
+
+int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int with_blend, float* agg,
+                     float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (sc.V < 1 || sc.V > 16) return set_error("aggregate: number of reference views must be in 1..16");
+  const size_t smem = AGG_SMEM_FLOATS * sizeof(float);
+  if (set_smem(aggregate_kernel, smem)) return 1;
+  const int TP = TP_MAX < 128 / sc.V ? TP_MAX : 128 / sc.V;
+  const unsigned grid = (unsigned)((N + TP - 1) / TP);
+  aggregate_kernel<<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
+  return check_launch("aggregate_kernel");
+}
+
+int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
+                    const float* d2, const float* agg, float* fagg, float* feature, float* weights, cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (K < 1 || K > 8) return set_error("neighbor: K must be in 1..8");
+  const size_t smem = NBR_SMEM_FLOATS * sizeof(float);
+  if (set_smem(neighbor_kernel, smem)) return 1;
+  const unsigned grid = (unsigned)((N + TP_MAX - 1) / TP_MAX);
+  neighbor_kernel<<<grid, NT, smem, st>>>(sc, w, ps, N, K, idx, d2, agg, fagg, feature, weights);
+  return check_launch("neighbor_kernel");
+}
+
+int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,
+                  float* out, int ldo, cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (Nout % 64 != 0) return set_error("linear: Nout must be a multiple of 64");
+  const int Kp = (K + 31) / 32 * 32;
+  if (Kp > 352) return set_error("linear: K too large for one shared-memory tile");
+  const size_t smem = (STAGE_FLOATS + 128 * (Kp + 4)) * sizeof(float);
+  if (set_smem(linear_kernel, smem)) return 1;
+  linear_kernel<<<(unsigned)((N + 127) / 128), NT, smem, st>>>(A, N, K, lda, Wt, bias, Nout, act, out, ldo);
+  return check_launch("linear_kernel");
+}
+
+int launch_sup_geo(const float* xyz, const float* dir, const float* conf, int64_t M, float* out, cudaStream_t st) {
+  if (M <= 0) return 0;
+  sup_geo_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(xyz, dir, conf, M, out);
+  return check_launch("sup_geo_kernel");
+}
+
+}  // namespace nlb

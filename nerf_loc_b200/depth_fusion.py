@@ -1,0 +1,168 @@
+"""Per-frame setup network: DepthFusionNet -> 32-channel visibility feature maps.
+
+Runs once per query frame BEFORE the hot path and feeds it `vis_featmaps`.  It is a small CNN, so it stays on
+torch/cuDNN (library code) for now; the module tree reproduces the reference's parameter names
+(`multiview_aggregator.depth_fusion.*`, nerf_loc/models/conditional_nerf/depth_fusion.py:239-282 and
+neuray_ops.py:89-239) so a reference checkpoint loads unchanged.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def _conv3(cin, cout, stride=1):
+    return nn.Conv2d(cin, cout, 3, stride, 1, bias=False, padding_mode="reflect")
+
+
+def _inorm(c):
+    return nn.InstanceNorm2d(c, track_running_stats=False, affine=True)
+
+
+class _Block(nn.Module):  # neuray_ops.py:89-124
+    def __init__(self, cin, planes, stride=1, downsample=None):
+        super().__init__()
+        self.conv1, self.bn1 = _conv3(cin, planes, stride), _inorm(planes)
+        self.conv2, self.bn2 = _conv3(planes, planes), _inorm(planes)
+        self.downsample = downsample
+
+    def forward(self, x):
+        out = self.bn2(self.conv2(F.relu(self.bn1(self.conv1(x)))))
+        idt = x if self.downsample is None else self.downsample(x)
+        return F.relu(out + idt)
+
+
+class _ConvNormElu(nn.Module):  # neuray_ops.py:126-139
+    def __init__(self, cin, cout, k, stride):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, stride, (k - 1) // 2, padding_mode="reflect")
+        self.bn = _inorm(cout)
+
+    def forward(self, x):
+        return F.elu(self.bn(self.conv(x)))
+
+
+class _UpConv(nn.Module):  # neuray_ops.py:141-149
+    def __init__(self, cin, cout, k, scale):
+        super().__init__()
+        self.scale = scale
+        self.conv = _ConvNormElu(cin, cout, k, 1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=self.scale, align_corners=True, mode="bilinear"))
+
+
+class ResEncoder(nn.Module):  # neuray_ops.py:152-239
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(12, 32, 8, 2, 2, bias=False, padding_mode="reflect")
+        self.bn1 = _inorm(32)
+        self.layer1 = self._layer(32, 32)
+        self.layer2 = self._layer(32, 64)
+        self.layer3 = self._layer(64, 128)
+        self.upconv3 = _UpConv(128, 64, 3, 2)
+        self.iconv3 = _ConvNormElu(128, 64, 3, 1)
+        self.upconv2 = _UpConv(64, 32, 3, 2)
+        self.iconv2 = _ConvNormElu(64, 32, 3, 1)
+        self.out_conv = nn.Conv2d(32, 32, 1, 1)
+
+    @staticmethod
+    def _layer(cin, planes):
+        down = nn.Sequential(nn.Conv2d(cin, planes, 1, 2, bias=False, padding_mode="reflect"), _inorm(planes))
+        return nn.Sequential(_Block(cin, planes, 2, down), _Block(planes, planes))
+
+    @staticmethod
+    def _skip(x1, x2):
+        dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
+        x1 = F.pad(x1, (dx // 2, dx - dx // 2, dy // 2, dy - dy // 2))
+        return torch.cat([x2, x1], 1)
+
+    def forward(self, x):
+        x = F.relu(self.bn1(self.conv1(x)))
+        x1 = self.layer1(x)
+        x2 = self.layer2(x1)
+        x3 = self.layer3(x2)
+        x = self.iconv3(self._skip(x2, self.upconv3(x3)))
+        x = self.iconv2(self._skip(x1, self.upconv2(x)))
+        return self.out_conv(x)
+
+
+def _grid_fetch(maps, pts, h, w, align):
+    """neuray_ops.py:14-36 with border padding."""
+    xn = pts[:, :, 0] / (w - 1) * 2 - 1
+    yn = pts[:, :, 1] / (h - 1) * 2 - 1
+    grid = torch.stack([xn, yn], -1).unsqueeze(1)
+    out = F.grid_sample(maps, grid, mode="bilinear", padding_mode="border", align_corners=align).squeeze(2)
+    return out.permute(0, 2, 1)
+
+
+def _project(pts, Rt, Ks, h, w):
+    """depth_fusion.py:78-126: pts [P,3] -> pix [V,P,2], depth [V,P,1], valid [V,P]."""
+    V = Rt.shape[0]
+    hp = torch.cat([pts, torch.ones_like(pts[:, :1])], 1)
+    last = torch.zeros([V, 1, 4], device=pts.device, dtype=pts.dtype)
+    last[:, :, 3] = 1.0
+    Hm = torch.cat([Ks @ Rt, last], 1)
+    cam = (Hm[:, None] @ hp[None, :, :, None])[:, :, :3, 0]
+    depth = cam[:, :, 2:].clone()
+    bad = depth.abs() < 1e-4
+    depth[bad] = 1e-3
+    p2 = cam[:, :, :2] / depth
+    outside = (p2[..., 0] < -0.5) | (p2[..., 0] >= w - 0.5) | (p2[..., 1] < -0.5) | (p2[..., 1] >= h - 0.5)
+    return p2, depth, (~bad[..., 0]) & (~outside)
+
+
+def cross_view_differences(imgs, depth_norm, Ks, Rt, depth_range):
+    """depth_fusion.py:167-207: every reference depth pixel is re-projected into every view; masked mean/variance of
+    the colour and inverse-depth discrepancies -> [V,8,h,w]."""
+    V, _, h, w = imgs.shape
+    near = depth_range[:, 0][:, None, None, None]
+    far = depth_range[:, 1][:, None, None, None]
+    near_inv, far_inv = -1 / near, -1 / far
+    depth = -1 / (depth_norm * (far_inv - near_inv) + near_inv)  # [V,1,h,w]
+    ys, xs = torch.meshgrid(torch.arange(h, device=imgs.device), torch.arange(w, device=imgs.device), indexing="ij")
+    pix = torch.stack([xs, ys, torch.ones_like(xs)], -1).float().reshape(1, h * w, 3)
+    pts = (depth.permute(0, 2, 3, 1).reshape(V, h * w, 1) * pix).permute(0, 2, 1)  # [V,3,hw]
+    pts = torch.inverse(Ks) @ pts
+    Rinv = Rt[:, :3, :3].permute(0, 2, 1)
+    pts = (Rinv @ pts + (-Rinv @ Rt[:, :3, 3:])).permute(0, 2, 1)  # world [V,hw,3]
+    p2, d_prj, valid = _project(pts.reshape(-1, 3), Rt, Ks, h, w)
+    d_int = _grid_fetch(depth, p2, h, w, True)
+    c_int = _grid_fetch(imgs, p2, h, w, True)
+    rgb_diff = (c_int - imgs.permute(0, 2, 3, 1).reshape(1, V * h * w, 3)).abs()
+    d_int = d_int.clamp(min=1e-5)
+    d_prj = d_prj.clamp(min=1e-5)
+    d_diff = (-1 / d_int + 1 / d_prj).abs() / (far_inv - near_inv)[:, :, 0]
+    d_diff = d_diff.clamp(max=1.5)
+    m = valid.float().unsqueeze(-1)
+    cnt = m.sum(0, keepdim=True).clamp_min(1e-4)
+
+    def mv(x):
+        mean = (x * m).sum(0, keepdim=True) / cnt
+        var = ((x - mean) ** 2 * m).sum(0, keepdim=True) / cnt
+        return mean, var
+    dm, dv = mv(d_diff)
+    cm, cv = mv(rgb_diff)
+    r = lambda t, c: t.reshape(V, h, w, c).permute(0, 3, 1, 2)
+    return torch.cat([r(cm, 3), r(cv, 3), r(dm, 1), r(dv, 1)], 1)
+
+
+class DepthFusionNet(nn.Module):
+    def __init__(self, cfg=None, in_channels=None):
+        super().__init__()
+        self.fuse_net = ResEncoder()
+        self.depth_skip = nn.Sequential(nn.Conv2d(1, 8, 2, 2), nn.ReLU(True), nn.Conv2d(8, 16, 2, 2))
+        self.conv_out = nn.Conv2d(16 + 32, 32, 1, 1)
+        self.out_channels = 32
+
+    def forward(self, imgs, feats, depths, Ks, poses, depth_range):
+        """imgs [V,3,H,W], depths [V,H,W], Ks [V,3,3], poses c2w [V,4,4], depth_range [2] -> [V,32,H/4,W/4]."""
+        V = imgs.shape[0]
+        rng = depth_range.view(1, 2).repeat(V, 1).float()
+        Rt = torch.inverse(poses)[:, :3]
+        near_inv = (-1 / rng[:, 0])[:, None, None, None]
+        far_inv = (-1 / rng[:, 1])[:, None, None, None]
+        d = -1 / depths.unsqueeze(1).clamp(min=1e-5)
+        d = ((d - near_inv) / (far_inv - near_inv)).clamp(0, 1.0)  # depth_fusion.py:223-237
+        diff = cross_view_differences(imgs, d, Ks, Rt, rng)
+        x = self.fuse_net(torch.cat([imgs, d, diff], 1))
+        return self.conv_out(torch.cat([self.depth_skip(d), x], 1))

@@ -1,0 +1,150 @@
+"""-m gpu parity tests of the render path: CUDA (through the C ABI) vs the CPU oracle and the golden vectors.
+
+Tolerances (BASELINE.json north_star): bit-exact KNN indices / masks; <= 1e-4 max-norm relative on every float output.
+"""
+import pytest
+import torch
+
+from nerf_loc_b200 import synthetic as syn
+from nerf_loc_b200.knn import KnnIndex, knn_points
+from oracle import knn_oracle as KO
+from oracle import nerfloc_oracle as O
+from tests.common import RENDER_CASES, golden, relerr, render_inputs
+from tests.gpu_common import cuda_model, oracle_scene, oracle_support, setup_frame
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def _cloud(n, seed, lattice=False, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    p = (torch.rand(n, 3, generator=g) * 2 - 1) * scale
+    return torch.round(p * 4) / 4 if lattice else p
+
+
+@pytest.mark.parametrize("K", [1, 8])
+@pytest.mark.parametrize("lattice", [False, True])
+@pytest.mark.parametrize("M", [3, 100, 20000])
+def test_knn_bit_exact(K, lattice, M):
+    q, s = _cloud(3000, 1, lattice, 1.5), _cloud(M, 2, lattice)
+    d_ref, i_ref = KO.knn_c(q, s, K)
+    d, i = KnnIndex(s.cuda()).query(q.cuda(), K)
+    assert torch.equal(i.cpu(), i_ref)
+    assert torch.equal(d.cpu(), d_ref)
+
+
+def test_knn_points_signature_and_surface_cloud():
+    sc = syn.make_scene(64, 96, 3, seed=9)
+    sd_dummy = None
+    from nerf_loc_b200.conditional_nerf import ConditionalNeRF
+    from nerf_loc_b200.config import default_args
+    m = ConditionalNeRF(default_args(16))
+    _, xyz, _, _ = m.backproject_support_frame(sc["topk_images"], sc["feat_fine_src"], sc["topk_depths"],
+                                               sc["topk_Ks"], sc["topk_poses"], stride=4)
+    px = syn.random_pixels(64, 96, 64)
+    ro, rd = syn.pixel_rays(sc["K"], sc["pose"], px)
+    z = torch.linspace(0.3, 5.0, 32)
+    q = (ro[:, None] + rd[:, None] * z[None, :, None]).reshape(-1, 3)
+    out = knn_points(q[None].cuda(), xyz[None].cuda(), K=8, return_nn=True)
+    d_ref, i_ref = KO.knn_c(q, xyz, 8)
+    assert out.idx.dtype == torch.int64 and tuple(out.idx.shape) == (1, q.shape[0], 8)
+    assert torch.equal(out.idx[0].cpu(), i_ref) and torch.equal(out.dists[0].cpu(), d_ref)
+    assert torch.equal(out.knn[0].cpu(), xyz[i_ref])
+
+
+@pytest.mark.parametrize("name", list(RENDER_CASES))
+def test_aggregator_and_support_points(name):
+    S, sd_cpu, sc, scene, ro, rd = render_inputs(name)
+    model, sd = cuda_model(S, RENDER_CASES[name][5])
+    data = setup_frame(model, sc)
+    model.build_support_neural_points(data)
+    sup = oracle_support(sd, sc)
+    g = golden(name)
+    for lv in ("coarse", "fine"):
+        for k, v in sup[lv].items():
+            assert relerr(model.support_neural_points[lv][k].cpu(), v) < TOL, (lv, k)
+    assert relerr(model.support_neural_points["fine"]["confidence"].cpu(), g["conf_fine"]) < TOL
+    z = O.sample_depths(S, *scene["depth_range"])
+    xyz = (ro[:, None, :] + rd[:, None, :] * z[None, :, None]).reshape(-1, 3)
+    fm = sc["feat_fine_src"].permute(0, 3, 1, 2)
+    with torch.no_grad():
+        out_o, rf_o, vis_o = O.aggregator_forward(sd, "multiview_aggregator", xyz, scene["Ks"], scene["c2ws"],
+                                                  scene["images"], fm, scene["vis_maps"], scene["depth_range"])
+    out, rf, vis = model.multiview_aggregator(xyz.cuda(), data["topk_Ks"], data["topk_poses"], data["topk_images"],
+                                              fm.cuda(), data["topk_depths"], data["depth_range"][0])
+    assert relerr(vis.cpu(), vis_o) < TOL
+    assert relerr(rf.cpu(), rf_o) < TOL
+    assert relerr(out.cpu(), out_o) < TOL
+
+
+@pytest.mark.parametrize("name", list(RENDER_CASES))
+def test_query_vs_oracle_and_golden(name):
+    S, sd_cpu, sc, scene, ro, rd = render_inputs(name)
+    model, sd = cuda_model(S, RENDER_CASES[name][5])
+    data = setup_frame(model, sc)
+    g = golden(name)
+    z = O.sample_depths(S, *scene["depth_range"])
+    xyz = (ro[:, None, :] + rd[:, None, :] * z[None, :, None]).reshape(-1, 3)
+    model.build_support_neural_points(data)
+    q = model.query(data, xyz.cuda(), support_featmaps=data["feat_fine_src"].permute(0, 3, 1, 2),
+                    support_neural_points=model.support_neural_points["fine"], direction=None, K=8)
+    assert torch.equal(q["knn_idx"].long().cpu(), g["knn_idx"])
+    assert relerr(q["multiview_visibility"].cpu(), g["q_vis"]) < TOL
+    assert relerr(q["feature_agg"].cpu(), g["q_feature_agg"]) < TOL
+    assert relerr(q["weights"].cpu(), g["q_weights"]) < TOL
+    assert tuple(q["feature"].shape) == (xyz.shape[0], 8, 128)
+    pts = oracle_support(sd, sc)["coarse"]["xyz"][::7][:40] + 0.01
+    dc, p3, ndc = model.query_coarse(data, points=pts.cuda())
+    df, _, _ = model.query_fine(data, pts.cuda())
+    assert relerr(dc.cpu(), g["desc_coarse"]) < TOL
+    assert relerr(df.cpu(), g["desc_fine"]) < TOL
+
+
+@pytest.mark.parametrize("name", list(RENDER_CASES))
+def test_render_rays_vs_golden(name):
+    S, sd_cpu, sc, scene, ro, rd = render_inputs(name)
+    model, sd = cuda_model(S, RENDER_CASES[name][5])
+    data = setup_frame(model, sc)
+    g = golden(name)
+    rays = {"rays_o": ro.cuda(), "rays_d": rd.cuda(), "depth_range": data["depth_range"][0]}
+    out = model.render_rays(data, rays, _debug=True)
+    sup = oracle_support(sd, sc)
+    with torch.no_grad():
+        ref = O.render_rays(sd, scene, sup["fine"], sc["feat_fine_src"].permute(0, 3, 1, 2), ro, rd, sc["pose"], S,
+                            return_debug=True)
+    report = {k: relerr(out[k].cpu(), ref[k]) for k in ("feature_agg", "sigma", "rgb", "depth", "weights",
+                                                         "depth_uncertainty", "feat")}
+    print(name, report)
+    for k, v in report.items():
+        assert v < TOL, (k, report)
+    for k in ("rgb", "depth", "weights", "depth_uncertainty", "feat"):
+        assert relerr(out[k].cpu(), g[k]) < TOL, k
+    assert torch.equal(out["mask"].cpu(), g["mask"])
+
+
+def test_render_chunking_is_invisible():
+    name = "render_s16"
+    S, sd_cpu, sc, scene, ro, rd = render_inputs(name)
+    model, sd = cuda_model(S, RENDER_CASES[name][5])
+    data = setup_frame(model, sc)
+    rays = {"rays_o": ro.cuda(), "rays_d": rd.cuda(), "depth_range": data["depth_range"][0]}
+    a = model.render_rays(data, rays)
+    model.chunk_rays = 7
+    b = model.render_rays(data, rays)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_render_image_shapes_and_white_background():
+    name = "render_s16"
+    S, sd_cpu, sc, scene, ro, rd = render_inputs(name)
+    model, sd = cuda_model(S, RENDER_CASES[name][5])
+    sc = dict(sc)
+    data = setup_frame(model, sc)
+    data["H"], data["W"] = 8, 12   # render a small crop of the frame
+    img = model.render_image(data)
+    assert tuple(img["rgb"].shape) == (8, 12, 3) and tuple(img["weights"].shape) == (8, 12, S)
+    data["white_bkgd"] = True
+    img2 = model.render_image(data)
+    wsum = img["weights"].sum(-1, keepdim=True)
+    assert relerr(img2["rgb"].cpu(), (img["rgb"] + (1 - wsum)).cpu()) < 1e-5

@@ -1,0 +1,70 @@
+"""CPU-side checks of the host mirror: parameter names, the torch per-frame setup network, library exports."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from nerf_loc_b200 import _lib, params, synthetic as syn
+from nerf_loc_b200.config import default_args
+from nerf_loc_b200.conditional_nerf import ConditionalNeRF
+from oracle import ref_harness as rh
+from tests.common import relerr
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nerfloc_b200.h")).read()
+    declared = set(re.findall(r"\b(nlb_[a-z0-9_]+)\s*\(", hdr))
+    declared.discard("nlb_scene")
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)  # loads without a GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.nlb_version() == 100
+    assert lib.nlb_render_param_count() == len(params.conditional_nerf_shapes(64))
+
+
+def test_mirror_state_dict_covers_the_inventory():
+    for S in (16, 64):
+        m = ConditionalNeRF(default_args(S))
+        sd = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+        inv = {k: tuple(v) for k, v in params.conditional_nerf_shapes(S).items()}
+        assert {k: v for k, v in sd.items() if "depth_fusion" not in k} == inv
+        assert list(k for k in sd if "depth_fusion" not in k) == list(inv)
+
+
+def test_no_cpu_fallback():
+    m = ConditionalNeRF(default_args(16))
+    with pytest.raises(RuntimeError):
+        m.packed_weights()  # CPU tensors are refused, nothing is computed on the host
+
+
+@pytest.mark.skipif(not rh.available(), reason="/root/reference not present")
+def test_mirror_matches_reference_names_and_depth_fusion():
+    R = rh.load()
+    torch.manual_seed(0)
+    ref = R.ConditionalNeRF(rh.default_args(16)).eval()
+    mine = ConditionalNeRF(default_args(16)).eval()
+    ref_sd = ref.state_dict()
+    assert {k: tuple(v.shape) for k, v in ref_sd.items()} == {k: tuple(v.shape) for k, v in mine.state_dict().items()}
+    mine.load_state_dict(ref_sd)  # a reference checkpoint loads unchanged
+    sc = syn.make_scene(64, 96, 3, seed=5)
+    args = (sc["topk_images"], sc["feat_fine_src"].permute(0, 3, 1, 2), sc["topk_depths"], sc["topk_Ks"],
+            sc["topk_poses"], sc["depth_range"][0])
+    with torch.no_grad():
+        a = ref.multiview_aggregator.depth_fusion(*args)
+        b = mine.multiview_aggregator.depth_fusion(*args)
+    assert a.shape == b.shape == (3, 32, 16, 24)
+    assert relerr(b, a) < 2e-5
+    # support-point construction (host plumbing)
+    data = {k: sc[k] for k in ("topk_images", "topk_depths", "topk_poses", "topk_Ks", "feat_fine_src")}
+    with torch.no_grad():
+        r4 = ref.backproject_support_frame(sc["topk_images"], sc["feat_fine_src"], sc["topk_depths"], sc["topk_Ks"],
+                                           sc["topk_poses"], stride=4)
+        m4 = mine.backproject_support_frame(sc["topk_images"], sc["feat_fine_src"], sc["topk_depths"], sc["topk_Ks"],
+                                            sc["topk_poses"], stride=4)
+    for x, y in zip(r4, m4):
+        assert torch.equal(x, y)
