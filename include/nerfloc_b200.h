@@ -46,10 +46,11 @@ int nlb_render_pack_weights(const float* const* params, int n_params, int S, flo
  * multiview_aggregator.vis_featmaps; reset protocol nerf_pose_estimator.py:289-290). */
 typedef struct nlb_scene {
   int32_t V, H, W, h, w;     /* reference views, image size, feature-map size */
+  int32_t vh, vw;            /* visibility-map size (always the fine level: H/4 x W/4, also for coarse queries) */
   float near_plane, far_plane;
   const float* images;       /* [V,H,W,4]  rgb + one pad channel (topk_images, channels last) */
   const float* featmaps;     /* [V,h,w,192] (feat_fine_src / feat_coarse_src, already channels last) */
-  const float* vis_maps;     /* [V,h,w,32]  DepthFusionNet output, channels last */
+  const float* vis_maps;     /* [V,vh,vw,32] DepthFusionNet output, channels last */
   const float* cams;         /* [V,32]: rows 0..2 of K_hom*inv(c2w) (12) | K*Rt (12) | camera centre (3) | pad (5) */
   int64_t M;                 /* support neural points of this level */
   const float* sup_pre;      /* [M,128] from nlb_support_prepare */

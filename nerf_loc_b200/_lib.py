@@ -15,7 +15,7 @@ c_void_p, c_int, c_int64, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, cty
 
 class NlbScene(ctypes.Structure):
     _fields_ = [("V", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("h", ctypes.c_int32),
-                ("w", ctypes.c_int32), ("near_plane", c_float), ("far_plane", c_float),
+                ("w", ctypes.c_int32), ("vh", ctypes.c_int32), ("vw", ctypes.c_int32), ("near_plane", c_float), ("far_plane", c_float),
                 ("images", c_void_p), ("featmaps", c_void_p), ("vis_maps", c_void_p), ("cams", c_void_p),
                 ("M", c_int64), ("sup_pre", c_void_p), ("sup_geo", c_void_p), ("knn_index", c_void_p),
                 ("query_center", c_float * 3)]

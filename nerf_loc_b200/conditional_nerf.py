@@ -103,8 +103,7 @@ class _Maps:
         self.h, self.w = feat_cl.shape[1], feat_cl.shape[2]
         if feat_cl.shape[3] != 192 or vis_maps.shape[1] != 32:
             raise RuntimeError("nerfloc_b200 kernels are built for 192-channel features and 32-channel visibility maps")
-        if tuple(vis_maps.shape[-2:]) != (self.h, self.w):
-            raise RuntimeError("visibility feature maps must have the feature-map resolution")
+        self.vh, self.vw = vis_maps.shape[-2], vis_maps.shape[-1]
         self.images = torch.cat([images.permute(0, 2, 3, 1), torch.zeros(V, H, W, 1, device=dev)], -1).float().contiguous()
         self.feat = _lib.f32(feat_cl)
         self.vis = _lib.f32(vis_maps.permute(0, 2, 3, 1))
@@ -121,6 +120,7 @@ class _Maps:
 
     def fill(self, sc):
         sc.V, sc.H, sc.W, sc.h, sc.w = self.V, self.H, self.W, self.h, self.w
+        sc.vh, sc.vw = self.vh, self.vw
         sc.near_plane, sc.far_plane = self.near, self.far
         sc.images, sc.featmaps = self.images.data_ptr(), self.feat.data_ptr()
         sc.vis_maps, sc.cams = self.vis.data_ptr(), self.cams.data_ptr()

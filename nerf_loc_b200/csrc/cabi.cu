@@ -25,7 +25,7 @@ int check_launch(const char* what) {
 
 static SceneDev to_dev(const nlb_scene* s) {
   SceneDev d{};
-  d.V = s->V; d.H = s->H; d.W = s->W; d.h = s->h; d.w = s->w;
+  d.V = s->V; d.H = s->H; d.W = s->W; d.h = s->h; d.w = s->w; d.vh = s->vh; d.vw = s->vw;
   d.images = s->images; d.feat = s->featmaps; d.vis = s->vis_maps; d.cams = s->cams;
   d.near_ = s->near_plane; d.far_ = s->far_plane;
   d.M = s->M; d.sup_pre = s->sup_pre; d.sup_geo = s->sup_geo; d.knn = s->knn_index;
@@ -39,7 +39,7 @@ static int check_scene(const nlb_scene* s, bool need_support = true) {
   if (need_support && (!s->sup_pre || !s->sup_geo || !s->knn_index || s->M < 1))
     return set_error("scene: support points not prepared");
   if (s->V < 1 || s->V > 16) return set_error("scene: number of reference views must be in 1..16");
-  if (s->H < 2 || s->W < 2 || s->h < 2 || s->w < 2) return set_error("scene: maps must be at least 2x2");
+  if (s->H < 2 || s->W < 2 || s->h < 2 || s->w < 2 || s->vh < 2 || s->vw < 2) return set_error("scene: maps must be at least 2x2");
   return 0;
 }
 

@@ -73,10 +73,10 @@ RenderW render_weights_view(const float* packed, int S);
 
 // ---- scene (per-frame) -----------------------------------------------------------------------------------------
 struct SceneDev {
-  int V, H, W, h, w;
+  int V, H, W, h, w, vh, vw;
   const float* images;   // [V][H][W][4]  rgb + pad
   const float* feat;     // [V][h][w][192]
-  const float* vis;      // [V][h][w][32]
+  const float* vis;      // [V][vh][vw][32]
   const float* cams;     // [V][32]: P=K_hom*w2c rows 0..2 (12) | K*Rt (12) | camera centre (3) | pad
   float near_, far_;
   int64_t M;             // support points

@@ -139,12 +139,12 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       ri[RI_VALID] = (!bad && !outside) ? 1.f : 0.f;
       ri[RI_DEPTH] = dep;
       const float xn = qx / (float)(sc.W - 1) * 2.f - 1.f, yn = qy / (float)(sc.H - 1) * 2.f - 1.f;
-      if (sc.h == sc.H && sc.w == sc.W) {  // align_corners=True only when the map has the image size
-        ri[RI_VX] = ((xn + 1.f) / 2.f) * (float)(sc.w - 1);
-        ri[RI_VY] = ((yn + 1.f) / 2.f) * (float)(sc.h - 1);
+      if (sc.vh == sc.H && sc.vw == sc.W) {  // align_corners=True only when the map has the image size
+        ri[RI_VX] = ((xn + 1.f) / 2.f) * (float)(sc.vw - 1);
+        ri[RI_VY] = ((yn + 1.f) / 2.f) * (float)(sc.vh - 1);
       } else {
-        ri[RI_VX] = ((xn + 1.f) * (float)sc.w - 1.f) / 2.f;
-        ri[RI_VY] = ((yn + 1.f) * (float)sc.h - 1.f) / 2.f;
+        ri[RI_VX] = ((xn + 1.f) * (float)sc.vw - 1.f) / 2.f;
+        ri[RI_VY] = ((yn + 1.f) * (float)sc.vh - 1.f) / 2.f;
       }
     } else {
 #pragma unroll
@@ -159,13 +159,13 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     if (r < rows) {
       const float* ri = sRI + r * RI_N;
       const int v = r % V;
-      const Taps t = make_taps(ri[RI_VX], ri[RI_VY], sc.w, sc.h, false);
-      const float* base = sc.vis + ((size_t)v * sc.h * sc.w) * C_VIS + lane;
+      const Taps t = make_taps(ri[RI_VX], ri[RI_VY], sc.vw, sc.vh, false);
+      const float* base = sc.vis + ((size_t)v * sc.vh * sc.vw) * C_VIS + lane;
       float a = 0.f;
-      if (t.w[0] != 0.f) a = __ldg(base + ((size_t)t.y0 * sc.w + t.x0) * C_VIS) * t.w[0];
-      if (t.w[1] != 0.f) a += __ldg(base + ((size_t)t.y0 * sc.w + t.x0 + 1) * C_VIS) * t.w[1];
-      if (t.w[2] != 0.f) a += __ldg(base + ((size_t)(t.y0 + 1) * sc.w + t.x0) * C_VIS) * t.w[2];
-      if (t.w[3] != 0.f) a += __ldg(base + ((size_t)(t.y0 + 1) * sc.w + t.x0 + 1) * C_VIS) * t.w[3];
+      if (t.w[0] != 0.f) a = __ldg(base + ((size_t)t.y0 * sc.vw + t.x0) * C_VIS) * t.w[0];
+      if (t.w[1] != 0.f) a += __ldg(base + ((size_t)t.y0 * sc.vw + t.x0 + 1) * C_VIS) * t.w[1];
+      if (t.w[2] != 0.f) a += __ldg(base + ((size_t)(t.y0 + 1) * sc.vw + t.x0) * C_VIS) * t.w[2];
+      if (t.w[3] != 0.f) a += __ldg(base + ((size_t)(t.y0 + 1) * sc.vw + t.x0 + 1) * C_VIS) * t.w[3];
       val = a * ri[RI_VALID];
     }
     sX[r * LDX + lane] = val;
