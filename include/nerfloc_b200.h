@@ -104,6 +104,11 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
 /* number of kernels nlb_render_rays launches for R rays (bench.py's gpu_launches claim) */
 int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays);
 
+/* Optional per-kernel device timing of nlb_render_rays (CUDA events on the launch stream, accumulated per kernel in the
+ * order knn, aggregate, neighbor, ray).  Enabling resets the counters; while enabled every chunk synchronises. */
+void nlb_profile_enable(int on);
+int nlb_profile_read(double* ms /*[n]*/, int64_t* launches /*[n]*/, int n /*<= 4*/);
+
 /* ---- Matcher weights --------------------------------------------------------------------------------------------------
  * `params` is a HOST array of 14 device pointers, reference layouts (nerf_loc/models/matcher.py:22,40-61):
  *   coarse_matcher.mlps.{0,2,4}.{weight,bias}  [128,192],[128],[128,128],[128],[1,128],[1]      (entries 0..5)

@@ -8,3 +8,4 @@ calling into it does.
 from .config import default_args  # noqa: F401
 from .conditional_nerf import ConditionalNeRF  # noqa: F401
 from .knn import KnnIndex, knn_gather, knn_points  # noqa: F401
+from .matcher import Matcher, S2DMatching  # noqa: F401

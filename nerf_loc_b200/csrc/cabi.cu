@@ -43,6 +43,35 @@ static int check_scene(const nlb_scene* s, bool need_support = true) {
   return 0;
 }
 
+// Optional per-kernel device timing of nlb_render_rays (bench.py's roofline figures): CUDA events on the launch stream
+// around each of the 4 kernels of a chunk.  flush() synchronises the stream, so it is off unless enabled.
+static bool g_prof_on = false;
+static double g_prof_ms[8];
+static int64_t g_prof_n[8];
+struct Prof {
+  cudaStream_t st;
+  cudaEvent_t ev[8];
+  int n = 0;
+  bool made = false;
+  explicit Prof(cudaStream_t s) : st(s) {}
+  void mark() {
+    if (!g_prof_on) return;
+    if (!made) { for (auto& e : ev) cudaEventCreate(&e); made = true; }
+    cudaEventRecord(ev[n++], st);
+  }
+  void flush(int kernels) {
+    if (!g_prof_on) return;
+    cudaEventSynchronize(ev[n - 1]);
+    for (int i = 0; i < kernels; ++i) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      g_prof_ms[i] += ms; g_prof_n[i] += 1;
+    }
+    n = 0;
+  }
+  ~Prof() { if (made) for (auto& e : ev) cudaEventDestroy(e); }
+};
+
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 struct Carver {
@@ -191,6 +220,7 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
   if (!c.ok) return set_error("nlb_render_rays: scratch too small (see nlb_render_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
+  Prof prof(st);
   for (int64_t r0 = 0; r0 < R; r0 += chunk_rays) {
     const int64_t rc = (R - r0) < chunk_rays ? (R - r0) : chunk_rays;
     const int64_t nc = rc * S;
@@ -198,14 +228,30 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
     const float* rd = rays_d + r0 * 3;
     PointSrc ps{nullptr, nullptr, ro, rd, z_vals, S};
     float* fa = dbg_feature_agg ? dbg_feature_agg + r0 * S * W_HID : fagg;
+    prof.mark();
     if (knn_query_rays(sc.knn, ro, rd, z_vals, rc, S, idx, d2, st)) return 1;
+    prof.mark();
     if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, st)) return 1;
+    prof.mark();
     if (launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)) return 1;
+    prof.mark();
     if (launch_ray(sc, w, z_vals, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                    weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
                    dbg_sigma ? dbg_sigma + r0 * S : nullptr, st))
       return 1;
+    prof.mark();
+    prof.flush(4);
   }
+  return 0;
+}
+
+void nlb_profile_enable(int on) {
+  g_prof_on = on != 0;
+  for (int i = 0; i < 8; ++i) { g_prof_ms[i] = 0.0; g_prof_n[i] = 0; }
+}
+
+int nlb_profile_read(double* ms, int64_t* launches, int n) {
+  for (int i = 0; i < n && i < 8; ++i) { ms[i] = g_prof_ms[i]; launches[i] = g_prof_n[i]; }
   return 0;
 }
 

@@ -164,5 +164,7 @@ class DepthFusionNet(nn.Module):
         d = -1 / depths.unsqueeze(1).clamp(min=1e-5)
         d = ((d - near_inv) / (far_inv - near_inv)).clamp(0, 1.0)  # depth_fusion.py:223-237
         diff = cross_view_differences(imgs, d, Ks, Rt, rng)
-        x = self.fuse_net(torch.cat([imgs, d, diff], 1))
-        return self.conv_out(torch.cat([self.depth_skip(d), x], 1))
+        # fp32 convolutions: cuDNN's TF32 default would put ~1e-3 noise into maps the parity-checked path reads
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            x = self.fuse_net(torch.cat([imgs, d, diff], 1))
+            return self.conv_out(torch.cat([self.depth_skip(d), x], 1))

@@ -68,3 +68,24 @@ def test_mirror_matches_reference_names_and_depth_fusion():
                                             sc["topk_poses"], stride=4)
     for x, y in zip(r4, m4):
         assert torch.equal(x, y)
+
+
+@pytest.mark.skipif(not rh.available(), reason="/root/reference not present")
+def test_matcher_mirror_loads_reference_state_dict_and_transformer_matches():
+    from nerf_loc_b200.matcher import Matcher, PositionEmbeddingSine
+    from oracle import matcher_oracle as MO
+    R = rh.load()
+    ref = R.Matcher(rh.default_args(), 192, 192, 192).eval()
+    mine = Matcher(default_args(), 192, 192, 192).eval()
+    mine.load_state_dict(ref.state_dict())
+    sd = {k: v for k, v in ref.state_dict().items()}
+    g = torch.Generator().manual_seed(0)
+    a, pa = torch.randn(1, 20, 192, generator=g), torch.randn(1, 20, 192, generator=g)
+    b, pb = torch.randn(1, 30, 192, generator=g), torch.randn(1, 30, 192, generator=g)
+    with torch.no_grad():
+        r0, r1 = ref.coarse_transformer(a, pa, b, pb)
+        m0, m1 = mine.coarse_transformer(a, pa, b, pb)
+        o0, o1 = MO.self_cross_transformer(sd, "coarse_transformer", a, pa, b, pb)
+    assert relerr(m0, r0) < 2e-5 and relerr(m1, r1) < 2e-5 and relerr(o0, r0) < 2e-5 and relerr(o1, r1) < 2e-5
+    pe = PositionEmbeddingSine(96, normalize=True)(torch.zeros(2, 7, 7))
+    assert torch.equal(pe, R.PositionEmbeddingSine(96, normalize=True, sine_type="lin_sine")(torch.zeros(2, 7, 7)))
