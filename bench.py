@@ -287,7 +287,10 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": args.cpu_rays / dt, "unit": "rays/s", "cores": torch.get_num_threads(),
                                 "kind": "port",
                                 "sample": f"{args.cpu_rays} evenly spaced rays of the frame x {S} samples (oracle/ render_rays, exact KNN on all host threads)"}
-        # parity of the benchmarked frame on that sample (checker only)
+        # parity of the benchmarked frame on that sample (checker only).  Both paths get the SAME per-frame inputs:
+        # the support points are injected from the CPU setup, because a 1-ulp difference between a GPU and a CPU
+        # back-projection flips near-tied nearest neighbours (the reference itself is discontinuous there).
+        model.support_neural_points = {"fine": {k: v.to(dev) for k, v in sup.items()}, "coarse": None}
         out = step_device()
         err = {k: float((out[k][idx.to(dev)].cpu() - ref[k]).abs().max() / ref[k].abs().max()) for k in ("rgb", "depth", "feat", "weights")}
         line["parity_on_sample"] = err

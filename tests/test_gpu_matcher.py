@@ -20,7 +20,8 @@ def cuda_matcher(seed, planted=False):
         for k in ("coarse_matcher.mlps.0.weight", "coarse_matcher.mlps.2.weight", "coarse_matcher.mlps.4.weight"):
             sd[k] = sd[k].abs()
         for k in ("coarse_matcher.mlps.0.bias", "coarse_matcher.mlps.2.bias", "coarse_matcher.mlps.4.bias"):
-            sd[k] = torch.full_like(sd[k], -0.5 if k.endswith("4.bias") else 0.0)
+            sd[k] = torch.full_like(sd[k], -3.0 if k.endswith("4.bias") else 0.0)
+        sd["coarse_matcher.mlps.4.weight"] = sd["coarse_matcher.mlps.4.weight"] * 0.03
     m = Matcher(default_args(), 192, 192, 192).eval()
     m.load_state_dict(sd)
     return m.cuda(), sd
