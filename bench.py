@@ -175,16 +175,13 @@ def run_b200(args):
     ro_h, rd_h = ro[lo:hi].contiguous().pin_memory(), rd[lo:hi].contiguous().pin_memory()
     ro_d, rd_d = ro_h.to(dev), rd_h.to(dev)
     Rl = hi - lo
-    feat_all = torch.empty(per * world, 192, device=dev) if world > 1 else None
+    from nerf_loc_b200.distributed import all_gather_rows
 
     def step_device():
         rays = {"rays_o": ro_d, "rays_d": rd_d, "depth_range": data["depth_range"][0]}
         out = model.render_rays(data, rays)
         if world > 1:
-            f = out["feat"]
-            if Rl < per:
-                f = torch.cat([f, torch.zeros(per - Rl, 192, device=dev)])
-            dist.all_gather_into_tensor(feat_all, f.contiguous())
+            out["feat_all"] = all_gather_rows(out["feat"], R_total)  # the one exchange step
         return out
 
     host_out = {}
@@ -194,10 +191,7 @@ def run_b200(args):
                 "depth_range": data["depth_range"][0]}
         out = model.render_rays(data, rays)
         if world > 1:
-            f = out["feat"]
-            if Rl < per:
-                f = torch.cat([f, torch.zeros(per - Rl, 192, device=dev)])
-            dist.all_gather_into_tensor(feat_all, f.contiguous())
+            all_gather_rows(out["feat"], R_total)
         nbytes = 0
         for k, v in out.items():
             if k not in host_out:
