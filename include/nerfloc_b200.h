@@ -142,6 +142,10 @@ int nlb_fine_windows(const float* packed_match_weights, int C, const float* feat
 int nlb_fine_match(const float* packed_match_weights, int C, const float* f0, const float* f1, int64_t Mm,
                    const float* mkps2d_c, float* expec_f, float* mkps2d_f, void* stream);
 
+/* ---- self-test of the tcgen05 building blocks: C[128,128] = A[128,K] * W[128,K]^T, K multiple of 8 <= 64;
+ * mode 0 = single-pass tf32, 1 = 3xTF32 (fp32-equivalent) -------------------------------------------------------------- */
+int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

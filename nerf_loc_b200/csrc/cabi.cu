@@ -90,6 +90,7 @@ struct Carver {
 
 }  // namespace nlb
 
+namespace nlb { int launch_tc_test(const float* A, const float* W, int K, int mode, float* C, cudaStream_t st); }
 using namespace nlb;
 
 extern "C" {
@@ -295,6 +296,11 @@ int nlb_fine_match(const float* packed, int C, const float* f0, const float* f1,
   if (Mm <= 0) return 0;
   if (!packed || !f0 || !f1 || !mkps2d_c || !expec_f || !mkps2d_f) return set_error("nlb_fine_match: NULL pointer");
   return launch_fine_match(match_weights_view(packed, C), f0, f1, Mm, mkps2d_c, expec_f, mkps2d_f, (cudaStream_t)stream);
+}
+
+int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C, void* stream) {
+  if (!A || !W || !C) return set_error("nlb_debug_tc_gemm: NULL pointer");
+  return launch_tc_test(A, W, K, mode, C, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,325 @@
+// neighbor_kernel: the K=8 support-point MLP + attention of ConditionalNeRF.query (conditional_nerf/model.py:371-427).
+//
+// A CTA owns 16 samples = 128 (sample, neighbour) rows.  The three 128-row layers of base_mlp run on the 5th-generation
+// tensor cores (tcgen05.mma kind::tf32, 3xTF32 split operands, accumulator in TMEM) through the warp-specialised pipeline
+// of tc_pipe.cuh: warps 0-7 produce the A operand / run the epilogues, warp 8 streams the pre-split weight tiles with bulk
+// copies and issues the MMAs.  The small per-sample pieces (query / folded key+value projections, softmax over the 8
+// neighbours, output projection, LayerNorm, neighbour weights) stay on the fp32 tile GEMM.
+//
+// Exact rewrites used here: layer 1 = gathered per-frame `sup_pre` + W1[:,195:285] [PE | ray_diff_fc];
+// attention with a broadcast query (K/V projections folded, one distinct `feature` row per sample).
+#include <float.h>
+#include "nlb_common.cuh"
+#include "nlb_internal.h"
+#include "render_kernels.h"
+#include "tc_pipe.cuh"
+
+namespace nlb {
+
+constexpr int NB_LDH = 132;
+constexpr int NB_TP = 16;                      // samples per CTA
+constexpr uint32_t NB_SBO1 = 96u * 32u;        // A operand of layer 1: K = 96
+constexpr uint32_t NB_SBO2 = 128u * 32u;       // A operand of layers 2, 3: K = 128
+// shared-memory map (bytes)
+constexpr uint32_t NB_STG = 0;                                   // 4 x 16 KB weight stages | later: fp32 staging + q~/ctx
+constexpr uint32_t NB_STG_BYTES = 67584;                         // >= 65536 and >= 32768 + 64*132*4
+constexpr uint32_t NB_ACT = NB_STG + NB_STG_BYTES;               // A hi (64 KB) | A lo (64 KB) | later: pf [128][132] fp32
+constexpr uint32_t NB_ACT_BYTES = 131072;
+constexpr uint32_t NB_SMALL = NB_ACT + NB_ACT_BYTES;             // sAgg, sQ, sO [16][132], sSc [512], sD [256]
+constexpr uint32_t NB_SMALL_BYTES = (3 * NB_TP * NB_LDH + 512 + 256) * 4;
+constexpr uint32_t NB_IDX = NB_SMALL + NB_SMALL_BYTES;           // int idx[128]
+constexpr uint32_t NB_SYNC = NB_IDX + 512;                       // tc::Sync + tc::Layer[3]
+constexpr uint32_t NB_SMEM_BYTES = NB_SYNC + 256 + 3 * 64;
+
+__global__ void __launch_bounds__(NT + 32, 1)
+neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int K,
+                const int* __restrict__ knn_idx, const float* __restrict__ knn_d2, const float* __restrict__ agg_in,
+                float* __restrict__ fagg_out, float* __restrict__ feature_out, float* __restrict__ weights_out) {
+  extern __shared__ __align__(1024) unsigned char smraw[];
+  unsigned char* stg = smraw + NB_STG;
+  unsigned char* actHi = smraw + NB_ACT;
+  unsigned char* actLo = actHi + 65536;
+  float* sA = reinterpret_cast<float*>(smraw + NB_ACT);           // [128][132] after layer 3
+  float* sB = reinterpret_cast<float*>(smraw + NB_STG);           // fp32 staging ring (after the tensor-core phase)
+  float* sQT = sB + STAGE_FLOATS;                                  // [64][132]
+  float* sAgg = reinterpret_cast<float*>(smraw + NB_SMALL);
+  float* sQ = sAgg + NB_TP * NB_LDH;
+  float* sO = sQ + NB_TP * NB_LDH;
+  float* sSc = sO + NB_TP * NB_LDH;
+  float* sD = sSc + 512;
+  int* sIdx = reinterpret_cast<int*>(smraw + NB_IDX);
+  tc::Sync& sy = *reinterpret_cast<tc::Sync*>(smraw + NB_SYNC);
+  tc::Layer* layers = reinterpret_cast<tc::Layer*>(smraw + NB_SYNC + 256);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t tmem = tc::setup(sy, warp, lane, 128);
+
+  if (warp == 8) {
+    // ------------------------------------------------ controller -------------------------------------------------------
+    if (lane == 0) {
+      const uint32_t hi = tc::smem_u32(actHi), lo = tc::smem_u32(actLo);
+      layers[0] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w1b), hi, lo, NB_SBO1, 6, 128, 0};
+      layers[1] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w2), hi, lo, NB_SBO2, 8, 128, 0};
+      layers[2] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w3), hi, lo, NB_SBO2, 8, 128, 0};
+      tc::controller(sy, stg, tmem, layers, 3);
+    }
+  } else {
+    // ------------------------------------------------ compute warps ------------------------------------------------------
+    const int64_t n0 = (int64_t)blockIdx.x * NB_TP;
+    const int np = (int)min((int64_t)NB_TP, N - n0);
+    const float range = sc.far_ - sc.near_;
+    uint32_t d_par = 0;
+
+    // ---- phase 0: per (sample, neighbour) geometry -> A operand of layer 1 (PE 63 | ray_diff_fc 27 | 0 x 6) ----------
+    if (tid < 128) {
+      const int p = tid >> 3, k = tid & 7;
+      float xr[96];
+      int id = 0;
+      if (p < np && k < K) {
+        const int64_t n = n0 + p;
+        id = knn_idx[n * K + k];
+        sD[tid] = knn_d2[n * K + k];
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8 + 4));
+        sD[128 + tid] = g1.z;  // confidence
+        float x, y, z;
+        if (ps.xyz) {
+          x = ps.xyz[n * 3]; y = ps.xyz[n * 3 + 1]; z = ps.xyz[n * 3 + 2];
+        } else {
+          const int64_t r = n / ps.S;
+          const float t = ps.z[n - r * ps.S];
+          x = __fadd_rn(ps.rays_o[r * 3 + 0], __fmul_rn(ps.rays_d[r * 3 + 0], t));
+          y = __fadd_rn(ps.rays_o[r * 3 + 1], __fmul_rn(ps.rays_d[r * 3 + 1], t));
+          z = __fadd_rn(ps.rays_o[r * 3 + 2], __fmul_rn(ps.rays_d[r * 3 + 2], t));
+        }
+        float dx, dy, dz;
+        if (ps.dirs) {
+          dx = ps.dirs[n * 3]; dy = ps.dirs[n * 3 + 1]; dz = ps.dirs[n * 3 + 2];
+        } else if (ps.rays_d && !ps.xyz) {
+          const int64_t r = n / ps.S;
+          dx = ps.rays_d[r * 3]; dy = ps.rays_d[r * 3 + 1]; dz = ps.rays_d[r * 3 + 2];
+        } else {  // direction=None: the nearest neighbour's own direction (model.py:391-392)
+          const int id0 = knn_idx[n * K];
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8));
+          const float4 h1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8 + 4));
+          dx = h0.w; dy = h1.x; dz = h1.y;
+        }
+        const float off[3] = {__fdiv_rn(__fsub_rn(x, g0.x), range), __fdiv_rn(__fsub_rn(y, g0.y), range),
+                              __fdiv_rn(__fsub_rn(z, g0.z), range)};
+        xr[0] = off[0]; xr[1] = off[1]; xr[2] = off[2];
+        float f = 1.f;
+#pragma unroll
+        for (int i = 0; i < 10; ++i) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float s, co;
+            sincosf(off[c] * f, &s, &co);
+            xr[3 + i * 6 + c] = s;
+            xr[3 + i * 6 + 3 + c] = co;
+          }
+          f *= 2.f;
+        }
+        // ray difference (model.py:396-399) and ray_diff_fc (4 -> 16 -> 27, LeakyReLU)
+        const float nx = g0.w, ny = g1.x, nz = g1.y;
+        const float rx = dx - nx, ry = dy - ny, rz = dz - nz;
+        const float rn = sqrtf(rx * rx + ry * ry + rz * rz) + 1e-8f;
+        const float rd[4] = {rx / rn, ry / rn, rz / rn, dx * nx + dy * ny + dz * nz};
+        float h1[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) {
+          float a = __ldg(w.rd1_b + o);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) a = fmaf(__ldg(w.rd1 + o * 4 + c), rd[c], a);
+          h1[o] = leaky(a);
+        }
+#pragma unroll
+        for (int o = 0; o < 27; ++o) {
+          float a = __ldg(w.rd2_b + o);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) a = fmaf(__ldg(w.rd2 + o * 16 + c), h1[c], a);
+          xr[63 + o] = leaky(a);
+        }
+#pragma unroll
+        for (int c = 90; c < 96; ++c) xr[c] = 0.f;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 96; ++c) xr[c] = 0.f;
+        sD[tid] = 1.f; sD[128 + tid] = 0.f;
+        id = -1;
+      }
+      sIdx[tid] = id;
+#pragma unroll
+      for (int c = 0; c < 96; c += 4) tc::store_split4(actHi, actLo, tid, c, NB_SBO1, xr[c], xr[c + 1], xr[c + 2], xr[c + 3]);
+    }
+    for (int i = tid; i < NB_TP * W_HID; i += NT) {
+      const int p = i >> 7, c = i & 127;
+      sAgg[p * NB_LDH + c] = p < np ? agg_in[(n0 + p) * W_HID + c] : 0.f;
+    }
+    tc::a_ready(sy);
+
+    // ---- base_mlp on the tensor cores: three 128 x 128 layers, epilogues out of TMEM -------------------------------------
+    const int row = (warp & 3) * 32 + lane;            // TMEM lane == (sample, neighbour) row
+    const int c0 = (warp >> 2) * 64;                    // this thread's 64 output columns
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    cta_sync();  // sIdx visible
+    for (int layer = 0; layer < 3; ++layer) {
+      tc::wait_d(sy, d_par);
+      const int id = sIdx[row];
+#pragma unroll
+      for (int cc = 0; cc < 64; cc += 32) {
+        float v[32];
+        tc::tmem_ld32(trow + (uint32_t)(c0 + cc), v);
+        if (layer == 0) {
+          // + per-frame precomputed support part of layer 1 (includes the bias)
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (id >= 0) s4 = __ldg(reinterpret_cast<const float4*>(sc.sup_pre + (size_t)id * W_HID + c0 + cc + j));
+            v[j] += s4.x; v[j + 1] += s4.y; v[j + 2] += s4.z; v[j + 3] += s4.w;
+          }
+        } else {
+          const float* bias = layer == 1 ? w.b2 : w.b3;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c0 + cc + j));
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = leaky(v[j]);
+        if (layer < 2) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            tc::store_split4(actHi, actLo, row, c0 + cc + j, NB_SBO2, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          // every thread must have finished reading TMEM / the MMAs are done: pf goes out as plain fp32 rows
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(sA + row * NB_LDH + c0 + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+      }
+      if (layer < 2) tc::a_ready(sy);
+    }
+    tc::fence_before_sync();
+    cta_sync();
+
+    // ---- q = Wq agg ; q~_h = Wk_h^T q_h ------------------------------------------------------------------------------------
+    tile_gemm<1, 8, 128, false>(plainA(sAgg, NB_LDH), NB_TP, w.wq, 128, 128, sB,
+                                [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v; });
+    for (int hd = 0; hd < 4; ++hd)
+      tile_gemm<1, 8, 128, false>(plainA(sQ + 32 * hd, NB_LDH), NB_TP, w.wk + 32 * hd * 128, 128, 32, sB,
+                                  [&](int r, int c, float v) { sQT[(r * 4 + hd) * NB_LDH + c] = v; });
+    cta_sync();
+    // ---- attention scores + softmax over the K neighbours -----------------------------------------------------------------
+    for (int it = 0; it < 2; ++it) {
+      const int i = tid + it * NT;  // (p, h, k), k fastest
+      const int p = i >> 5, hd = (i >> 3) & 3, k = i & 7;
+      const float* qv = sQT + (p * 4 + hd) * NB_LDH;
+      const float* kv = sA + (p * 8 + k) * NB_LDH;
+      float a = 0.f;
+#pragma unroll 8
+      for (int c = 0; c < 128; c += 4) {
+        const float4 q4 = *reinterpret_cast<const float4*>(qv + c);
+        const float4 k4 = *reinterpret_cast<const float4*>(kv + c);
+        a = fmaf(q4.x, k4.x, a); a = fmaf(q4.y, k4.y, a); a = fmaf(q4.z, k4.z, a); a = fmaf(q4.w, k4.w, a);
+      }
+      a *= 0.17677669529663687f;  // 1/sqrt(d_k = 32)
+      if (k >= K) a = -FLT_MAX;
+      float m = a;
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+      const float e = k < K ? expf(a - m) : 0.f;
+      float s = e;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      sSc[i] = e / s;
+    }
+    cta_sync();
+    // ---- per-head context = sum_k a_k * point_feature_k (overwrites q~) -----------------------------------------------------
+    {
+      const int ph = tid >> 2, cb = (tid & 3) * 32;
+      const int p = ph >> 2;
+      float acc[32];
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+      for (int k = 0; k < 8; ++k) {
+        const float a = sSc[ph * 8 + k];
+        const float* kv = sA + (p * 8 + k) * NB_LDH + cb;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 v4 = *reinterpret_cast<const float4*>(kv + c);
+          acc[c] = fmaf(a, v4.x, acc[c]); acc[c + 1] = fmaf(a, v4.y, acc[c + 1]);
+          acc[c + 2] = fmaf(a, v4.z, acc[c + 2]); acc[c + 3] = fmaf(a, v4.w, acc[c + 3]);
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) sQT[ph * NB_LDH + cb + c] = acc[c];
+    }
+    // ---- o_h = Wv_h ctx_h ; fc + residual -------------------------------------------------------------------------------------
+    for (int hd = 0; hd < 4; ++hd)
+      tile_gemm<1, 4, 32, false>(plainA(sQT + hd * NB_LDH, 4 * NB_LDH), NB_TP, w.wv + 32 * hd, 128, 128, sB,
+                                 [&](int r, int c, float v) { sO[r * NB_LDH + 32 * hd + c] = v; });
+    tile_gemm<1, 8, 128, false>(plainA(sO, NB_LDH), NB_TP, w.wfc, 128, 128, sB,
+                                [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v + sAgg[r * NB_LDH + c]; });
+    cta_sync();
+    // ---- LayerNorm(eps 1e-6), neighbour weights, weighted sum -------------------------------------------------------------------
+    if (tid < NB_TP) {
+      // weights = (1/clamp(dist)) * softmax_K(corr) * conf, normalised (model.py:415-426); corr rows are identical
+      // across K, so softmax_K(corr) is exactly 1/K.
+      float wk[8], s = 0.f;
+      const float corr = 1.f / (float)K;
+      for (int k = 0; k < 8; ++k) {
+        float v = 0.f;
+        if (k < K) {
+          v = 1.f / fmaxf(sqrtf(sD[tid * 8 + k]), 1e-8f);
+          v *= corr;
+          v *= sD[128 + tid * 8 + k];
+        }
+        wk[k] = v; s += v;
+      }
+      s = fmaxf(s, 1e-8f);
+      for (int k = 0; k < 8; ++k) {
+        wk[k] = wk[k] / s;
+        sSc[tid * 8 + k] = wk[k];
+        if (weights_out && tid < np && k < K) weights_out[(n0 + tid) * K + k] = wk[k];
+      }
+    }
+    for (int p = warp; p < NB_TP; p += NT / 32) {
+      const float4 y = *reinterpret_cast<const float4*>(sQ + p * NB_LDH + lane * 4);
+      const float mean = warp_sum(y.x + y.y + y.z + y.w) * (1.f / 128.f);
+      const float d0 = y.x - mean, d1 = y.y - mean, d2 = y.z - mean, d3 = y.w - mean;
+      const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / 128.f);
+      const float rstd = 1.f / sqrtf(var + 1e-6f);
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w.ln_g + lane * 4));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(w.ln_b + lane * 4));
+      float4 f;
+      f.x = d0 * rstd * g.x + b.x; f.y = d1 * rstd * g.y + b.y; f.z = d2 * rstd * g.z + b.z; f.w = d3 * rstd * g.w + b.w;
+      *reinterpret_cast<float4*>(sO + p * NB_LDH + lane * 4) = f;
+    }
+    cta_sync();
+    for (int i = tid; i < np * W_HID; i += NT) {
+      const int p = i >> 7, c = i & 127;
+      const float f = sO[p * NB_LDH + c];
+      float a = 0.f;
+      for (int k = 0; k < K; ++k) a += f * sSc[p * 8 + k];
+      fagg_out[(n0 + p) * W_HID + c] = a;
+      if (feature_out) feature_out[(n0 + p) * W_HID + c] = f;
+    }
+  }
+  tc::teardown(sy, warp, tmem, 128);
+}
+
+int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
+                    const float* d2, const float* agg, float* fagg, float* feature, float* weights, cudaStream_t st) {
+  if (N <= 0) return 0;
+  if (K < 1 || K > 8) return set_error("neighbor: K must be in 1..8");
+  cudaError_t e = cudaFuncSetAttribute(neighbor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NB_SMEM_BYTES);
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  const unsigned grid = (unsigned)((N + NB_TP - 1) / NB_TP);
+  neighbor_kernel<<<grid, NT + 32, NB_SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, agg, fagg, feature, weights);
+  return check_launch("neighbor_kernel");
+}
+
+}  // namespace nlb

@@ -3,6 +3,8 @@
 #include "pack.cu"
 #include "knn.cu"
 #include "render_point.cu"
+#include "neighbor_tc.cu"
 #include "render_ray.cu"
 #include "match.cu"
+#include "tc_test.cu"
 #include "cabi.cu"

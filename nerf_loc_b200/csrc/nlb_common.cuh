@@ -19,6 +19,10 @@ constexpr int NT = 256;  // threads per CTA for all tile kernels
 constexpr int KT = 32;   // K-tile of the weight staging ring
 constexpr int STAGE_FLOATS = 2 * KT * 128;  // two stages of [KT][<=128]
 
+// Barrier over the NT compute threads of a CTA (named barrier 1).  Kernels that add a tcgen05 controller warp on top
+// of the NT compute threads keep that warp out of these barriers; for plain NT-thread kernels it is a __syncthreads.
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
@@ -41,9 +45,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Block-wide sum over NT threads; `red` is >= 8 floats of shared scratch.  All threads get the result.
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
-  __syncthreads();
+  cta_sync();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-  __syncthreads();
+  cta_sync();
   float t = 0.f;
 #pragma unroll
   for (int i = 0; i < NT / 32; ++i) t += red[i];
@@ -84,7 +88,7 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  __syncthreads();  // previous users of sB (and producers of A) are done
+  cta_sync();  // previous users of sB (and producers of A) are done
   for (int c = tid; c < CHUNKS; c += NT) {
     const int k = c / (COLS / 4), n4 = c % (COLS / 4);
     cp_async16(sB + k * COLS + n4 * 4, Wt + (size_t)k * ldb + n4 * 4);
@@ -104,7 +108,7 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
         *p = v;
       }
     }
-    __syncthreads();
+    cta_sync();
     if (kt + 1 < nkt) {
       float* dst = sB + ((kt + 1) & 1) * (KT * COLS);
       const float* src = Wt + (size_t)(kt + 1) * KT * ldb;
@@ -161,7 +165,7 @@ __device__ __forceinline__ void tile_gemm(const ASrc A, const int rows, const fl
     const bool active = r0 < rows;
     float acc[TM][TN];
     gemm_core<TM, TN, COLS, false>(A, r0, active, Wt, ldb, K, sB, nullptr, acc);
-    if (SYNC_BEFORE_EPI) __syncthreads();
+    if (SYNC_BEFORE_EPI) cta_sync();
     if (active) {
 #pragma unroll
       for (int i = 0; i < TM; ++i)

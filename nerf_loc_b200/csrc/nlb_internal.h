@@ -55,6 +55,8 @@ struct RenderW {
   const float *w2, *b2, *w3, *b3;  // [128][128], [128]
   const float *wq, *wk, *wv, *wfc; // wq^T, wk natural ([h*32+j][c]), wv^T, wfc^T; all [128][128]
   const float *ln_g, *ln_b;     // [128]
+  // tensor-core (3xTF32) copies of the three 128-row base_mlp layers: per K-tile of 16, [hi | lo] canonical K-major tiles
+  const float *tc_w1b, *tc_w2, *tc_w3;
   // ray stage
   UnetLayer u[7];               // conv1, conv2, conv3, trans_conv3, trans_conv2, trans_conv1, conv_out
   const float *sig_w, *sig_b;   // [128], [1]

@@ -60,6 +60,7 @@ static RenderW layout(const float* base, int S, size_t* total) {
   w.w3 = a.take(128 * 128); w.b3 = a.take(128);
   w.wq = a.take(128 * 128); w.wk = a.take(128 * 128); w.wv = a.take(128 * 128); w.wfc = a.take(128 * 128);
   w.ln_g = a.take(128); w.ln_b = a.take(128);
+  w.tc_w1b = a.take(2 * 128 * 96); w.tc_w2 = a.take(2 * 128 * 128); w.tc_w3 = a.take(2 * 128 * 128);
   for (int l = 0; l < 7; ++l) {
     const int sl = S > 0 ? S / UN_SDIV[l] : 0;
     w.u[l].w = a.take((size_t)3 * UN_CIN[l] * UN_COUT[l]);
@@ -107,6 +108,22 @@ __global__ void pack_conv_kernel(float* dst, const float* __restrict__ src, int 
   dst[i] = transposed ? src[((size_t)ci * Cout + co) * 3 + t] : src[((size_t)co * Cin + ci) * 3 + t];
 }
 
+// tensor-core B operand: W [N][src_ld] (reference layout, K-major) -> per K-tile of 16: hi tile then lo tile, each the
+// canonical no-swizzle K-major layout (8-row core matrices of 16 bytes, 8-row groups 512 bytes apart); 3xTF32 split.
+__global__ void pack_tcb_kernel(float* dst, const float* __restrict__ src, int N, int Kp, int src_ld, int src_off, int Kv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * Kp) return;
+  const int n = i / Kp, k = i % Kp;
+  const float x = k < Kv ? src[(size_t)n * src_ld + src_off + k] : 0.f;
+  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  const float lo = x - hi;
+  const int kt = k / 16, kl = k % 16;
+  const size_t base = (size_t)kt * (2 * N * 16);
+  const size_t off = (size_t)(n / 8) * 128 + (kl / 4) * 32 + (n % 8) * 4 + (kl % 4);
+  dst[base + off] = hi;
+  dst[base + (size_t)N * 16 + off] = lo;
+}
+
 namespace {
 struct Packer {
   const float* const* p;
@@ -118,6 +135,10 @@ struct Packer {
   }
   void c(const float* dst, int src, int n, int dst_off = 0) {
     pack_copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst) + dst_off, p[src], n);
+  }
+  void tcb(const float* dst, int src, int N, int Kp, int src_ld, int src_off, int Kv) {
+    const int n = N * Kp;
+    pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv);
   }
   void conv(const float* dst, int src, int Cin, int Cout, int ntaps, int t0, int t1, int t2, bool tr) {
     const int n = ntaps * Cin * Cout;
@@ -169,6 +190,9 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
   k.t(w.wv, AT_V, 128, 128, 128, 0, 128);
   k.t(w.wfc, AT_FC, 128, 128, 128, 0, 128);
   k.c(w.ln_g, AT_LNG, 128);  k.c(w.ln_b, AT_LNB, 128);
+  k.tcb(w.tc_w1b, BM0_W, 128, 96, 285, 195, 90);
+  k.tcb(w.tc_w2, BM2_W, 128, 128, 128, 0, 128);
+  k.tcb(w.tc_w3, BM4_W, 128, 128, 128, 0, 128);
   // --- RayUnet ---
   if (S > 0) {
     for (int l = 0; l < 7; ++l) {

@@ -151,7 +151,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       for (int i = 0; i < RI_N; ++i) ri[i] = 0.f;
     }
   }
-  __syncthreads();
+  cta_sync();
 
   // ---- phase 2: 32-channel visibility features (border padding), one warp per row ------------------------------
   for (int r = warp; r < 128; r += NT / 32) {
@@ -180,7 +180,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       sH[r * LDH + 32 * hd + c] = elu(v + __ldg(w.dec2_b + 32 * hd + c));
     });
   }
-  __syncthreads();
+  cta_sync();
   if (tid < rows) {
     const float* hrow = sH + tid * LDH;
     float o[6];
@@ -206,7 +206,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     const float vis = (1.f - cdf0) * aw + (1.f - cdf1) * (1.f - aw);
     ri[RI_VIS] = vis * ri[RI_VALID];
   }
-  __syncthreads();
+  cta_sync();
 
   // ---- phase 4: per-sample view weights --------------------------------------------------------------------------
   if (tid < np) {
@@ -234,7 +234,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     for (int k = 393; k < 416; ++k) g[k] = 0.f;
     if (nvalid_out) nvalid_out[n0 + tid] = (unsigned char)nval;
   }
-  __syncthreads();  // sH (arena) is dead from here on
+  cta_sync();  // sH (arena) is dead from here on
 
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
   for (int r = warp; r < 128; r += NT / 32) {
@@ -299,7 +299,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       for (int k = lane; k < LDF; k += 32) frow[k] = 0.f;
     }
   }
-  __syncthreads();
+  cta_sync();
   if (mvf_out) {
     for (int i = tid; i < rows * C_RGBF; i += NT) {
       const int r = i / C_RGBF, c = i - r * C_RGBF;
@@ -334,227 +334,6 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     tile_gemm<4, 4, 32, false>(plainA(sF, LDF), 128, w.bl1v, 32, 224, sB, [&](int r, int c, float v) {
       if (r < rows) partial_out[(n0 * V + r) * 32 + c] = v + __ldg(w.bl1_b + c);
     });
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// neighbour MLP + attention
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int LDP = 100;  // PE(63) + ray_diff_fc(27) -> 96 (+4)
-constexpr int NBR_SMEM_FLOATS = STAGE_FLOATS + 128 * LDH + 128 * LDP + 3 * TP_MAX * LDH + 512 + 128 * 2 + TP_MAX * 4;
-
-__global__ void __launch_bounds__(NT, 1)
-neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int K,
-                const int* __restrict__ knn_idx, const float* __restrict__ knn_d2, const float* __restrict__ agg_in,
-                float* __restrict__ fagg_out, float* __restrict__ feature_out, float* __restrict__ weights_out) {
-  extern __shared__ __align__(16) float smem[];
-  float* sB = smem;
-  float* sA = sB + STAGE_FLOATS;        // [128][LDH]  neighbour activations
-  float* sX = sA + 128 * LDH;           // [128][LDP]  PE | ray_diff_fc ; later q~ / context [64][LDH]
-  float* sAgg = sX + 128 * LDP;         // [16][LDH]
-  float* sQ = sAgg + TP_MAX * LDH;      // [16][LDH]
-  float* sO = sQ + TP_MAX * LDH;        // [16][LDH]
-  float* sSc = sO + TP_MAX * LDH;       // [16][4][8]
-  float* sD = sSc + 512;                // [128] sqrt-dist, [128] conf
-  float* sWs = sD + 256;                // [16][4]
-  float* sQT = sX;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t n0 = (int64_t)blockIdx.x * TP_MAX;
-  const int np = (int)min((int64_t)TP_MAX, N - n0);
-  const float inv_range = sc.far_ - sc.near_;
-
-  // ---- phase 0: per (sample, neighbour) geometry: positional encoding and ray difference -------------------------
-  if (tid < 128) {
-    const int p = tid >> 3, k = tid & 7;
-    float* xr = sX + tid * LDP;
-    if (p < np && k < K) {
-      const int64_t n = n0 + p;
-      const int id = knn_idx[n * K + k];
-      sD[tid] = knn_d2[n * K + k];
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8 + 4));
-      sD[128 + tid] = g1.z;  // confidence
-      float x, y, z;
-      load_point(ps, n, x, y, z);
-      float dx, dy, dz;
-      if (ps.dirs) {
-        dx = ps.dirs[n * 3]; dy = ps.dirs[n * 3 + 1]; dz = ps.dirs[n * 3 + 2];
-      } else if (ps.rays_d && !ps.xyz) {
-        const int64_t r = n / ps.S;
-        dx = ps.rays_d[r * 3]; dy = ps.rays_d[r * 3 + 1]; dz = ps.rays_d[r * 3 + 2];
-      } else {  // direction=None: the nearest neighbour's own direction (model.py:391-392)
-        const int id0 = knn_idx[n * K];
-        const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8));
-        const float4 h1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8 + 4));
-        dx = h0.w; dy = h1.x; dz = h1.y;
-      }
-      const float off[3] = {__fdiv_rn(__fsub_rn(x, g0.x), inv_range), __fdiv_rn(__fsub_rn(y, g0.y), inv_range),
-                            __fdiv_rn(__fsub_rn(z, g0.z), inv_range)};
-      xr[0] = off[0]; xr[1] = off[1]; xr[2] = off[2];
-      float f = 1.f;
-#pragma unroll
-      for (int i = 0; i < 10; ++i) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float s, co;
-          sincosf(off[c] * f, &s, &co);
-          xr[3 + i * 6 + c] = s;
-          xr[3 + i * 6 + 3 + c] = co;
-        }
-        f *= 2.f;
-      }
-      // ray difference (model.py:396-399) and ray_diff_fc (4 -> 16 -> 27, LeakyReLU)
-      const float nx = g0.w, ny = g1.x, nz = g1.y;
-      float rx = dx - nx, ry = dy - ny, rz = dz - nz;
-      const float rn = sqrtf(rx * rx + ry * ry + rz * rz) + 1e-8f;
-      const float rd[4] = {rx / rn, ry / rn, rz / rn, dx * nx + dy * ny + dz * nz};
-      float h1[16];
-#pragma unroll
-      for (int o = 0; o < 16; ++o) {
-        float a = __ldg(w.rd1_b + o);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) a = fmaf(__ldg(w.rd1 + o * 4 + c), rd[c], a);
-        h1[o] = leaky(a);
-      }
-      for (int o = 0; o < 27; ++o) {
-        float a = __ldg(w.rd2_b + o);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) a = fmaf(__ldg(w.rd2 + o * 16 + c), h1[c], a);
-        xr[63 + o] = leaky(a);
-      }
-#pragma unroll
-      for (int c = 90; c < 96; ++c) xr[c] = 0.f;
-    } else {
-      for (int c = 0; c < 96; ++c) xr[c] = 0.f;
-      sD[tid] = 1.f; sD[128 + tid] = 0.f;
-    }
-  }
-  // ---- phase 1: gather the per-frame precomputed support part of layer 1 ------------------------------------------
-  for (int r = warp; r < 128; r += NT / 32) {
-    const int p = r >> 3, k = r & 7;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p < np && k < K) {
-      const int id = knn_idx[(n0 + p) * K + k];
-      v = __ldg(reinterpret_cast<const float4*>(sc.sup_pre + (size_t)id * W_HID + lane * 4));
-    }
-    *reinterpret_cast<float4*>(sA + r * LDH + lane * 4) = v;
-  }
-  for (int i = tid; i < TP_MAX * W_HID; i += NT) {
-    const int p = i >> 7, c = i & 127;
-    sAgg[p * LDH + c] = p < np ? agg_in[(n0 + p) * W_HID + c] : 0.f;
-  }
-  // ---- phase 2/3: base_mlp ------------------------------------------------------------------------------------------
-  tile_gemm<8, 8, 128, false>(plainA(sX, LDP), 128, w.w1b, 128, 96, sB,
-                              [&](int r, int c, float v) { sA[r * LDH + c] = leaky(v + sA[r * LDH + c]); });
-  tile_gemm<8, 8, 128, true>(plainA(sA, LDH), 128, w.w2, 128, 128, sB,
-                             [&](int r, int c, float v) { sA[r * LDH + c] = leaky(v + __ldg(w.b2 + c)); });
-  tile_gemm<8, 8, 128, true>(plainA(sA, LDH), 128, w.w3, 128, 128, sB,
-                             [&](int r, int c, float v) { sA[r * LDH + c] = leaky(v + __ldg(w.b3 + c)); });
-  // ---- phase 4: q = Wq agg ; phase 5: q~_h = Wk_h^T q_h -------------------------------------------------------------
-  tile_gemm<1, 8, 128, false>(plainA(sAgg, LDH), TP_MAX, w.wq, 128, 128, sB,
-                              [&](int r, int c, float v) { sQ[r * LDH + c] = v; });
-  for (int hd = 0; hd < 4; ++hd)
-    tile_gemm<1, 8, 128, false>(plainA(sQ + 32 * hd, LDH), TP_MAX, w.wk + 32 * hd * 128, 128, 32, sB,
-                                [&](int r, int c, float v) { sQT[(r * 4 + hd) * LDH + c] = v; });
-  __syncthreads();
-  // ---- phase 6: attention scores + softmax over the K neighbours ----------------------------------------------------
-  for (int it = 0; it < 2; ++it) {
-    const int i = tid + it * NT;  // (p, h, k), k fastest
-    const int p = i >> 5, hd = (i >> 3) & 3, k = i & 7;
-    const float* qv = sQT + (p * 4 + hd) * LDH;
-    const float* kv = sA + (p * 8 + k) * LDH;
-    float a = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < 128; c += 4) {
-      const float4 q4 = *reinterpret_cast<const float4*>(qv + c);
-      const float4 k4 = *reinterpret_cast<const float4*>(kv + c);
-      a = fmaf(q4.x, k4.x, a); a = fmaf(q4.y, k4.y, a); a = fmaf(q4.z, k4.z, a); a = fmaf(q4.w, k4.w, a);
-    }
-    a *= 0.17677669529663687f;  // 1/sqrt(d_k = 32)
-    if (k >= K) a = -FLT_MAX;
-    float m = a;
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-    const float e = k < K ? expf(a - m) : 0.f;
-    float s = e;
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    sSc[i] = e / s;
-  }
-  __syncthreads();
-  // ---- phase 7: per-head context = sum_k a_k * point_feature_k (overwrites q~) --------------------------------------
-  {
-    const int ph = tid >> 2, c0 = (tid & 3) * 32;
-    const int p = ph >> 2;
-    float acc[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-    for (int k = 0; k < 8; ++k) {
-      const float a = sSc[ph * 8 + k];
-      const float* kv = sA + (p * 8 + k) * LDH + c0;
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        const float4 v4 = *reinterpret_cast<const float4*>(kv + c);
-        acc[c] = fmaf(a, v4.x, acc[c]); acc[c + 1] = fmaf(a, v4.y, acc[c + 1]);
-        acc[c + 2] = fmaf(a, v4.z, acc[c + 2]); acc[c + 3] = fmaf(a, v4.w, acc[c + 3]);
-      }
-    }
-    __syncthreads();  // every score has been consumed from sQT's neighbours; q~ itself is dead
-#pragma unroll
-    for (int c = 0; c < 32; ++c) sQT[ph * LDH + c0 + c] = acc[c];
-  }
-  // ---- phase 8: o_h = Wv_h ctx_h ; phase 9: fc + residual ------------------------------------------------------------
-  for (int hd = 0; hd < 4; ++hd)
-    tile_gemm<1, 4, 32, false>(plainA(sQT + hd * LDH, 4 * LDH), TP_MAX, w.wv + 32 * hd, 128, 128, sB,
-                               [&](int r, int c, float v) { sO[r * LDH + 32 * hd + c] = v; });
-  tile_gemm<1, 8, 128, false>(plainA(sO, LDH), TP_MAX, w.wfc, 128, 128, sB,
-                              [&](int r, int c, float v) { sQ[r * LDH + c] = v + sAgg[r * LDH + c]; });
-  __syncthreads();
-  // ---- phase 10: LayerNorm(eps 1e-6), neighbour weights, weighted sum -------------------------------------------------
-  if (tid < TP_MAX) {
-    // weights = (1/clamp(dist)) * softmax_K(corr) * conf, normalised (model.py:415-426); corr rows are identical
-    // across K, so softmax_K(corr) is exactly 1/K.
-    float wk[8], s = 0.f;
-    const float corr = 1.f / (float)K;
-    for (int k = 0; k < 8; ++k) {
-      float v = 0.f;
-      if (k < K) {
-        v = 1.f / fmaxf(sqrtf(sD[tid * 8 + k]), 1e-8f);
-        v *= corr;
-        v *= sD[128 + tid * 8 + k];
-      }
-      wk[k] = v; s += v;
-    }
-    s = fmaxf(s, 1e-8f);
-    for (int k = 0; k < 8; ++k) {
-      wk[k] = wk[k] / s;
-      sSc[tid * 8 + k] = wk[k];
-      if (weights_out && tid < np && k < K) weights_out[(n0 + tid) * K + k] = wk[k];
-    }
-  }
-  for (int p = warp; p < TP_MAX; p += NT / 32) {
-    const float4 y = *reinterpret_cast<const float4*>(sQ + p * LDH + lane * 4);
-    const float mean = warp_sum(y.x + y.y + y.z + y.w) * (1.f / 128.f);
-    const float d0 = y.x - mean, d1 = y.y - mean, d2 = y.z - mean, d3 = y.w - mean;
-    const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / 128.f);
-    const float rstd = 1.f / sqrtf(var + 1e-6f);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(w.ln_g + lane * 4));
-    const float4 b = __ldg(reinterpret_cast<const float4*>(w.ln_b + lane * 4));
-    float4 f;
-    f.x = d0 * rstd * g.x + b.x; f.y = d1 * rstd * g.y + b.y; f.z = d2 * rstd * g.z + b.z; f.w = d3 * rstd * g.w + b.w;
-    *reinterpret_cast<float4*>(sO + p * LDH + lane * 4) = f;
-  }
-  __syncthreads();
-  for (int i = tid; i < np * W_HID; i += NT) {
-    const int p = i >> 7, c = i & 127;
-    const float f = sO[p * LDH + c];
-    float a = 0.f;
-    for (int k = 0; k < K; ++k) a += f * sSc[p * 8 + k];
-    fagg_out[(n0 + p) * W_HID + c] = a;
-    if (feature_out) feature_out[(n0 + p) * W_HID + c] = f;
   }
 }
 
@@ -617,17 +396,6 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   const unsigned grid = (unsigned)((N + TP - 1) / TP);
   aggregate_kernel<<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
   return check_launch("aggregate_kernel");
-}
-
-int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
-                    const float* d2, const float* agg, float* fagg, float* feature, float* weights, cudaStream_t st) {
-  if (N <= 0) return 0;
-  if (K < 1 || K > 8) return set_error("neighbor: K must be in 1..8");
-  const size_t smem = NBR_SMEM_FLOATS * sizeof(float);
-  if (set_smem(neighbor_kernel, smem)) return 1;
-  const unsigned grid = (unsigned)((N + TP_MAX - 1) / TP_MAX);
-  neighbor_kernel<<<grid, NT, smem, st>>>(sc, w, ps, N, K, idx, d2, agg, fagg, feature, weights);
-  return check_launch("neighbor_kernel");
 }
 
 int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,

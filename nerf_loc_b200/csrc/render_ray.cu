@@ -45,7 +45,7 @@ __device__ __forceinline__ void ln_elu_smem(float* base, int ld, int rows, int c
     float* p = base + r * ld + c;
     *p = elu((*p - mean) * rstd * __ldg(g + i) + __ldg(be + i));
   }
-  __syncthreads();
+  cta_sync();
 }
 
 // LayerNorm statistics of a register fragment (bias already added).  Returns mean / rstd to every thread.
@@ -99,7 +99,7 @@ __device__ __forceinline__ void enc_block(const ASrc A, int rows, const UnetLaye
       }
     }
   }
-  __syncthreads();
+  cta_sync();
 }
 
 // Decoder block: stride-2 transposed conv written to dst rows [0, 2*rows), then LayerNorm + ELU in place.
@@ -110,7 +110,7 @@ __device__ __forceinline__ void dec_block(const float* in, int ldi, int rows, co
                                [&](int r, int c, float v) { dst[(2 * r) * ldd + c] = v + __ldg(L.b + c); });
   tile_gemm<1, 8, COLS, false>(ASrc{in, ldi, cin, 0, 1, 0}, rows, L.w + (size_t)cin * COLS, COLS, 2 * cin, sB,
                                [&](int r, int c, float v) { dst[(2 * r + 1) * ldd + c] = v + __ldg(L.b + c); });
-  __syncthreads();
+  cta_sync();
   ln_elu_smem(dst, ldd, 2 * rows, COLS, L.g, L.be, red);
 }
 
@@ -155,12 +155,12 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
   float* sBl = bC1;      // [S][36]: feature_agg half of layer 1
   float* sLogit = bC2;   // [S][V]
   tile_gemm<4, 4, 32, false>(plainA(X, LDXR), S, w.bl1a, 32, 128, sB, [&](int r, int c, float v) { sBl[r * 36 + c] = v; });
-  __syncthreads();
+  cta_sync();
   float* sW2 = sB;  // [16][32] | b2[16] | w3[16] | b3
   for (int i = tid; i < 512; i += NT) sW2[i] = __ldg(w.bl2 + i);
   if (tid < 16) { sW2[512 + tid] = __ldg(w.bl2_b + tid); sW2[528 + tid] = __ldg(w.bl3 + tid); }
   if (tid == 0) sW2[544] = __ldg(w.bl3_b);
-  __syncthreads();
+  cta_sync();
   for (int i = tid; i < S * V; i += NT) {
     const int s = i / V;
     const float4* pp = reinterpret_cast<const float4*>(partial + (s0 * V + i) * 32);
@@ -183,7 +183,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
     const float vis = __ldg(rgbvis + (s0 * V + i) * 4 + 3);
     sLogit[i] = vis == 0.f ? -1e9f : logit;
   }
-  __syncthreads();
+  cta_sync();
   if (tid < S) {
     float m = -FLT_MAX;
     for (int v = 0; v < V; ++v) m = fmaxf(m, sLogit[tid * V + v]);
@@ -195,11 +195,11 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
     }
     sRGB[tid * 4] = r / den; sRGB[tid * 4 + 1] = g / den; sRGB[tid * 4 + 2] = b / den;
   }
-  __syncthreads();
+  cta_sync();
   // the blend scratch aliased the halo rows of bC1 / bC2: clear them again
   for (int i = tid; i < LDC1; i += NT) bC1[i] = 0.f;
   for (int i = tid; i < LDC2; i += NT) bC2[i] = 0.f;
-  __syncthreads();
+  cta_sync();
 
   // ---- RayUnet ---------------------------------------------------------------------------------------------------------
   enc_block<4, 64>(ASrc{X, LDXR, 128, -1, 0, 1}, S, w.u[0], 128, sB, red, C1, LDC1);            // conv1 -> c1 [S/2][64]
@@ -247,7 +247,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
       if (f.active && (tid & 15) == 0) sSig[f.r0 + i] = softplus(v + __ldg(w.sig_b));
     }
   }
-  __syncthreads();
+  cta_sync();
 
   // ---- compositing (model.py:541-575) -------------------------------------------------------------------------------------
   if (tid < S) {
@@ -255,12 +255,12 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
     const float delta = tid + 1 < S ? sZ[tid + 1] - sZ[tid] : 1e2f;
     sSig[tid] = 1.f - expf(-delta * sSig[tid]);  // alpha
   }
-  __syncthreads();
+  cta_sync();
   if (tid == 0) {
     float T = 1.f;
     for (int s = 0; s < S; ++s) { sT[s] = T; T *= (1.f - sSig[s]); }
   }
-  __syncthreads();
+  cta_sync();
   float wv = 0.f, zz = 0.f, cr = 0.f, cg = 0.f, cb = 0.f, nv = 0.f;
   if (tid < S) {
     wv = sSig[tid] * sT[tid];
@@ -287,7 +287,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
   if (feat_out) {
     Frag<8, 8, 128> f;
     tile_gemm_frag<8, 8, 128>(plainA(X, LDXR), S, w.ft1, 128, 128, sB, f);
-    __syncthreads();  // staging ring is free: reuse it for the per-row-group partial sums
+    cta_sync();  // staging ring is free: reuse it for the per-row-group partial sums
     float* sPart = sB;  // [16][128]
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -300,7 +300,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
       }
       sPart[(tid / 16) * 128 + c] = a;
     }
-    __syncthreads();
+    cta_sync();
     float* sHs = sB + 16 * 128;
     if (tid < 128) {
       float a = 0.f;
@@ -308,7 +308,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
       for (int t = 0; t < 16; ++t) a += sPart[t * 128 + tid];
       sHs[tid] = a;
     }
-    __syncthreads();
+    cta_sync();
     if (tid < C_FEAT) {
       float a = __ldg(w.ft2_b + tid) * wsum;
       for (int k = 0; k < 128; ++k) a = fmaf(__ldg(w.ft2 + k * C_FEAT + tid), sHs[k], a);

@@ -1,0 +1,107 @@
+// tcgen05 (5th-generation tensor core) building blocks for sm_100a, written as inline PTX.
+//
+// MMA mode "3xTF32": the parity bar (1e-4) rules out single-pass tf32/bf16 operands, so every fp32 operand x is split
+// into hi = x with the low 13 mantissa bits cleared (exactly representable in tf32) and lo = x - hi (exact in fp32, the
+// hardware keeps its top 11 bits), and a product is evaluated as  Alo*Bhi + Ahi*Blo + Ahi*Bhi  with fp32 accumulation in
+// TMEM: three tcgen05.mma.kind::tf32 passes, ~2^-21 relative operand error.
+//
+// Operand layout in shared memory: the K-major, no-swizzle canonical layout of the UMMA shared-memory descriptor -
+// 8-row x 16-byte "core matrices" stored contiguously (128 B), core matrices adjacent in K `LBO` bytes apart, adjacent
+// 8-row groups `SBO` bytes apart.  Element (row r, col k) of a tile with KT columns lives at byte
+//     (r/8)*SBO + (k/4)*128 + (r%8)*16 + (k%4)*4,      LBO = 128, SBO = KT*32 (+ optional skew).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nlb {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMEM allocation (one full warp) -------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_in_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_in_smem)), "r"(ncols));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+// arrives on the mbarrier once every tcgen05 operation issued so far by this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- descriptors --------------------------------------------------------------------------------------------------------
+// shared-memory matrix descriptor, K-major, no swizzle
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);  // version 1 (Blackwell), base offset 0, SWIZZLE_NONE
+  return ((uint64_t)hi << 32) | lo;
+}
+// instruction descriptor: tf32 x tf32 -> f32, both operands K-major
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, one K = 8 step; issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// ---- TMEM -> registers: this thread's row (TMEM lane), 32 consecutive fp32 columns ----------------------------------------
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- 3xTF32 operand split ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+// byte offset of element (r, k) in a canonical K-major tile whose 8-row groups are `sbo` bytes apart
+__device__ __forceinline__ uint32_t canon_off(int r, int k, uint32_t sbo) {
+  return (uint32_t)(r >> 3) * sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 3) * 4u;
+}
+
+}  // namespace tc
+}  // namespace nlb

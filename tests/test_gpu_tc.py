@@ -1,0 +1,25 @@
+"""tcgen05 building blocks: single-pass tf32 and 3xTF32 GEMM against an fp64 reference."""
+import pytest
+import torch
+
+from nerf_loc_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("K", [8, 32, 64])
+def test_tc_gemm_modes(K):
+    L = _lib.load()
+    g = torch.Generator().manual_seed(K)
+    A = torch.randn(128, K, generator=g).cuda()
+    W = torch.randn(128, K, generator=g).cuda()
+    ref = (A.double() @ W.double().t())
+    errs = {}
+    for mode in (0, 1):
+        C = torch.zeros(128, 128, device="cuda")
+        _lib.check(L.nlb_debug_tc_gemm(_lib.ptr(A), _lib.ptr(W), K, mode, _lib.ptr(C), _lib.stream()))
+        torch.cuda.synchronize()
+        errs[mode] = float((C.double() - ref).abs().max() / ref.abs().max())
+    print("K", K, "tf32 err", errs[0], "3xTF32 err", errs[1])
+    assert errs[0] < 5e-3
+    assert errs[1] < 2e-6
