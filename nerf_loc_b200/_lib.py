@@ -46,6 +46,7 @@ SIGNATURES = {
                                 c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nlb_render_launch_count": (c_int64, [c_int64, c_int64]),
+    "nlb_debug_read_prof": (c_int, [c_void_p, c_int]),
     "nlb_debug_tc_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "nlb_profile_enable": (None, [c_int]),
     "nlb_profile_read": (c_int, [c_void_p, c_void_p, c_int]),

@@ -91,6 +91,7 @@ struct Carver {
 }  // namespace nlb
 
 namespace nlb { int launch_tc_test(const float* A, const float* W, int K, int mode, float* C, cudaStream_t st); }
+namespace nlb { int read_prof(long long* out, int n); }
 using namespace nlb;
 
 extern "C" {
@@ -302,5 +303,7 @@ int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C,
   if (!A || !W || !C) return set_error("nlb_debug_tc_gemm: NULL pointer");
   return launch_tc_test(A, W, K, mode, C, (cudaStream_t)stream);
 }
+
+int nlb_debug_read_prof(long long* out, int n) { return read_prof(out, n); }
 
 }  // extern "C"

@@ -16,6 +16,10 @@
 
 namespace nlb {
 
+// phase timestamps of block 0 (debug aid, read with nlb_debug_read_prof)
+__device__ long long g_prof[32];
+#define NLB_STAMP(i) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) g_prof[i] = clock64(); } while (0)
+
 constexpr int NB_LDH = 132;
 constexpr int NB_TP = 16;                      // samples per CTA
 constexpr uint32_t NB_SBO1 = 96u * 32u;        // A operand of layer 1: K = 96
@@ -69,6 +73,7 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     const int np = (int)min((int64_t)NB_TP, N - n0);
     const float range = sc.far_ - sc.near_;
     uint32_t d_par = 0;
+    NLB_STAMP(0);
 
     // ---- phase 0: per (sample, neighbour) geometry -> A operand of layer 1 (PE 63 | ray_diff_fc 27 | 0 x 6) ----------
     if (tid < 128) {
@@ -156,6 +161,7 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
       sAgg[p * NB_LDH + c] = p < np ? agg_in[(n0 + p) * W_HID + c] : 0.f;
     }
     tc::a_ready(sy);
+    NLB_STAMP(1);
 
     // ---- base_mlp on the tensor cores: three 128 x 128 layers, epilogues out of TMEM -------------------------------------
     const int row = (warp & 3) * 32 + lane;            // TMEM lane == (sample, neighbour) row
@@ -164,6 +170,7 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     cta_sync();  // sIdx visible
     for (int layer = 0; layer < 3; ++layer) {
       tc::wait_d(sy, d_par);
+      NLB_STAMP(2 + 2 * layer);
       const int id = sIdx[row];
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 32) {
@@ -199,17 +206,21 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         }
       }
       if (layer < 2) tc::a_ready(sy);
+      NLB_STAMP(3 + 2 * layer);
     }
     tc::fence_before_sync();
     cta_sync();
 
+    NLB_STAMP(8);
     // ---- q = Wq agg ; q~_h = Wk_h^T q_h ------------------------------------------------------------------------------------
-    tile_gemm<1, 8, 128, false>(plainA(sAgg, NB_LDH), NB_TP, w.wq, 128, 128, sB,
-                                [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v; });
-    for (int hd = 0; hd < 4; ++hd)
-      tile_gemm<1, 8, 128, false>(plainA(sQ + 32 * hd, NB_LDH), NB_TP, w.wk + 32 * hd * 128, 128, 32, sB,
-                                  [&](int r, int c, float v) { sQT[(r * 4 + hd) * NB_LDH + c] = v; });
+    rows16_gemm<128>([&](int r, int) { return sAgg + r * NB_LDH; }, w.wq, 128, 128, sB,
+                     [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v; });
     cta_sync();
+    for (int hd = 0; hd < 4; ++hd)
+      rows16_gemm<128>([&](int r, int) { return sQ + r * NB_LDH + 32 * hd; }, w.wk + 32 * hd * 128, 128, 32, sB,
+                       [&](int r, int c, float v) { sQT[(r * 4 + hd) * NB_LDH + c] = v; });
+    cta_sync();
+    NLB_STAMP(9);
     // ---- attention scores + softmax over the K neighbours -----------------------------------------------------------------
     for (int it = 0; it < 2; ++it) {
       const int i = tid + it * NT;  // (p, h, k), k fastest
@@ -239,31 +250,36 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     cta_sync();
     // ---- per-head context = sum_k a_k * point_feature_k (overwrites q~) -----------------------------------------------------
     {
-      const int ph = tid >> 2, cb = (tid & 3) * 32;
+      // thread = (sample-head row ph, quarter q): columns q*4 + 16*j .. +3, so the 4 quarter-lanes of a row read one
+      // contiguous 64-byte run per j and the rows of a warp stay on distinct banks
+      const int ph = tid >> 2, q4 = (tid & 3) * 4;
       const int p = ph >> 2;
-      float acc[32];
+      float4 acc[8];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+      for (int j = 0; j < 8; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = 0; k < 8; ++k) {
         const float a = sSc[ph * 8 + k];
-        const float* kv = sA + (p * 8 + k) * NB_LDH + cb;
+        const float* kv = sA + (p * 8 + k) * NB_LDH + q4;
 #pragma unroll
-        for (int c = 0; c < 32; c += 4) {
-          const float4 v4 = *reinterpret_cast<const float4*>(kv + c);
-          acc[c] = fmaf(a, v4.x, acc[c]); acc[c + 1] = fmaf(a, v4.y, acc[c + 1]);
-          acc[c + 2] = fmaf(a, v4.z, acc[c + 2]); acc[c + 3] = fmaf(a, v4.w, acc[c + 3]);
+        for (int j = 0; j < 8; ++j) {
+          const float4 v4 = *reinterpret_cast<const float4*>(kv + 16 * j);
+          acc[j].x = fmaf(a, v4.x, acc[j].x); acc[j].y = fmaf(a, v4.y, acc[j].y);
+          acc[j].z = fmaf(a, v4.z, acc[j].z); acc[j].w = fmaf(a, v4.w, acc[j].w);
         }
       }
 #pragma unroll
-      for (int c = 0; c < 32; ++c) sQT[ph * NB_LDH + cb + c] = acc[c];
+      for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(sQT + ph * NB_LDH + q4 + 16 * j) = acc[j];
     }
+    NLB_STAMP(10);
     // ---- o_h = Wv_h ctx_h ; fc + residual -------------------------------------------------------------------------------------
-    for (int hd = 0; hd < 4; ++hd)
-      tile_gemm<1, 4, 32, false>(plainA(sQT + hd * NB_LDH, 4 * NB_LDH), NB_TP, w.wv + 32 * hd, 128, 128, sB,
-                                 [&](int r, int c, float v) { sO[r * NB_LDH + 32 * hd + c] = v; });
-    tile_gemm<1, 8, 128, false>(plainA(sO, NB_LDH), NB_TP, w.wfc, 128, 128, sB,
-                                [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v + sAgg[r * NB_LDH + c]; });
     cta_sync();
+    rows16_gemm<128>([&](int r, int c) { return sQT + (r * 4 + (c >> 5)) * NB_LDH; }, w.wv, 128, 128, sB,
+                     [&](int r, int c, float v) { sO[r * NB_LDH + c] = v; });
+    cta_sync();
+    rows16_gemm<128>([&](int r, int) { return sO + r * NB_LDH; }, w.wfc, 128, 128, sB,
+                     [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v + sAgg[r * NB_LDH + c]; });
+    cta_sync();
+    NLB_STAMP(11);
     // ---- LayerNorm(eps 1e-6), neighbour weights, weighted sum -------------------------------------------------------------------
     if (tid < NB_TP) {
       // weights = (1/clamp(dist)) * softmax_K(corr) * conf, normalised (model.py:415-426); corr rows are identical
@@ -308,7 +324,12 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
       if (feature_out) feature_out[(n0 + p) * W_HID + c] = f;
     }
   }
+  NLB_STAMP(12);
   tc::teardown(sy, warp, tmem, 128);
+}
+
+int read_prof(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_prof, sizeof(long long) * (n < 32 ? n : 32)) == cudaSuccess ? 0 : set_error("read_prof failed");
 }
 
 int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,

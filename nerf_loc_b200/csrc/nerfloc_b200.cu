@@ -2,8 +2,8 @@
 // device code, so they are compiled together instead of with relocatable device code.
 #include "pack.cu"
 #include "knn.cu"
-#include "render_point.cu"
 #include "neighbor_tc.cu"
+#include "render_point.cu"
 #include "render_ray.cu"
 #include "match.cu"
 #include "tc_test.cu"

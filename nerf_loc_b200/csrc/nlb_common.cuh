@@ -16,8 +16,9 @@
 namespace nlb {
 
 constexpr int NT = 256;  // threads per CTA for all tile kernels
-constexpr int KT = 32;   // K-tile of the weight staging ring
-constexpr int STAGE_FLOATS = 2 * KT * 128;  // two stages of [KT][<=128]
+constexpr int KT = 16;   // K-tile of the weight staging ring
+constexpr int NSTG = 4;  // ring depth: loads run NSTG-1 tiles ahead of the FFMA loop
+constexpr int STAGE_FLOATS = NSTG * KT * 128;  // NSTG slots of [KT][<=128]
 
 // Barrier over the NT compute threads of a CTA (named barrier 1).  Kernels that add a tcgen05 controller warp on top
 // of the NT compute threads keep that warp out of these barriers; for plain NT-thread kernels it is a __syncthreads.
@@ -80,6 +81,7 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
   constexpr int GSTRIDE = COLS / NG;
   static_assert(NT % TC == 0, "bad tile");
   constexpr int CHUNKS = KT * COLS / 4;  // 16-byte chunks per stage
+  constexpr int STG = KT * 128;          // floats per stage slot
   const int tid = threadIdx.x;
   const int tc = tid % TC;
   const int nkt = K / KT;
@@ -88,17 +90,26 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
+  auto stage_load = [&](int kt) {
+    if (kt < nkt) {
+      float* dst = sB + (kt % NSTG) * STG;
+      const float* src = Wt + (size_t)kt * KT * ldb;
+      for (int c = tid; c < CHUNKS; c += NT) {
+        const int k = c / (COLS / 4), n4 = c % (COLS / 4);
+        cp_async16(dst + k * COLS + n4 * 4, src + (size_t)k * ldb + n4 * 4);
+      }
+    }
+    cp_async_commit();  // always commit: keeps the group count uniform
+  };
+
   cta_sync();  // previous users of sB (and producers of A) are done
-  for (int c = tid; c < CHUNKS; c += NT) {
-    const int k = c / (COLS / 4), n4 = c % (COLS / 4);
-    cp_async16(sB + k * COLS + n4 * 4, Wt + (size_t)k * ldb + n4 * 4);
-  }
-  cp_async_commit();
+#pragma unroll
+  for (int i = 0; i < NSTG - 1; ++i) stage_load(i);
 
   for (int kt = 0; kt < nkt; ++kt) {
-    cp_async_wait<0>();
+    cp_async_wait<NSTG - 2>();  // tile kt has landed (this thread's part)
     if (SCALE) {
-      float* cur = sB + (kt & 1) * (KT * COLS);
+      float* cur = sB + (kt % NSTG) * STG;
       for (int c = tid; c < CHUNKS; c += NT) {
         const int k = c / (COLS / 4), n4 = c % (COLS / 4);
         const float sc = kscale[kt * KT + k];
@@ -108,22 +119,14 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
         *p = v;
       }
     }
-    cta_sync();
-    if (kt + 1 < nkt) {
-      float* dst = sB + ((kt + 1) & 1) * (KT * COLS);
-      const float* src = Wt + (size_t)(kt + 1) * KT * ldb;
-      for (int c = tid; c < CHUNKS; c += NT) {
-        const int k = c / (COLS / 4), n4 = c % (COLS / 4);
-        cp_async16(dst + k * COLS + n4 * 4, src + (size_t)k * ldb + n4 * 4);
-      }
-      cp_async_commit();
-    }
+    cta_sync();                  // everybody's part of tile kt is visible; tile kt-1's slot is free
+    stage_load(kt + NSTG - 1);   // refill the slot tile kt-1 used
     if (active) {
       const int k0 = kt * KT;
       const int tap = k0 / A.cin;
       const int roff = tap == 0 ? A.off0 : (tap == 1 ? A.off1 : A.off2);
       const float* arow = A.base + (r0 + roff) * A.ld + (k0 - tap * A.cin);
-      const float* bt = sB + (kt & 1) * (KT * COLS) + tc * 4;
+      const float* bt = sB + (kt % NSTG) * STG + tc * 4;
 #pragma unroll
       for (int kk = 0; kk < KT; kk += 4) {
         float4 a[TM];
@@ -147,6 +150,7 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
       }
     }
   }
+  cp_async_wait<0>();
 }
 
 // C = A * Wt (+ epilogue).  rows: runtime; threads whose rows fall outside are idle but still help staging.
@@ -198,6 +202,57 @@ __device__ __forceinline__ void tile_gemm_frag(const ASrc A, const int rows, con
   f.r0 = (threadIdx.x / TC) * TM;
   f.active = f.r0 < rows;
   gemm_core<TM, TN, COLS, SCALE>(A, f.r0, f.active, Wt, ldb, K, sB, kscale, f.acc);
+}
+
+// Small-M GEMM: out[r][c] = sum_k A_r[k] * Wt[k*ldb + c] for r < 16, c < COLS.  A tile GEMM would give every thread one
+// row and re-read the staged weight tile 16 times; here a thread owns one output COLUMN for all 16 rows (16 independent
+// accumulators), reads its weight column straight from L2 (a warp reads 128 contiguous bytes per k, no staging, no
+// barrier per K-tile) and the 256 threads split K in NT/COLS slices that are reduced through `red`
+// (>= (NT/COLS)*16*COLS floats of shared scratch).  arow(r, c) -> shared-memory pointer to row r as seen by column c.
+template <int COLS, class ARow, class Epi>
+__device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__ Wt, const int ldb, const int K, float* red,
+                                            Epi epi) {
+  constexpr int KSPLIT = NT / COLS;
+  const int tid = threadIdx.x;
+  const int c = tid % COLS, ks = tid / COLS;
+  const int kper = K / KSPLIT;
+  const int k0 = ks * kper;
+  float acc[16];
+#pragma unroll
+  for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+  const float* wp = Wt + (size_t)k0 * ldb + c;
+  for (int k = 0; k < kper; k += 8) {
+    float b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) b[j] = (k + j < kper) ? __ldg(wp + (size_t)(k + j) * ldb) : 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float* ap = arow(r, c) + k0 + k;
+      const float4 a0 = *reinterpret_cast<const float4*>(ap);
+      acc[r] = fmaf(a0.x, b[0], acc[r]); acc[r] = fmaf(a0.y, b[1], acc[r]);
+      acc[r] = fmaf(a0.z, b[2], acc[r]); acc[r] = fmaf(a0.w, b[3], acc[r]);
+      if (k + 4 < kper) {
+        const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
+        acc[r] = fmaf(a1.x, b[4], acc[r]); acc[r] = fmaf(a1.y, b[5], acc[r]);
+        acc[r] = fmaf(a1.z, b[6], acc[r]); acc[r] = fmaf(a1.w, b[7], acc[r]);
+      }
+    }
+  }
+  if (KSPLIT == 1) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) epi(r, c, acc[r]);
+  } else {
+    cta_sync();  // `red` may alias a buffer an earlier phase still reads
+#pragma unroll
+    for (int r = 0; r < 16; ++r) red[(ks * 16 + r) * COLS + c] = acc[r];
+    cta_sync();
+    for (int i = tid; i < 16 * COLS; i += NT) {
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < KSPLIT; ++q) v += red[q * 16 * COLS + i];
+      epi(i / COLS, i % COLS, v);
+    }
+  }
 }
 
 }  // namespace nlb

@@ -22,6 +22,9 @@
 
 namespace nlb {
 
+
+#define AGG_STAMP(i) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) g_prof[16 + i] = clock64(); } while (0)
+
 // ------------------------------------------------------------------------------------------------------------------
 // shared geometry helpers
 // ------------------------------------------------------------------------------------------------------------------
@@ -103,6 +106,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   const int rows = np * V;
   const float near_ = sc.near_, far_ = sc.far_;
 
+  AGG_STAMP(0);
   // ---- phase 1: projections, one thread per (sample, view) row -----------------------------------------------
   if (tid < 128) {
     float* ri = sRI + tid * RI_N;
@@ -153,25 +157,47 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   }
   cta_sync();
 
+  AGG_STAMP(1);
   // ---- phase 2: 32-channel visibility features (border padding), one warp per row ------------------------------
-  for (int r = warp; r < 128; r += NT / 32) {
-    float val = 0.f;
-    if (r < rows) {
-      const float* ri = sRI + r * RI_N;
-      const int v = r % V;
-      const Taps t = make_taps(ri[RI_VX], ri[RI_VY], sc.vw, sc.vh, false);
-      const float* base = sc.vis + ((size_t)v * sc.vh * sc.vw) * C_VIS + lane;
-      float a = 0.f;
-      if (t.w[0] != 0.f) a = __ldg(base + ((size_t)t.y0 * sc.vw + t.x0) * C_VIS) * t.w[0];
-      if (t.w[1] != 0.f) a += __ldg(base + ((size_t)t.y0 * sc.vw + t.x0 + 1) * C_VIS) * t.w[1];
-      if (t.w[2] != 0.f) a += __ldg(base + ((size_t)(t.y0 + 1) * sc.vw + t.x0) * C_VIS) * t.w[2];
-      if (t.w[3] != 0.f) a += __ldg(base + ((size_t)(t.y0 + 1) * sc.vw + t.x0 + 1) * C_VIS) * t.w[3];
-      val = a * ri[RI_VALID];
+  // All four taps of two rows are requested before any is consumed (addresses clamped into the map, taps outside
+  // carry weight 0), so a warp keeps 8 independent loads in flight instead of one.
+  for (int rb = warp; rb < 128; rb += 2 * (NT / 32)) {
+    float q[2][4], wgt[2][4], valid[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = rb + u * (NT / 32);
+      valid[u] = 0.f;
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { q[u][t] = 0.f; wgt[u][t] = 0.f; }
+      if (r < rows) {
+        const float* ri = sRI + r * RI_N;
+        const int v = r % V;
+        const Taps t = make_taps(ri[RI_VX], ri[RI_VY], sc.vw, sc.vh, false);
+        const float* base = sc.vis + ((size_t)v * sc.vh * sc.vw) * C_VIS + lane;
+        const int x0 = min(max(t.x0, 0), sc.vw - 1), x1 = min(max(t.x0 + 1, 0), sc.vw - 1);
+        const int y0 = min(max(t.y0, 0), sc.vh - 1), y1 = min(max(t.y0 + 1, 0), sc.vh - 1);
+        q[u][0] = __ldg(base + ((size_t)y0 * sc.vw + x0) * C_VIS);
+        q[u][1] = __ldg(base + ((size_t)y0 * sc.vw + x1) * C_VIS);
+        q[u][2] = __ldg(base + ((size_t)y1 * sc.vw + x0) * C_VIS);
+        q[u][3] = __ldg(base + ((size_t)y1 * sc.vw + x1) * C_VIS);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wgt[u][k] = t.w[k];
+        valid[u] = ri[RI_VALID];
+      }
     }
-    sX[r * LDX + lane] = val;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = rb + u * (NT / 32);
+      float a = q[u][0] * wgt[u][0];
+      a += q[u][1] * wgt[u][1];
+      a += q[u][2] * wgt[u][2];
+      a += q[u][3] * wgt[u][3];
+      sX[r * LDX + lane] = a * valid[u];
+    }
   }
   // (tile_gemm starts with a __syncthreads)
 
+  AGG_STAMP(2);
   // ---- phase 3: visibility decoder ------------------------------------------------------------------------------
   tile_gemm<8, 8, 128, false>(plainA(sX, LDX), 128, w.dec1, 128, 32, sB,
                               [&](int r, int c, float v) { sH[r * LDH + c] = elu(v + __ldg(w.dec1_b + c)); });
@@ -208,6 +234,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   }
   cta_sync();
 
+  AGG_STAMP(3);
   // ---- phase 4: per-sample view weights --------------------------------------------------------------------------
   if (tid < np) {
     float sum = 0.f;
@@ -236,6 +263,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   }
   cta_sync();  // sH (arena) is dead from here on
 
+  AGG_STAMP(4);
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
   for (int r = warp; r < 128; r += NT / 32) {
     float* frow = sF + r * LDF;
@@ -244,19 +272,24 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       const int p = r / V, v = r - p * V;
       const Taps tf = make_taps(ri[RI_FX], ri[RI_FY], sc.w, sc.h, true);
       const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
+      // branch-free: the 12 loads of the 4 taps are all in flight before the first use
+      const int fx0 = min(max(tf.x0, 0), sc.w - 1), fx1 = min(max(tf.x0 + 1, 0), sc.w - 1);
+      const int fy0 = min(max(tf.y0, 0), sc.h - 1), fy1 = min(max(tf.y0 + 1, 0), sc.h - 1);
+      const float* tp[4] = {fb + ((size_t)fy0 * sc.w + fx0) * C_FEAT, fb + ((size_t)fy0 * sc.w + fx1) * C_FEAT,
+                            fb + ((size_t)fy1 * sc.w + fx0) * C_FEAT, fb + ((size_t)fy1 * sc.w + fx1) * C_FEAT};
+      float2 q[4][3];
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) q[t][j] = __ldg(reinterpret_cast<const float2*>(tp[t] + j * 64));
       float2 acc[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        if (tf.w[t] != 0.f) {
-          const float* tp = fb + ((size_t)(tf.y0 + (t >> 1)) * sc.w + tf.x0 + (t & 1)) * C_FEAT;
+      for (int t = 0; t < 4; ++t)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const float2 q = __ldg(reinterpret_cast<const float2*>(tp + j * 64));
-            acc[j].x = fmaf(q.x, tf.w[t], acc[j].x);
-            acc[j].y = fmaf(q.y, tf.w[t], acc[j].y);
-          }
+        for (int j = 0; j < 3; ++j) {
+          acc[j].x = fmaf(q[t][j].x, tf.w[t], acc[j].x);
+          acc[j].y = fmaf(q[t][j].y, tf.w[t], acc[j].y);
         }
-      }
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         frow[3 + j * 64 + lane * 2] = acc[j].x;
@@ -307,6 +340,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     }
   }
 
+  AGG_STAMP(5);
   // ---- phase 6: visibility-weighted mean / variance over views (ibrnet.py:8-12) ---------------------------------
   for (int i = tid; i < np * C_RGBF; i += NT) {
     const int p = i / C_RGBF, c = i - p * C_RGBF;
@@ -322,19 +356,24 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   }
   for (int i = tid; i < (TP_MAX - np) * LDG; i += NT) sG[np * LDG + i] = 0.f;
 
+  AGG_STAMP(6);
   // ---- phase 7: out_fc 393 -> 64 -> 128 (ELU) --------------------------------------------------------------------
-  tile_gemm<1, 4, 64, false>(plainA(sG, LDG), TP_MAX, w.fc1, 64, 416, sB,
-                             [&](int r, int c, float v) { sO1[r * 68 + c] = elu(v + __ldg(w.fc1_b + c)); });
-  tile_gemm<1, 8, 128, false>(plainA(sO1, 68), TP_MAX, w.fc2, 128, 64, sB, [&](int r, int c, float v) {
+  cta_sync();  // sG complete
+  rows16_gemm<64>([&](int r, int) { return sG + r * LDG; }, w.fc1, 64, 416, sB,
+                  [&](int r, int c, float v) { sO1[r * 68 + c] = elu(v + __ldg(w.fc1_b + c)); });
+  cta_sync();
+  rows16_gemm<128>([&](int r, int) { return sO1 + r * 68; }, w.fc2, 128, 64, sB, [&](int r, int c, float v) {
     if (r < np) agg_out[(n0 + r) * W_HID + c] = elu(v + __ldg(w.fc2_b + c));
   });
 
+  AGG_STAMP(7);
   // ---- phase 8: per-view half of the colour-blend first layer ----------------------------------------------------
   if (with_blend) {
     tile_gemm<4, 4, 32, false>(plainA(sF, LDF), 128, w.bl1v, 32, 224, sB, [&](int r, int c, float v) {
       if (r < rows) partial_out[(n0 * V + r) * 32 + c] = v + __ldg(w.bl1_b + c);
     });
   }
+  AGG_STAMP(8);
 }
 
 // ------------------------------------------------------------------------------------------------------------------

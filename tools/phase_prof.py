@@ -1,0 +1,31 @@
+"""Prints the clock64 phase stamps of block 0 of the neighbour kernel (GPU box)."""
+import ctypes, os, sys
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench
+from nerf_loc_b200 import _lib
+from nerf_loc_b200.conditional_nerf import ConditionalNeRF
+from nerf_loc_b200.config import default_args
+sc, sd, ro, rd = bench.build_frame()
+dev = torch.device("cuda")
+model = ConditionalNeRF(default_args(bench.S)).eval(); model.load_state_dict(sd, strict=False); model = model.to(dev)
+data = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items() if k != "vis_featmaps"}
+data["scene"], data["filename"] = "s", "f"
+model.support_neural_points = None
+model.multiview_aggregator.vis_featmaps = sc["vis_featmaps"].to(dev)
+rays = {"rays_o": ro[150000:150000 + 4736].to(dev), "rays_d": rd[150000:150000 + 4736].to(dev), "depth_range": data["depth_range"][0]}
+for _ in range(2):
+    model.render_rays(data, rays)
+torch.cuda.synchronize()
+buf = (ctypes.c_longlong * 32)()
+_lib.load().nlb_debug_read_prof(buf, 32)
+v = list(buf)
+names = ["phase0 (PE, rd_fc, A1 write)", "wait L1", "epi L1", "wait L2", "epi L2", "wait L3", "epi L3", "sync", "q + q~ GEMMs", "scores+softmax", "ctx", "o + fc GEMMs", "LN + out"]
+for i in range(12):
+    print(f"{names[i]:32s} {v[i+1]-v[i]:8d} clk")
+print("total", v[12] - v[0])
+
+an = ["proj", "vis gather", "decoder GEMMs+heads", "view weights", "rgb/feat gather", "mean/var", "out_fc", "blend partial"]
+for i in range(8):
+    print(f"agg {an[i]:28s} {v[17+i]-v[16+i]:8d} clk")
+print("agg total", v[24] - v[16])
