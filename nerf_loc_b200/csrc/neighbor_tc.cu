@@ -74,20 +74,31 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     const float range = sc.far_ - sc.near_;
     uint32_t d_par = 0;
     NLB_STAMP(0);
+    // aggregated features of the 16 samples: asynchronous copy, consumed after the tensor-core phase
+    for (int i = tid; i < NB_TP * 32; i += NT) {
+      const int p = i >> 5, c4 = i & 31;
+      if (p < np) cp_async16(sAgg + p * NB_LDH + c4 * 4, agg_in + (n0 + p) * W_HID + c4 * 4);
+      else *reinterpret_cast<float4*>(sAgg + p * NB_LDH + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
 
     // ---- phase 0: per (sample, neighbour) geometry -> A operand of layer 1 (PE 63 | ray_diff_fc 27 | 0 x 6) ----------
-    if (tid < 128) {
-      const int p = tid >> 3, k = tid & 7;
-      float xr[96];
-      int id = 0;
-      if (p < np && k < K) {
+    // two threads per row: threads 0..127 do the positional encoding, threads 128..255 the ray-difference MLP
+    float* sW = sQ;  // ray_diff_fc weights: rd1 [16][4] | b1 [16] | rd2 [27][16] | b2 [27]  (sQ is free until the q GEMM)
+    for (int i = tid; i < 64 + 16 + 432 + 27; i += NT)
+      sW[i] = i < 64 ? __ldg(w.rd1 + i) : (i < 80 ? __ldg(w.rd1_b + i - 64) : (i < 512 ? __ldg(w.rd2 + i - 80) : __ldg(w.rd2_b + i - 512)));
+    {
+      const int rowp = tid & 127, half = tid >> 7;
+      const int p = rowp >> 3, k = rowp & 7;
+      const bool live = p < np && k < K;
+      int id = -1;
+      float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+      float x = 0.f, y = 0.f, z = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
+      if (live) {
         const int64_t n = n0 + p;
         id = knn_idx[n * K + k];
-        sD[tid] = knn_d2[n * K + k];
-        const float4 g0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8));
-        const float4 g1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8 + 4));
-        sD[128 + tid] = g1.z;  // confidence
-        float x, y, z;
+        g0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8));
+        g1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8 + 4));
         if (ps.xyz) {
           x = ps.xyz[n * 3]; y = ps.xyz[n * 3 + 1]; z = ps.xyz[n * 3 + 2];
         } else {
@@ -97,33 +108,52 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           y = __fadd_rn(ps.rays_o[r * 3 + 1], __fmul_rn(ps.rays_d[r * 3 + 1], t));
           z = __fadd_rn(ps.rays_o[r * 3 + 2], __fmul_rn(ps.rays_d[r * 3 + 2], t));
         }
-        float dx, dy, dz;
-        if (ps.dirs) {
-          dx = ps.dirs[n * 3]; dy = ps.dirs[n * 3 + 1]; dz = ps.dirs[n * 3 + 2];
-        } else if (ps.rays_d && !ps.xyz) {
-          const int64_t r = n / ps.S;
-          dx = ps.rays_d[r * 3]; dy = ps.rays_d[r * 3 + 1]; dz = ps.rays_d[r * 3 + 2];
-        } else {  // direction=None: the nearest neighbour's own direction (model.py:391-392)
-          const int id0 = knn_idx[n * K];
-          const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8));
-          const float4 h1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8 + 4));
-          dx = h0.w; dy = h1.x; dz = h1.y;
+        if (half == 1) {
+          if (ps.dirs) {
+            dx = ps.dirs[n * 3]; dy = ps.dirs[n * 3 + 1]; dz = ps.dirs[n * 3 + 2];
+          } else if (ps.rays_d && !ps.xyz) {
+            const int64_t r = n / ps.S;
+            dx = ps.rays_d[r * 3]; dy = ps.rays_d[r * 3 + 1]; dz = ps.rays_d[r * 3 + 2];
+          } else {  // direction=None: the nearest neighbour's own direction (model.py:391-392)
+            const int id0 = knn_idx[n * K];
+            const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8));
+            const float4 h1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8 + 4));
+            dx = h0.w; dy = h1.x; dz = h1.y;
+          }
         }
-        const float off[3] = {__fdiv_rn(__fsub_rn(x, g0.x), range), __fdiv_rn(__fsub_rn(y, g0.y), range),
-                              __fdiv_rn(__fsub_rn(z, g0.z), range)};
-        xr[0] = off[0]; xr[1] = off[1]; xr[2] = off[2];
+      }
+      cta_sync();  // sW loaded
+      auto put = [&](int c, float v) {
+        float hi, lo;
+        tc::split_tf32(v, hi, lo);
+        const uint32_t o = tc::a_off(rowp, c, NB_SBO1);
+        *reinterpret_cast<float*>(actHi + o) = hi;
+        *reinterpret_cast<float*>(actLo + o) = lo;
+      };
+      if (half == 0) {
+        if (live) {
+          sD[rowp] = knn_d2[(n0 + p) * K + k];
+          sD[128 + rowp] = g1.z;  // confidence
+        } else {
+          sD[rowp] = 1.f; sD[128 + rowp] = 0.f;
+        }
+        sIdx[rowp] = id;
+        const float off[3] = {live ? __fdiv_rn(__fsub_rn(x, g0.x), range) : 0.f, live ? __fdiv_rn(__fsub_rn(y, g0.y), range) : 0.f,
+                              live ? __fdiv_rn(__fsub_rn(z, g0.z), range) : 0.f};
+        put(0, off[0]); put(1, off[1]); put(2, off[2]);
         float f = 1.f;
 #pragma unroll
         for (int i = 0; i < 10; ++i) {
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
-            float s, co;
-            sincosf(off[c] * f, &s, &co);
-            xr[3 + i * 6 + c] = s;
-            xr[3 + i * 6 + 3 + c] = co;
+            float sn = 0.f, co = 0.f;
+            if (live) sincosf(off[c] * f, &sn, &co);
+            put(3 + i * 6 + c, sn);
+            put(3 + i * 6 + 3 + c, co);
           }
           f *= 2.f;
         }
+      } else {
         // ray difference (model.py:396-399) and ray_diff_fc (4 -> 16 -> 27, LeakyReLU)
         const float nx = g0.w, ny = g1.x, nz = g1.y;
         const float rx = dx - nx, ry = dy - ny, rz = dz - nz;
@@ -132,34 +162,23 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         float h1[16];
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
-          float a = __ldg(w.rd1_b + o);
+          float a = sW[64 + o];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) a = fmaf(__ldg(w.rd1 + o * 4 + c), rd[c], a);
+          for (int c = 0; c < 4; ++c) a = fmaf(sW[o * 4 + c], rd[c], a);
           h1[o] = leaky(a);
         }
 #pragma unroll
         for (int o = 0; o < 27; ++o) {
-          float a = __ldg(w.rd2_b + o);
+          float a = sW[512 + o];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) a = fmaf(__ldg(w.rd2 + o * 16 + c), h1[c], a);
-          xr[63 + o] = leaky(a);
+          for (int c = 0; c < 16; ++c) a = fmaf(sW[80 + o * 16 + c], h1[c], a);
+          put(63 + o, live ? leaky(a) : 0.f);
         }
 #pragma unroll
-        for (int c = 90; c < 96; ++c) xr[c] = 0.f;
-      } else {
-#pragma unroll
-        for (int c = 0; c < 96; ++c) xr[c] = 0.f;
-        sD[tid] = 1.f; sD[128 + tid] = 0.f;
-        id = -1;
+        for (int c = 90; c < 96; ++c) put(c, 0.f);
       }
-      sIdx[tid] = id;
-#pragma unroll
-      for (int c = 0; c < 96; c += 4) tc::store_split4(actHi, actLo, tid, c, NB_SBO1, xr[c], xr[c + 1], xr[c + 2], xr[c + 3]);
     }
-    for (int i = tid; i < NB_TP * W_HID; i += NT) {
-      const int p = i >> 7, c = i & 127;
-      sAgg[p * NB_LDH + c] = p < np ? agg_in[(n0 + p) * W_HID + c] : 0.f;
-    }
+    cp_async_wait<0>();  // the agg tile requested at kernel start
     tc::a_ready(sy);
     NLB_STAMP(1);
 
@@ -216,9 +235,37 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     rows16_gemm<128>([&](int r, int) { return sAgg + r * NB_LDH; }, w.wq, 128, 128, sB,
                      [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v; });
     cta_sync();
-    for (int hd = 0; hd < 4; ++hd)
-      rows16_gemm<128>([&](int r, int) { return sQ + r * NB_LDH + 32 * hd; }, w.wk + 32 * hd * 128, 128, 32, sB,
-                       [&](int r, int c, float v) { sQT[(r * 4 + hd) * NB_LDH + c] = v; });
+    {
+      // q~[p][h][c] = sum_j q[p][32h+j] Wk[32h+j][c]: thread = (column c, head pair); all 64 weight loads of a thread are
+      // independent, no K split and no reduction
+      const int c = tid & 127, hp = tid >> 7;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int hd = hp * 2 + hh;
+        float acc[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+        const float* wp = w.wk + (size_t)(32 * hd) * 128 + c;
+#pragma unroll
+        for (int k = 0; k < 32; k += 8) {
+          float b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b[j] = __ldg(wp + (size_t)(k + j) * 128);
+#pragma unroll
+          for (int r = 0; r < 16; ++r) {
+            const float* ap = sQ + r * NB_LDH + 32 * hd + k;
+            const float4 a0 = *reinterpret_cast<const float4*>(ap);
+            const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
+            acc[r] = fmaf(a0.x, b[0], acc[r]); acc[r] = fmaf(a0.y, b[1], acc[r]);
+            acc[r] = fmaf(a0.z, b[2], acc[r]); acc[r] = fmaf(a0.w, b[3], acc[r]);
+            acc[r] = fmaf(a1.x, b[4], acc[r]); acc[r] = fmaf(a1.y, b[5], acc[r]);
+            acc[r] = fmaf(a1.z, b[6], acc[r]); acc[r] = fmaf(a1.w, b[7], acc[r]);
+          }
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) sQT[(r * 4 + hd) * NB_LDH + c] = acc[r];
+      }
+    }
     cta_sync();
     NLB_STAMP(9);
     // ---- attention scores + softmax over the K neighbours -----------------------------------------------------------------

@@ -33,7 +33,9 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
-__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : expm1f(x); }
+// ELU(alpha=1).  exp(x) - 1 with the hardware exponential: absolute error ~1e-7 for x < 0 (the library expm1f costs ~40
+// instructions per element and was 15 % of aggregate_kernel's samples); far inside the 1e-4 parity bar.
+__device__ __forceinline__ float elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 __device__ __forceinline__ float softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
 

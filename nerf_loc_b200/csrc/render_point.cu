@@ -265,36 +265,58 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
 
   AGG_STAMP(4);
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
+  // features: a warp handles two rows per iteration and requests all 2 x 4 taps x 3 chunks (24 independent 8-byte loads
+  // per lane) before it consumes any; addresses are clamped into the map and taps outside carry weight 0.
+  for (int rb = warp; rb < 128; rb += 2 * (NT / 32)) {
+    float2 q[2][4][3];
+    float wt[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int r = rb + u * (NT / 32);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        wt[u][t] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) q[u][t][j] = make_float2(0.f, 0.f);
+      }
+      if (r < rows) {
+        const float* ri = sRI + r * RI_N;
+        const int v = r % V;
+        const Taps tf = make_taps(ri[RI_FX], ri[RI_FY], sc.w, sc.h, true);
+        const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
+        const int fx0 = min(max(tf.x0, 0), sc.w - 1), fx1 = min(max(tf.x0 + 1, 0), sc.w - 1);
+        const int fy0 = min(max(tf.y0, 0), sc.h - 1), fy1 = min(max(tf.y0 + 1, 0), sc.h - 1);
+        const float* tp[4] = {fb + ((size_t)fy0 * sc.w + fx0) * C_FEAT, fb + ((size_t)fy0 * sc.w + fx1) * C_FEAT,
+                              fb + ((size_t)fy1 * sc.w + fx0) * C_FEAT, fb + ((size_t)fy1 * sc.w + fx1) * C_FEAT};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          wt[u][t] = tf.w[t];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) q[u][t][j] = __ldg(reinterpret_cast<const float2*>(tp[t] + j * 64));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      float* frow = sF + (rb + u * (NT / 32)) * LDF;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          acc.x = fmaf(q[u][t][j].x, wt[u][t], acc.x);
+          acc.y = fmaf(q[u][t][j].y, wt[u][t], acc.y);
+        }
+        frow[3 + j * 64 + lane * 2] = acc.x;
+        frow[3 + j * 64 + lane * 2 + 1] = acc.y;
+      }
+    }
+  }
   for (int r = warp; r < 128; r += NT / 32) {
     float* frow = sF + r * LDF;
     if (r < rows) {
       const float* ri = sRI + r * RI_N;
       const int p = r / V, v = r - p * V;
-      const Taps tf = make_taps(ri[RI_FX], ri[RI_FY], sc.w, sc.h, true);
-      const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
-      // branch-free: the 12 loads of the 4 taps are all in flight before the first use
-      const int fx0 = min(max(tf.x0, 0), sc.w - 1), fx1 = min(max(tf.x0 + 1, 0), sc.w - 1);
-      const int fy0 = min(max(tf.y0, 0), sc.h - 1), fy1 = min(max(tf.y0 + 1, 0), sc.h - 1);
-      const float* tp[4] = {fb + ((size_t)fy0 * sc.w + fx0) * C_FEAT, fb + ((size_t)fy0 * sc.w + fx1) * C_FEAT,
-                            fb + ((size_t)fy1 * sc.w + fx0) * C_FEAT, fb + ((size_t)fy1 * sc.w + fx1) * C_FEAT};
-      float2 q[4][3];
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) q[t][j] = __ldg(reinterpret_cast<const float2*>(tp[t] + j * 64));
-      float2 acc[3] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          acc[j].x = fmaf(q[t][j].x, tf.w[t], acc[j].x);
-          acc[j].y = fmaf(q[t][j].y, tf.w[t], acc[j].y);
-        }
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        frow[3 + j * 64 + lane * 2] = acc[j].x;
-        frow[3 + j * 64 + lane * 2 + 1] = acc[j].y;
-      }
       // rgb: lanes 0..3 fetch one tap each
       const Taps ti = make_taps(ri[RI_IX], ri[RI_IY], sc.W, sc.H, true);
       float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -307,30 +329,36 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       c.x += __shfl_xor_sync(0xffffffffu, c.x, 2); c.y += __shfl_xor_sync(0xffffffffu, c.y, 2); c.z += __shfl_xor_sync(0xffffffffu, c.z, 2);
       if (lane == 0) {
         frow[0] = c.x; frow[1] = c.y; frow[2] = c.z;
-        frow[195] = ri[RI_VIS];
-        // colour-blend ray difference (ibrnet.py:144-167) between the query camera and view v
-        const float x = sPt[p * 4], y = sPt[p * 4 + 1], z = sPt[p * 4 + 2];
-        const float* cc = sc.cams + v * 32 + 24;
-        float ax = sc.qc[0] - x, ay = sc.qc[1] - y, az = sc.qc[2] - z;
-        float an = sqrtf(ax * ax + ay * ay + az * az) + 1e-6f;
-        ax /= an; ay /= an; az /= an;
-        float bx = cc[0] - x, by = cc[1] - y, bz = cc[2] - z;
-        float bn = sqrtf(bx * bx + by * by + bz * bz) + 1e-6f;
-        bx /= bn; by /= bn; bz /= bn;
-        const float dx = ax - bx, dy = ay - by, dz = az - bz;
-        const float dn = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);
-        frow[196] = dx / dn; frow[197] = dy / dn; frow[198] = dz / dn;
-        frow[199] = ax * bx + ay * by + az * bz;
         if (rgbvis_out) {
           float4 o = make_float4(c.x, c.y, c.z, ri[RI_VIS]);
           *reinterpret_cast<float4*>(rgbvis_out + ((n0 + p) * V + v) * 4) = o;
         }
-        if (mvv_out) mvv_out[(n0 + p) * V + v] = ri[RI_VIS];
       }
       if (lane < 28) frow[200 + lane] = 0.f;
     } else {
       for (int k = lane; k < LDF; k += 32) frow[k] = 0.f;
     }
+  }
+  // per-row scalars, one thread per row: visibility column and the colour-blend ray difference (ibrnet.py:144-167)
+  // between the query camera and view v
+  if (tid < rows) {
+    const float* ri = sRI + tid * RI_N;
+    float* frow = sF + tid * LDF;
+    const int p = tid / V, v = tid - p * V;
+    frow[195] = ri[RI_VIS];
+    const float x = sPt[p * 4], y = sPt[p * 4 + 1], z = sPt[p * 4 + 2];
+    const float* cc = sc.cams + v * 32 + 24;
+    float ax = sc.qc[0] - x, ay = sc.qc[1] - y, az = sc.qc[2] - z;
+    const float an = sqrtf(ax * ax + ay * ay + az * az) + 1e-6f;
+    ax /= an; ay /= an; az /= an;
+    float bx = cc[0] - x, by = cc[1] - y, bz = cc[2] - z;
+    const float bn = sqrtf(bx * bx + by * by + bz * bz) + 1e-6f;
+    bx /= bn; by /= bn; bz /= bn;
+    const float dx = ax - bx, dy = ay - by, dz = az - bz;
+    const float dn = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);
+    frow[196] = dx / dn; frow[197] = dy / dn; frow[198] = dz / dn;
+    frow[199] = ax * bx + ay * by + az * bz;
+    if (mvv_out) mvv_out[(n0 + p) * V + v] = ri[RI_VIS];
   }
   cta_sync();
   if (mvf_out) {
