@@ -182,7 +182,7 @@ class ConditionalNeRF(nn.Module):
         self._packed = None
         self._packed_key = None
         self._frame = {}
-        self.chunk_rays = 4096  # rays per kernel wave inside nlb_render_rays
+        self.chunk_rays = 18944  # rays per kernel wave inside nlb_render_rays (148 SMs x 128)
 
     # ---- per-frame cache protocol -------------------------------------------------------------------------------------
     @property

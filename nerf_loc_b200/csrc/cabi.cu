@@ -231,7 +231,7 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
     PointSrc ps{nullptr, nullptr, ro, rd, z_vals, S};
     float* fa = dbg_feature_agg ? dbg_feature_agg + r0 * S * W_HID : fagg;
     prof.mark();
-    if (knn_query_rays(sc.knn, ro, rd, z_vals, rc, S, idx, d2, st)) return 1;
+    if (knn_query_rays(sc.knn, ro, rd, z_vals, sc.sup_geo, rc, S, idx, d2, st)) return 1;
     prof.mark();
     if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, st)) return 1;
     prof.mark();

@@ -256,8 +256,11 @@ struct TopK {
   }
 };
 
+// `bound`: a squared distance that at least K support points are known to lie within (FLT_MAX if unknown).  Nothing
+// strictly farther than it can be part of the answer, so it prunes exactly like the running K-th distance does.
 template <int K>
-__device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy, float qz, TopK<K>& best) {
+__device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy, float qz, TopK<K>& best,
+                                           const float bound = FLT_MAX) {
   constexpr int STACK = 12 * FAN;
   unsigned stk_node[STACK];
   float stk_d[STACK];
@@ -271,7 +274,7 @@ __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy,
   while (sp > 0) {
     --sp;
     const float nd = stk_d[sp];
-    if (nd > best.worst()) continue;  // strict: equal distance may still hide a smaller index
+    if (nd > fminf(best.worst(), bound)) continue;  // strict: equal distance may still hide a smaller index
     const unsigned code = stk_node[sp];
     const int lvl = code >> 28;
     const int node = code & 0x0fffffffu;
@@ -281,7 +284,8 @@ __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy,
       for (int k = 0; k < LEAF; ++k) {
         if (p0 + k < t.M) {
           const float4 p = t.pts[p0 + k];
-          best.push(d2_exact(qx, qy, qz, p.x, p.y, p.z), __float_as_int(p.w));
+          const float d = d2_exact(qx, qy, qz, p.x, p.y, p.z);
+          if (d <= bound) best.push(d, __float_as_int(p.w));
         }
       }
     } else {
@@ -300,7 +304,7 @@ __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy,
           if (cd[k] < nearest_d) { nearest_d = cd[k]; nearest = k; }
         }
       }
-      const float w = best.worst();
+      const float w = fminf(best.worst(), bound);
 #pragma unroll
       for (int k = 0; k < FAN; ++k) {
         if (k < nc && k != nearest && cd[k] <= w && sp < STACK) {
@@ -350,29 +354,50 @@ __global__ void __launch_bounds__(128) knn_query_kernel(const void* __restrict__
 
 // Ray-sample query used by the render path: sample n = r*S + s sits at o_r + d_r * z_s, computed with the
 // reference's operation order (one rounding per multiply/add, conditional_nerf/model.py:498).
+// One thread walks SEG consecutive samples of a ray.  The K neighbours of sample s are real support points, so the largest
+// of their distances to sample s+1 bounds the K-th distance there: every search after the first of a segment starts with a
+// tight, exact pruning radius instead of +inf.  Adjacent lanes hold adjacent rays at the same depth (coherent traversal).
 template <int K>
 __global__ void __launch_bounds__(128) knn_query_rays_kernel(const void* __restrict__ index, const float* __restrict__ rays_o,
                                                              const float* __restrict__ rays_d, const float* __restrict__ z_vals,
-                                                             int64_t R, int S, int* idx32, float* dist2) {
+                                                             const float* __restrict__ sup_geo, int64_t R, int S, int SEG,
+                                                             int* idx32, float* dist2) {
   __shared__ KnnTree tree;
   if (threadIdx.x == 0) tree = load_tree(index);
   __syncthreads();
-  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= R * S) return;
-  const int64_t r = i / S;
-  const int s = (int)(i - r * S);
-  const float z = z_vals[s];
-  const float qx = __fadd_rn(rays_o[r * 3 + 0], __fmul_rn(rays_d[r * 3 + 0], z));
-  const float qy = __fadd_rn(rays_o[r * 3 + 1], __fmul_rn(rays_d[r * 3 + 1], z));
-  const float qz = __fadd_rn(rays_o[r * 3 + 2], __fmul_rn(rays_d[r * 3 + 2], z));
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int nseg = (S + SEG - 1) / SEG;
+  if (g >= R * nseg) return;
+  const int64_t r = g % R;
+  const int s0 = (int)(g / R) * SEG;
+  const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
+  const float dx = rays_d[r * 3 + 0], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
   TopK<K> best;
-  best.init();
-  knn_search<K>(tree, qx, qy, qz, best);
+  bool have_prev = false;
+  for (int s = s0; s < min(S, s0 + SEG); ++s) {
+    const float z = z_vals[s];
+    const float qx = __fadd_rn(ox, __fmul_rn(dx, z));
+    const float qy = __fadd_rn(oy, __fmul_rn(dy, z));
+    const float qz = __fadd_rn(oz, __fmul_rn(dz, z));
+    float bound = FLT_MAX;
+    if (have_prev) {
+      bound = 0.f;
 #pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const bool ok = best.id[k] != 0x7fffffff;
-    idx32[i * K + k] = ok ? best.id[k] : 0;
-    dist2[i * K + k] = ok ? best.d[k] : 0.f;
+      for (int k = 0; k < K; ++k) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(sup_geo + (size_t)best.id[k] * 8));
+        bound = fmaxf(bound, d2_exact(qx, qy, qz, p.x, p.y, p.z));
+      }
+    }
+    best.init();
+    knn_search<K>(tree, qx, qy, qz, best, bound);
+    const int64_t i = r * S + s;
+    have_prev = best.id[K - 1] != 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const bool ok = best.id[k] != 0x7fffffff;
+      idx32[i * K + k] = ok ? best.id[k] : 0;
+      dist2[i * K + k] = ok ? best.d[k] : 0.f;
+    }
   }
 }
 
@@ -392,12 +417,14 @@ int knn_query(const void* index, const float* p1, int64_t N, int K, int64_t* idx
   return check_launch("knn_query");
 }
 
-int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, int64_t R, int S,
-                   int* idx32, float* dist2, cudaStream_t st) {
-  const int64_t N = R * S;
-  if (N <= 0) return 0;
+int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, const float* sup_geo,
+                   int64_t R, int S, int* idx32, float* dist2, cudaStream_t st) {
+  if (R * S <= 0) return 0;
   const int T = 128;
-  knn_query_rays_kernel<8><<<(unsigned)((N + T - 1) / T), T, 0, st>>>(index, rays_o, rays_d, z_vals, R, S, idx32, dist2);
+  const int SEG = S >= 64 ? 16 : 8;
+  const int64_t threads = R * ((S + SEG - 1) / SEG);
+  knn_query_rays_kernel<8><<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(index, rays_o, rays_d, z_vals, sup_geo, R, S, SEG,
+                                                                           idx32, dist2);
   return check_launch("knn_query_rays");
 }
 
