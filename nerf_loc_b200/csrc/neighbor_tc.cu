@@ -62,9 +62,9 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     // ------------------------------------------------ controller -------------------------------------------------------
     if (lane == 0) {
       const uint32_t hi = tc::smem_u32(actHi), lo = tc::smem_u32(actLo);
-      layers[0] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w1b), hi, lo, NB_SBO1, 6, 128, 0};
-      layers[1] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w2), hi, lo, NB_SBO2, 8, 128, 0};
-      layers[2] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w3), hi, lo, NB_SBO2, 8, 128, 0};
+      layers[0] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w1b), hi, lo, NB_SBO1, 6, 128, 0, tc::WAIT_A | tc::SIGNAL_D};
+      layers[1] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w2), hi, lo, NB_SBO2, 8, 128, 0, tc::WAIT_A | tc::SIGNAL_D};
+      layers[2] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w3), hi, lo, NB_SBO2, 8, 128, 0, tc::WAIT_A | tc::SIGNAL_D};
       tc::controller(sy, stg, tmem, layers, 3);
     }
   } else {

@@ -257,4 +257,34 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
   }
 }
 
+// Register-tile GEMM against a weight tile that is ALREADY resident in shared memory (no staging, no barriers):
+// acc[i][j] += sum_k A[r0+i][k] * Bs[k*ldb + col(j)], columns col(j) = (j/4)*gstride + c0 + (j%4).
+template <int TM, int TN>
+__device__ __forceinline__ void gemm_resident(const float* __restrict__ arow, const int lda, const float* __restrict__ Bs,
+                                              const int ldb, const int c0, const int gstride, const int K,
+                                              float (&acc)[TM][TN]) {
+  constexpr int NG = TN / 4;
+#pragma unroll 2
+  for (int kk = 0; kk < K; kk += 4) {
+    float4 a[TM];
+#pragma unroll
+    for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(arow + i * lda + kk);
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      float b[TN];
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const float4 bv = *reinterpret_cast<const float4*>(Bs + (kk + k4) * ldb + g * gstride + c0);
+        b[g * 4 + 0] = bv.x; b[g * 4 + 1] = bv.y; b[g * 4 + 2] = bv.z; b[g * 4 + 3] = bv.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i) {
+        const float av = k4 == 0 ? a[i].x : (k4 == 1 ? a[i].y : (k4 == 2 ? a[i].z : a[i].w));
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av, b[j], acc[i][j]);
+      }
+    }
+  }
+}
+
 }  // namespace nlb

@@ -107,6 +107,15 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   const float near_ = sc.near_, far_ = sc.far_;
 
   AGG_STAMP(0);
+  // decoder weights (32 KB) go into the staging ring, which is idle until phase 7: dec1 as [32][128], dec2 as [32][128]
+  // with the four heads side by side.  Requested now, consumed in phase 3.
+  for (int i = tid; i < 1024; i += NT) cp_async16(sB + i * 4, w.dec1 + i * 4);
+  for (int i = tid; i < 1024; i += NT) {
+    const int hd = i >> 8, k = (i >> 3) & 31, j4 = i & 7;   // source chunk (head, k, j4) of the 4 x [32][32] blocks
+    cp_async16(sB + 4096 + k * 128 + hd * 32 + j4 * 4, w.dec2 + hd * 1024 + k * 32 + j4 * 4);
+  }
+  cp_async_commit();
+
   // ---- phase 1: projections, one thread per (sample, view) row -----------------------------------------------
   if (tid < 128) {
     float* ri = sRI + tid * RI_N;
@@ -199,14 +208,48 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
 
   AGG_STAMP(2);
   // ---- phase 3: visibility decoder ------------------------------------------------------------------------------
-  tile_gemm<8, 8, 128, false>(plainA(sX, LDX), 128, w.dec1, 128, 32, sB,
-                              [&](int r, int c, float v) { sH[r * LDH + c] = elu(v + __ldg(w.dec1_b + c)); });
-  for (int hd = 0; hd < 4; ++hd) {
-    tile_gemm<4, 4, 32, true>(plainA(sH + 32 * hd, LDH), 128, w.dec2 + 1024 * hd, 32, 32, sB, [&](int r, int c, float v) {
-      sH[r * LDH + 32 * hd + c] = elu(v + __ldg(w.dec2_b + 32 * hd + c));
-    });
+  cp_async_wait<0>();
+  cta_sync();  // decoder weights landed, sX complete
+  AGG_STAMP(9);
+  {
+    // layer 1 of the four heads at once: [128 x 32] -> [128 x 128], 8 x 8 register tile
+    const int tc = tid & 15, r0 = (tid >> 4) * 8;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    gemm_resident<8, 8>(sX + r0 * LDX, LDX, sB, 128, tc * 4, 64, 32, acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = (j >> 2) * 64 + tc * 4 + (j & 3);
+        sH[(r0 + i) * LDH + c] = elu(acc[i][j] + __ldg(w.dec1_b + c));
+      }
   }
   cta_sync();
+  AGG_STAMP(10);
+  {
+    // layer 2, block diagonal: head h maps columns [32h, 32h+32) to themselves; 16 x 4 register tile inside one head
+    const int cg = tid & 31, r0 = (tid >> 5) * 16, hd = cg >> 3;
+    float acc[16][4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    gemm_resident<16, 4>(sH + r0 * LDH + 32 * hd, LDH, sB + 4096, 128, cg * 4, 0, 32, acc);
+    cta_sync();  // every thread has read its inputs: write in place
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int c = cg * 4 + j;
+        sH[(r0 + i) * LDH + c] = elu(acc[i][j] + __ldg(w.dec2_b + c));
+      }
+  }
+  cta_sync();
+  AGG_STAMP(11);
   if (tid < rows) {
     const float* hrow = sH + tid * LDH;
     float o[6];

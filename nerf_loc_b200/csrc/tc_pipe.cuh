@@ -27,7 +27,11 @@ struct Layer {        // D[128 x N] (+)= A[128 x K] * B[N x K]^T
   int nkt;                   // K / 16
   int N;                     // multiple of 16, <= 128
   uint32_t tmem_col;         // accumulator column offset inside the CTA's TMEM allocation
+  uint32_t flags;            // WAIT_A | SIGNAL_D | ACCUM
 };
+constexpr uint32_t WAIT_A = 1u;    // wait for the compute warps' a_ready before the first MMA of this GEMM
+constexpr uint32_t SIGNAL_D = 2u;  // commit d_ready after the last MMA of this GEMM
+constexpr uint32_t ACCUM = 4u;     // accumulate onto what is already in the TMEM columns (K split over several GEMMs)
 
 struct Sync {
   uint64_t full[NSTAGE];
@@ -110,7 +114,7 @@ __device__ __forceinline__ void controller(Sync& sy, unsigned char* stages, uint
   while (copied < total && copied < NSTAGE - 1) copy_next();
   while (issued < total) {
     const Layer& l = L[m_layer];
-    if (m_kt == 0) {
+    if (m_kt == 0 && (l.flags & WAIT_A)) {
       mbar_wait(&sy.a_ready, a_par);
       a_par ^= 1u;
     }
@@ -130,12 +134,12 @@ __device__ __forceinline__ void controller(Sync& sy, unsigned char* stages, uint
       for (int ks = 0; ks < KTB / 8; ++ks) {
         const uint64_t ad = smem_desc(a + (uint32_t)(m_kt * (KTB / 4) + ks * 2) * 128u, 128u, l.a_sbo);
         const uint64_t bd = smem_desc(b + (uint32_t)ks * 256u, 128u, B_SBO);
-        mma_tf32(d, ad, bd, idesc, (m_kt | pass | ks) != 0 ? 1u : 0u);
+        mma_tf32(d, ad, bd, idesc, ((m_kt | pass | ks) != 0 || (l.flags & ACCUM)) ? 1u : 0u);
       }
     }
     mma_commit(&sy.empty[s]);
     if (++m_kt == l.nkt) {
-      mma_commit(&sy.d_ready);
+      if (l.flags & SIGNAL_D) mma_commit(&sy.d_ready);
       m_kt = 0;
       ++m_layer;
     }

@@ -29,3 +29,4 @@ an = ["proj", "vis gather", "decoder GEMMs+heads", "view weights", "rgb/feat gat
 for i in range(8):
     print(f"agg {an[i]:28s} {v[17+i]-v[16+i]:8d} clk")
 print("agg total", v[24] - v[16])
+print("decoder detail: wait weights/sX", v[25]-v[18], "dec1", v[26]-v[25], "dec2", v[27]-v[26], "heads+vis", v[19]-v[27])
