@@ -145,7 +145,7 @@ int nlb_fine_match(const float* packed_match_weights, int C, const float* f0, co
 /* ---- self-test of the tcgen05 building blocks: C[128,128] = A[128,K] * W[128,K]^T, K multiple of 8 <= 64;
  * mode 0 = single-pass tf32, 1 = 3xTF32 (fp32-equivalent) -------------------------------------------------------------- */
 /* clock64() phase stamps of block 0 of the last neighbor_kernel launch (debug aid) */
-int nlb_debug_read_prof(long long* out /*[n]*/, int n /*<= 32*/);
+int nlb_debug_read_prof(long long* out /*[n]*/, int n /*<= 64: 0..31 neighbour/aggregate, 32..63 ray kernel*/);
 int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C, void* stream);
 
 #ifdef __cplusplus

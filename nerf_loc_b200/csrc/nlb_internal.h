@@ -59,6 +59,9 @@ struct RenderW {
   const float *tc_w1b, *tc_w2, *tc_w3;
   // ray stage
   UnetLayer u[7];               // conv1, conv2, conv3, trans_conv3, trans_conv2, trans_conv1, conv_out
+  const float* tcu[7][3];       // tensor-core operands of the RayUnet layers (see pack.cu)
+  const float* tcu_x2[3];       // conv_out, x2 part (K = 32)
+  const float *tc_bl1a, *tc_ft1;
   const float *sig_w, *sig_b;   // [128], [1]
   const float *ft1, *ft1_b;     // [128][128], [128]
   const float *ft2, *ft2_b;     // [128][192], [192]

@@ -68,6 +68,15 @@ static RenderW layout(const float* base, int S, size_t* total) {
     w.u[l].g = a.take((size_t)sl * UN_COUT[l]);
     w.u[l].be = a.take((size_t)sl * UN_COUT[l]);
   }
+  // tensor-core copies of the ray stage (3xTF32 hi|lo tiles): per RayUnet layer three GEMM operands [Cout x Cin]
+  // (conv: taps 0,1,2; transposed conv: taps 1,2,0), conv_out split into its x (K=128) and x2 (K=32) parts
+  for (int l = 0; l < 7; ++l)
+    for (int t = 0; t < 3; ++t) {
+      if (l == 6) { w.tcu[l][t] = a.take(2 * 128 * 128); w.tcu_x2[t] = a.take(2 * 128 * 32); }
+      else w.tcu[l][t] = a.take((size_t)2 * UN_COUT[l] * UN_CIN[l]);
+    }
+  w.tc_bl1a = a.take(2 * 32 * 128);
+  w.tc_ft1 = a.take(2 * 128 * 128);
   w.sig_w = a.take(128); w.sig_b = a.take(1);
   w.ft1 = a.take(128 * 128); w.ft1_b = a.take(128);
   w.ft2 = a.take(128 * 192); w.ft2_b = a.take(192);
@@ -110,11 +119,12 @@ __global__ void pack_conv_kernel(float* dst, const float* __restrict__ src, int 
 
 // tensor-core B operand: W [N][src_ld] (reference layout, K-major) -> per K-tile of 16: hi tile then lo tile, each the
 // canonical no-swizzle K-major layout (8-row core matrices of 16 bytes, 8-row groups 512 bytes apart); 3xTF32 split.
-__global__ void pack_tcb_kernel(float* dst, const float* __restrict__ src, int N, int Kp, int src_ld, int src_off, int Kv) {
+__global__ void pack_tcb_kernel(float* dst, const float* __restrict__ src, int N, int Kp, int src_ld, int src_off, int Kv,
+                                int src_ks) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * Kp) return;
   const int n = i / Kp, k = i % Kp;
-  const float x = k < Kv ? src[(size_t)n * src_ld + src_off + k] : 0.f;
+  const float x = k < Kv ? src[(size_t)n * src_ld + src_off + (size_t)k * src_ks] : 0.f;
   const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   const float lo = x - hi;
   const int kt = k / 16, kl = k % 16;
@@ -136,9 +146,10 @@ struct Packer {
   void c(const float* dst, int src, int n, int dst_off = 0) {
     pack_copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst) + dst_off, p[src], n);
   }
-  void tcb(const float* dst, int src, int N, int Kp, int src_ld, int src_off, int Kv) {
+  // B[n][k] = src[n*src_ld + src_off + k*src_ks]
+  void tcb(const float* dst, int src, int N, int Kp, int src_ld, int src_off, int Kv, int src_ks = 1) {
     const int n = N * Kp;
-    pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv);
+    pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv, src_ks);
   }
   void conv(const float* dst, int src, int Cin, int Cout, int ntaps, int t0, int t1, int t2, bool tr) {
     const int n = ntaps * Cin * Cout;
@@ -208,6 +219,24 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
       k.t(w.u[l].be, b + 3, sl, co, sl, 0, sl);
     }
   }
+  if (S > 0) {
+    for (int l = 0; l < 7; ++l) {
+      const int b = UNET + 4 * l, ci = UN_CIN[l], co = UN_COUT[l];
+      for (int t = 0; t < 3; ++t) {
+        if (UN_TR[l]) {                       // ConvTranspose1d weight [ci][co][3]: operands in the order tap 1, 2, 0
+          const int tap = t == 0 ? 1 : (t == 1 ? 2 : 0);
+          k.tcb(w.tcu[l][t], b, co, ci, 3, tap, ci, co * 3);
+        } else if (l == 6) {                  // conv_out [128][160][3]: x part then x2 part
+          k.tcb(w.tcu[l][t], b, 128, 128, 160 * 3, t, 128, 3);
+          k.tcb(w.tcu_x2[t], b, 128, 32, 160 * 3, 128 * 3 + t, 32, 3);
+        } else {                              // Conv1d weight [co][ci][3]
+          k.tcb(w.tcu[l][t], b, co, ci, ci * 3, t, ci, 3);
+        }
+      }
+    }
+  }
+  k.tcb(w.tc_bl1a, BL0_W, 32, 128, 328, 0, 128);
+  k.tcb(w.tc_ft1, FT0_W, 128, 128, 128, 0, 128);
   k.c(w.sig_w, SIG_W, 128);  k.c(w.sig_b, SIG_B, 1);
   k.t(w.ft1, FT0_W, 128, 128, 128, 0, 128);  k.c(w.ft1_b, FT0_B, 128);
   k.t(w.ft2, FT2_W, 128, 192, 128, 0, 128);  k.c(w.ft2_b, FT2_B, 192);

@@ -31,15 +31,20 @@ struct Layer {        // D[128 x N] (+)= A[128 x K] * B[N x K]^T
 };
 constexpr uint32_t WAIT_A = 1u;    // wait for the compute warps' a_ready before the first MMA of this GEMM
 constexpr uint32_t SIGNAL_D = 2u;  // commit d_ready after the last MMA of this GEMM
+constexpr uint32_t SIGNAL_AUX = 8u; // commit d_aux instead of d_ready
 constexpr uint32_t ACCUM = 4u;     // accumulate onto what is already in the TMEM columns (K split over several GEMMs)
 
-struct Sync {
-  uint64_t full[NSTAGE];
-  uint64_t empty[NSTAGE];
+template <int NS>
+struct SyncT {
+  uint64_t full[NS];
+  uint64_t empty[NS];
   uint64_t a_ready;
   uint64_t d_ready;
+  uint64_t d_aux;     // completion of a GEMM that runs right behind another signalled one (an mbarrier must not run two
+                      // phases ahead of its waiters)
   uint32_t tmem_slot;
 };
+using Sync = SyncT<NSTAGE>;
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -54,13 +59,15 @@ __device__ __forceinline__ void bulk_copy(void* dst_smem, const void* src_gmem, 
 }
 
 // executed by ALL threads of the CTA (NT compute + 32 controller) at kernel start
-__device__ __forceinline__ uint32_t setup(Sync& sy, int warp, int lane, uint32_t tmem_cols) {
+template <int NS>
+__device__ __forceinline__ uint32_t setup(SyncT<NS>& sy, int warp, int lane, uint32_t tmem_cols) {
   if (warp == 8) {
     tmem_alloc(&sy.tmem_slot, tmem_cols);
     if (lane == 0) {
-      for (int i = 0; i < NSTAGE; ++i) { mbar_init(&sy.full[i], 1); mbar_init(&sy.empty[i], 1); }
+      for (int i = 0; i < NS; ++i) { mbar_init(&sy.full[i], 1); mbar_init(&sy.empty[i], 1); }
       mbar_init(&sy.a_ready, 256);
       mbar_init(&sy.d_ready, 1);
+      mbar_init(&sy.d_aux, 1);
     }
   }
   fence_before_sync();
@@ -70,7 +77,8 @@ __device__ __forceinline__ uint32_t setup(Sync& sy, int warp, int lane, uint32_t
 }
 
 // executed by ALL threads at kernel end (after the last TMEM read)
-__device__ __forceinline__ void teardown(Sync& sy, int warp, uint32_t tmem, uint32_t tmem_cols) {
+template <int NS>
+__device__ __forceinline__ void teardown(SyncT<NS>& sy, int warp, uint32_t tmem, uint32_t tmem_cols) {
   fence_before_sync();
   __syncthreads();
   if (warp == 8) {
@@ -80,28 +88,31 @@ __device__ __forceinline__ void teardown(Sync& sy, int warp, uint32_t tmem, uint
 }
 
 // compute threads: the A operand of the next layer is in shared memory
-__device__ __forceinline__ void a_ready(Sync& sy) {
+template <int NS>
+__device__ __forceinline__ void a_ready(SyncT<NS>& sy) {
   fence_async_smem();
   fence_before_sync();
   mbar_arrive(&sy.a_ready);
 }
 // compute threads: wait for the accumulator of the current layer
-__device__ __forceinline__ void wait_d(Sync& sy, uint32_t& parity) {
+template <int NS>
+__device__ __forceinline__ void wait_d(SyncT<NS>& sy, uint32_t& parity) {
   mbar_wait(&sy.d_ready, parity);
   parity ^= 1u;
   fence_after_sync();
 }
 
 // controller lane: runs `nlayers` GEMMs back to back
-__device__ __forceinline__ void controller(Sync& sy, unsigned char* stages, uint32_t tmem, const Layer* L, int nlayers) {
+template <int NS>
+__device__ __forceinline__ void controller(SyncT<NS>& sy, unsigned char* stages, uint32_t tmem, const Layer* L, int nlayers) {
   int total = 0;
   for (int i = 0; i < nlayers; ++i) total += L[i].nkt;
   int c_layer = 0, c_kt = 0, copied = 0;
   int m_layer = 0, m_kt = 0, issued = 0;
   uint32_t full_par = 0, empty_par = 0, a_par = 0;
   auto copy_next = [&]() {
-    const int s = copied % NSTAGE;
-    if (copied >= NSTAGE) {
+    const int s = copied % NS;
+    if (copied >= NS) {
       mbar_wait(&sy.empty[s], (empty_par >> s) & 1u);
       empty_par ^= 1u << s;
     }
@@ -111,14 +122,14 @@ __device__ __forceinline__ void controller(Sync& sy, unsigned char* stages, uint
     ++copied;
     if (++c_kt == L[c_layer].nkt) { c_kt = 0; ++c_layer; }
   };
-  while (copied < total && copied < NSTAGE - 1) copy_next();
+  while (copied < total && copied < NS - 1) copy_next();
   while (issued < total) {
     const Layer& l = L[m_layer];
     if (m_kt == 0 && (l.flags & WAIT_A)) {
       mbar_wait(&sy.a_ready, a_par);
       a_par ^= 1u;
     }
-    const int s = issued % NSTAGE;
+    const int s = issued % NS;
     mbar_wait(&sy.full[s], (full_par >> s) & 1u);
     full_par ^= 1u << s;
     fence_after_sync();
@@ -140,6 +151,7 @@ __device__ __forceinline__ void controller(Sync& sy, unsigned char* stages, uint
     mma_commit(&sy.empty[s]);
     if (++m_kt == l.nkt) {
       if (l.flags & SIGNAL_D) mma_commit(&sy.d_ready);
+      if (l.flags & SIGNAL_AUX) mma_commit(&sy.d_aux);
       m_kt = 0;
       ++m_layer;
     }

@@ -17,8 +17,8 @@ rays = {"rays_o": ro[150000:150000 + 4736].to(dev), "rays_d": rd[150000:150000 +
 for _ in range(2):
     model.render_rays(data, rays)
 torch.cuda.synchronize()
-buf = (ctypes.c_longlong * 32)()
-_lib.load().nlb_debug_read_prof(buf, 32)
+buf = (ctypes.c_longlong * 64)()
+_lib.load().nlb_debug_read_prof(buf, 64)
 v = list(buf)
 names = ["phase0 (PE, rd_fc, A1 write)", "wait L1", "epi L1", "wait L2", "epi L2", "wait L3", "epi L3", "sync", "q + q~ GEMMs", "scores+softmax", "ctx", "o + fc GEMMs", "LN + out"]
 for i in range(12):
@@ -30,3 +30,10 @@ for i in range(8):
     print(f"agg {an[i]:28s} {v[17+i]-v[16+i]:8d} clk")
 print("agg total", v[24] - v[16])
 print("decoder detail: wait weights/sX", v[25]-v[18], "dec1", v[26]-v[25], "dec2", v[27]-v[26], "heads+vis", v[19]-v[27])
+
+rn = ["load x", "blend weights + wait blend GEMM", "blend MLP + softmax", "wait conv1", "epi conv1", "wait conv2", "epi conv2", "wait conv3", "epi conv3",
+      "wait tconv3", "epi tconv3", "wait tconv2", "epi tconv2", "wait tconv1", "epi tconv1 + reload x", "wait conv_out", "epi conv_out", "composite", "feat"]
+rv = v[32:]
+for i in range(18):
+    print(f"ray {rn[i]:34s} {rv[i+1]-rv[i]:8d} clk")
+print("ray total", rv[18] - rv[0])
