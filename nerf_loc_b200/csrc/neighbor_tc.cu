@@ -35,7 +35,7 @@ constexpr uint32_t NB_IDX = NB_SMALL + NB_SMALL_BYTES;           // int idx[128]
 constexpr uint32_t NB_SYNC = NB_IDX + 512;                       // tc::Sync + tc::Layer[3]
 constexpr uint32_t NB_SMEM_BYTES = NB_SYNC + 256 + 3 * 64;
 
-__global__ void __launch_bounds__(NT + 32, 1)
+__global__ void __launch_bounds__(NT + 64, 1)
 neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int K,
                 const int* __restrict__ knn_idx, const float* __restrict__ knn_d2, const float* __restrict__ agg_in,
                 float* __restrict__ fagg_out, float* __restrict__ feature_out, float* __restrict__ weights_out) {
@@ -53,19 +53,23 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
   float* sD = sSc + 512;
   int* sIdx = reinterpret_cast<int*>(smraw + NB_IDX);
   tc::Sync& sy = *reinterpret_cast<tc::Sync*>(smraw + NB_SYNC);
-  tc::Layer* layers = reinterpret_cast<tc::Layer*>(smraw + NB_SYNC + 256);
+  tc::Layer* layer_buf = reinterpret_cast<tc::Layer*>(smraw + NB_SYNC + 128);  // one private copy per service warp
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tmem = tc::setup(sy, warp, lane, 128);
 
-  if (warp == 8) {
-    // ------------------------------------------------ controller -------------------------------------------------------
-    if (lane == 0) {
+  if (warp >= 8) {
+    // ------------------------------------------------ service warps: 8 = MMA issuer, 9 = weight producer -----------------
+    {
+      // warp-uniform: every lane builds the same list and runs the same loop, one elected lane issues
+      tc::Layer* layers = layer_buf + (warp == 9 ? 3 : 0);
       const uint32_t hi = tc::smem_u32(actHi), lo = tc::smem_u32(actLo);
-      layers[0] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w1b), hi, lo, NB_SBO1, 6, 128, 0, tc::WAIT_A | tc::SIGNAL_D};
-      layers[1] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w2), hi, lo, NB_SBO2, 8, 128, 0, tc::WAIT_A | tc::SIGNAL_D};
-      layers[2] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w3), hi, lo, NB_SBO2, 8, 128, 0, tc::WAIT_A | tc::SIGNAL_D};
-      tc::controller(sy, stg, tmem, layers, 3);
+      layers[0] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w1b), hi, lo, NB_SBO1, 6, 128, 16, 0, tc::WAIT_A | tc::SIGNAL_D};
+      layers[1] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w2), hi, lo, NB_SBO2, 8, 128, 16, 0, tc::WAIT_A | tc::SIGNAL_D};
+      layers[2] = tc::Layer{reinterpret_cast<const unsigned char*>(w.tc_w3), hi, lo, NB_SBO2, 8, 128, 16, 0, tc::WAIT_A | tc::SIGNAL_D};
+      __syncwarp();
+      if (warp == 8) tc::mma_issuer(sy, stg, tmem, layers, 3);
+      else tc::producer(sy, stg, layers, 3);
     }
   } else {
     // ------------------------------------------------ compute warps ------------------------------------------------------
@@ -386,7 +390,7 @@ int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, in
   cudaError_t e = cudaFuncSetAttribute(neighbor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NB_SMEM_BYTES);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   const unsigned grid = (unsigned)((N + NB_TP - 1) / NB_TP);
-  neighbor_kernel<<<grid, NT + 32, NB_SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, agg, fagg, feature, weights);
+  neighbor_kernel<<<grid, NT + 64, NB_SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, agg, fagg, feature, weights);
   return check_launch("neighbor_kernel");
 }
 

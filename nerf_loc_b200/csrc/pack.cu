@@ -117,21 +117,21 @@ __global__ void pack_conv_kernel(float* dst, const float* __restrict__ src, int 
   dst[i] = transposed ? src[((size_t)ci * Cout + co) * 3 + t] : src[((size_t)co * Cin + ci) * 3 + t];
 }
 
-// tensor-core B operand: W [N][src_ld] (reference layout, K-major) -> per K-tile of 16: hi tile then lo tile, each the
-// canonical no-swizzle K-major layout (8-row core matrices of 16 bytes, 8-row groups 512 bytes apart); 3xTF32 split.
+// tensor-core B operand: W [N][K] -> per K-tile of `ktile` = 2048 / N columns (a 16 KB tile): hi tile then lo tile, each the
+// canonical no-swizzle K-major layout (8-row core matrices of 16 bytes, 8-row groups ktile*32 bytes apart); 3xTF32 split.
 __global__ void pack_tcb_kernel(float* dst, const float* __restrict__ src, int N, int Kp, int src_ld, int src_off, int Kv,
-                                int src_ks) {
+                                int src_ks, int ktile) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * Kp) return;
   const int n = i / Kp, k = i % Kp;
   const float x = k < Kv ? src[(size_t)n * src_ld + src_off + (size_t)k * src_ks] : 0.f;
   const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   const float lo = x - hi;
-  const int kt = k / 16, kl = k % 16;
-  const size_t base = (size_t)kt * (2 * N * 16);
-  const size_t off = (size_t)(n / 8) * 128 + (kl / 4) * 32 + (n % 8) * 4 + (kl % 4);
+  const int kt = k / ktile, kl = k % ktile;
+  const size_t base = (size_t)kt * (2 * N * ktile);
+  const size_t off = (size_t)(n / 8) * (ktile * 8) + (kl / 4) * 32 + (n % 8) * 4 + (kl % 4);
   dst[base + off] = hi;
-  dst[base + (size_t)N * 16 + off] = lo;
+  dst[base + (size_t)N * ktile + off] = lo;
 }
 
 namespace {
@@ -149,7 +149,8 @@ struct Packer {
   // B[n][k] = src[n*src_ld + src_off + k*src_ks]
   void tcb(const float* dst, int src, int N, int Kp, int src_ld, int src_off, int Kv, int src_ks = 1) {
     const int n = N * Kp;
-    pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv, src_ks);
+    pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv, src_ks,
+                                                     2048 / N);
   }
   void conv(const float* dst, int src, int Cin, int Cout, int ntaps, int t0, int t1, int t2, bool tr) {
     const int n = ntaps * Cin * Cout;

@@ -43,7 +43,7 @@ constexpr uint32_t RY_STG = 163840;                         // RY_NS x 16 KB wei
 constexpr uint32_t RY_MISC = RY_STG + RY_NS * 16384;        // small arrays, barriers, layer list
 constexpr uint32_t RY_MISC_FLOATS = 512 + 512 + 64 + 256 + 256 + 256;
 constexpr uint32_t RY_SYNC = RY_MISC + RY_MISC_FLOATS * 4;
-constexpr uint32_t RY_SMEM_BYTES = RY_SYNC + 128 + 28 * 48;  // sizeof(tc::Layer) == 40
+constexpr uint32_t RY_SMEM_BYTES = RY_SYNC + 128 + 2 * 28 * 40;  // two layer lists, sizeof(tc::Layer) == 40
 constexpr uint32_t SBO128 = 4096, SBO256 = 8192, SBO32 = 1024;
 
 struct RayCtx {
@@ -191,14 +191,23 @@ __device__ __forceinline__ void dec_epilogue(const RayCtx& c, const uint32_t tme
 }
 
 __device__ __forceinline__ void load_x(unsigned char* sm, const float* __restrict__ fagg, int64_t s0, int S, int tid) {
-  for (int i = tid; i < S * 32; i += NT) {
-    const int s = i >> 5, c4 = i & 31;
-    const float4 v = __ldg(reinterpret_cast<const float4*>(fagg + (s0 + s) * W_HID + c4 * 4));
-    tc::store_split4(sm + RY_X_HI, sm + RY_X_LO, s, c4 * 4, SBO128, v.x, v.y, v.z, v.w);
+  // four independent 16-byte loads in flight per thread before the first split / store
+  for (int i0 = tid; i0 < S * 32; i0 += 4 * NT) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * NT;
+      v[u] = i < S * 32 ? __ldg(reinterpret_cast<const float4*>(fagg + (s0 + (i >> 5)) * W_HID + (i & 31) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * NT;
+      if (i < S * 32) tc::store_split4(sm + RY_X_HI, sm + RY_X_LO, i >> 5, (i & 31) * 4, SBO128, v[u].x, v[u].y, v[u].z, v[u].w);
+    }
   }
 }
 
-__global__ void __launch_bounds__(NT + 32, 1)
+__global__ void __launch_bounds__(NT + 64, 1)
 ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals, const int S, const int white_bkgd,
            const float* __restrict__ fagg, const float* __restrict__ partial, const float* __restrict__ rgbvis,
            const unsigned char* __restrict__ nvalid, float* __restrict__ rgb_out, float* __restrict__ depth_out,
@@ -214,7 +223,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
   float* sSigP = xchD + 256;        // [2][128] sigma partial dots
   float* sSig = sV, *sT = sV + 128, *sWt = sV + 256, *sZ = sV + 384;
   tc::SyncT<RY_NS>& sy = *reinterpret_cast<tc::SyncT<RY_NS>*>(sm + RY_SYNC);
-  tc::Layer* layers = reinterpret_cast<tc::Layer*>(sm + RY_SYNC + 128);
+  tc::Layer* layer_buf = reinterpret_cast<tc::Layer*>(sm + RY_SYNC + 128);  // one private copy per service warp
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t tmem = tc::setup(sy, warp, lane, 512);
@@ -222,38 +231,43 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
   const int64_t s0 = ray * S;
   const int V = sc.V;
 
-  if (warp == 8) {
-    // ------------------------------------------------ controller -------------------------------------------------------
-    if (lane == 0) {
+  if (warp >= 8) {
+    // ------------------------------------------------ service warps: 8 = MMA issuer, 9 = weight producer -----------------
+    {
+      // warp-uniform: every lane builds the same list and runs the same loop, one elected lane issues
+      tc::Layer* layers = layer_buf + (warp == 9 ? 28 : 0);
       const uint32_t b = tc::smem_u32(sm);
       auto B = [](const float* p) { return reinterpret_cast<const unsigned char*>(p); };
       int n = 0;
+      // GEMM list: {weights, A hi, A lo, A SBO, K tiles, N, K per tile (2048 / N), TMEM column, flags}
       // blend (feature_agg half of layer 1) and conv1 read x
-      layers[n++] = tc::Layer{B(w.tc_bl1a), b + RY_X_HI, b + RY_X_LO, SBO128, 8, 32, 448, tc::WAIT_A | tc::SIGNAL_D};
+      layers[n++] = tc::Layer{B(w.tc_bl1a), b + RY_X_HI, b + RY_X_LO, SBO128, 2, 32, 64, 448, tc::WAIT_A | tc::SIGNAL_D};
       for (int t = 0; t < 3; ++t)
-        layers[n++] = tc::Layer{B(w.tcu[0][t]), b + RY_X_HI, b + RY_X_LO, SBO128, 8, 64, (uint32_t)(64 * t), t == 2 ? tc::SIGNAL_D : 0u};
+        layers[n++] = tc::Layer{B(w.tcu[0][t]), b + RY_X_HI, b + RY_X_LO, SBO128, 4, 64, 32, (uint32_t)(64 * t), t == 2 ? tc::SIGNAL_D : 0u};
       for (int t = 0; t < 3; ++t)  // conv2 on c1 (K = 64)
-        layers[n++] = tc::Layer{B(w.tcu[1][t]), b + RY_B1_HI, b + RY_B1_LO, SBO128, 4, 128, (uint32_t)(128 * t),
+        layers[n++] = tc::Layer{B(w.tcu[1][t]), b + RY_B1_HI, b + RY_B1_LO, SBO128, 4, 128, 16, (uint32_t)(128 * t),
                                 (t == 0 ? tc::WAIT_A : 0u) | (t == 2 ? tc::SIGNAL_D : 0u)};
       for (int t = 0; t < 3; ++t)  // conv3 on c2 (K = 128 of the 256-wide tile)
-        layers[n++] = tc::Layer{B(w.tcu[2][t]), b + RY_B2_HI, b + RY_B2_LO, SBO256, 8, 128, (uint32_t)(128 * t),
+        layers[n++] = tc::Layer{B(w.tcu[2][t]), b + RY_B2_HI, b + RY_B2_LO, SBO256, 8, 128, 16, (uint32_t)(128 * t),
                                 (t == 0 ? tc::WAIT_A : 0u) | (t == 2 ? tc::SIGNAL_D : 0u)};
       for (int t = 0; t < 3; ++t)  // trans_conv3 on c3
-        layers[n++] = tc::Layer{B(w.tcu[3][t]), b + RY_B3_HI, b + RY_B3_LO, SBO128, 8, 128, (uint32_t)(128 * t),
+        layers[n++] = tc::Layer{B(w.tcu[3][t]), b + RY_B3_HI, b + RY_B3_LO, SBO128, 8, 128, 16, (uint32_t)(128 * t),
                                 (t == 0 ? tc::WAIT_A : 0u) | (t == 2 ? tc::SIGNAL_D : 0u)};
       for (int t = 0; t < 3; ++t)  // trans_conv2 on c2|x0 (K = 256)
-        layers[n++] = tc::Layer{B(w.tcu[4][t]), b + RY_B2_HI, b + RY_B2_LO, SBO256, 16, 64, (uint32_t)(64 * t),
+        layers[n++] = tc::Layer{B(w.tcu[4][t]), b + RY_B2_HI, b + RY_B2_LO, SBO256, 8, 64, 32, (uint32_t)(64 * t),
                                 (t == 0 ? tc::WAIT_A : 0u) | (t == 2 ? tc::SIGNAL_D : 0u)};
       for (int t = 0; t < 3; ++t)  // trans_conv1 on c1|x1 (K = 128)
-        layers[n++] = tc::Layer{B(w.tcu[5][t]), b + RY_B1_HI, b + RY_B1_LO, SBO128, 8, 32, (uint32_t)(32 * t),
+        layers[n++] = tc::Layer{B(w.tcu[5][t]), b + RY_B1_HI, b + RY_B1_LO, SBO128, 2, 32, 64, (uint32_t)(32 * t),
                                 (t == 0 ? tc::WAIT_A : 0u) | (t == 2 ? tc::SIGNAL_D : 0u)};
       for (int t = 0; t < 3; ++t) {  // conv_out on x (K = 128) and x2 (K = 32), same accumulator
-        layers[n++] = tc::Layer{B(w.tcu[6][t]), b + RY_X_HI, b + RY_X_LO, SBO128, 8, 128, (uint32_t)(128 * t), t == 0 ? tc::WAIT_A : 0u};
-        layers[n++] = tc::Layer{B(w.tcu_x2[t]), b + RY_X2_HI, b + RY_X2_LO, SBO32, 2, 128, (uint32_t)(128 * t),
+        layers[n++] = tc::Layer{B(w.tcu[6][t]), b + RY_X_HI, b + RY_X_LO, SBO128, 8, 128, 16, (uint32_t)(128 * t), t == 0 ? tc::WAIT_A : 0u};
+        layers[n++] = tc::Layer{B(w.tcu_x2[t]), b + RY_X2_HI, b + RY_X2_LO, SBO32, 2, 128, 16, (uint32_t)(128 * t),
                                 tc::ACCUM | (t == 2 ? tc::SIGNAL_D : 0u)};
       }
-      layers[n++] = tc::Layer{B(w.tc_ft1), b + RY_X_HI, b + RY_X_LO, SBO128, 8, 128, 384, tc::SIGNAL_AUX};  // feat_mlp layer 1
-      tc::controller<RY_NS>(sy, sm + RY_STG, tmem, layers, n);
+      layers[n++] = tc::Layer{B(w.tc_ft1), b + RY_X_HI, b + RY_X_LO, SBO128, 8, 128, 16, 384, tc::SIGNAL_AUX};  // feat_mlp layer 1
+      __syncwarp();
+      if (warp == 8) tc::mma_issuer<RY_NS>(sy, sm + RY_STG, tmem, layers, n);
+      else tc::producer<RY_NS>(sy, sm + RY_STG, layers, n);
     }
   } else {
     // ------------------------------------------------ compute warps ------------------------------------------------------
@@ -368,9 +382,10 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
         tc::tmem_ld32(c.trow + tmem + 256 + c.half * 64 + cc, y2);
         shift_combine<32>(c, y0, y1, y2, S, true, o);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          v[cc + j] = o[j] + __ldg(w.u[6].b + c.half * 64 + cc + j);
-          if (c.row < S) sum += v[cc + j];
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.u[6].b + c.half * 64 + cc + j));
+          v[cc + j] = o[j] + b4.x; v[cc + j + 1] = o[j + 1] + b4.y; v[cc + j + 2] = o[j + 2] + b4.z; v[cc + j + 3] = o[j + 3] + b4.w;
+          if (c.row < S) sum += (v[cc + j] + v[cc + j + 1]) + (v[cc + j + 2] + v[cc + j + 3]);
         }
       }
       const float n = (float)(S * 128);
@@ -381,13 +396,19 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
         for (int j = 0; j < 64; ++j) { const float d = v[j] - mean; q += d * d; }
       const float rstd = 1.f / sqrtf(block_sum(q, red) / n + 1e-5f);
       float part = 0.f;
-      if (c.row < S)
+      if (c.row < S) {
+        const float4* g4 = reinterpret_cast<const float4*>(w.u[6].g + c.row * 128 + c.half * 64);
+        const float4* b4 = reinterpret_cast<const float4*>(w.u[6].be + c.row * 128 + c.half * 64);
+        const float4* s4 = reinterpret_cast<const float4*>(w.sig_w + c.half * 64);
 #pragma unroll
-        for (int j = 0; j < 64; ++j) {
-          const int col = c.half * 64 + j;
-          const float y = elu((v[j] - mean) * rstd * __ldg(w.u[6].g + c.row * 128 + col) + __ldg(w.u[6].be + c.row * 128 + col));
-          part = fmaf(y, __ldg(w.sig_w + col), part);
+        for (int j = 0; j < 64; j += 4) {
+          const float4 g = __ldg(g4 + (j >> 2)), be = __ldg(b4 + (j >> 2)), sw = __ldg(s4 + (j >> 2));
+          part = fmaf(elu((v[j] - mean) * rstd * g.x + be.x), sw.x, part);
+          part = fmaf(elu((v[j + 1] - mean) * rstd * g.y + be.y), sw.y, part);
+          part = fmaf(elu((v[j + 2] - mean) * rstd * g.z + be.z), sw.z, part);
+          part = fmaf(elu((v[j + 3] - mean) * rstd * g.w + be.w), sw.w, part);
         }
+      }
       sSigP[c.half * 128 + c.row] = part;
     }
     cta_sync();
@@ -483,7 +504,7 @@ int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_
   if (sc.V > 16) return set_error("ray stage: at most 16 reference views");
   cudaError_t e = cudaFuncSetAttribute(ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RY_SMEM_BYTES);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-  ray_kernel<<<(unsigned)R, NT + 32, RY_SMEM_BYTES, st>>>(sc, w, z_vals, S, white_bkgd, fagg, partial, rgbvis, nvalid, rgb,
+  ray_kernel<<<(unsigned)R, NT + 64, RY_SMEM_BYTES, st>>>(sc, w, z_vals, S, white_bkgd, fagg, partial, rgbvis, nvalid, rgb,
                                                         depth, weights, mask, depth_unc, feat, sigma_dbg);
   return check_launch("ray_kernel");
 }

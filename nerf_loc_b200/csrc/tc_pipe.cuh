@@ -1,14 +1,13 @@
 // Warp-specialised tcgen05 pipeline for chains of 128-row GEMMs inside one CTA.
 //
-// A CTA has NT = 256 compute threads (warps 0-7) plus one controller warp (warp 8).  One lane of the controller
-//   * streams the pre-split weight tiles (B operand, hi|lo, K-tile of 16) from L2 into a ring of NSTAGE shared-memory
-//     stages with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier),
-//   * issues the 3xTF32 tcgen05.mma sequence for every tile (lo*hi, hi*lo, hi*hi; fp32 accumulate in TMEM),
-//   * commits stage reuse (`empty`) and layer completion (`d_ready`) through tcgen05.commit.
+// A CTA has NT = 256 compute threads (warps 0-7) plus two single-lane service warps:
+//   * warp 9, the producer, streams the pre-split weight tiles (B operand, hi|lo, 16 KB each) from L2 into a ring of
+//     shared-memory stages with 1-D bulk copies (cp.async.bulk -> UBLKCP, completion on an mbarrier);
+//   * warp 8, the MMA issuer, issues the 3xTF32 tcgen05.mma sequence of every tile (lo*hi, hi*lo, hi*hi; fp32 accumulate
+//     in TMEM) and commits stage reuse (`empty`) and layer completion (`d_ready`) through tcgen05.commit.
 // The compute warps write the A operand of a layer (canonical K-major hi / lo tiles), arrive on `a_ready`, wait on
 // `d_ready`, and run the epilogue straight out of TMEM (tcgen05.ld: warp w reads lanes 32*(w&3).., columns by w>>2).
-// Copies are issued NSTAGE-1 tiles ahead and a refill always waits on the tile BEFORE the one just issued, so the tensor
-// pipe never drains inside a layer.
+// The issuer's per-MMA work is two adds: descriptors are kept as (low, high) words and only the low word moves.
 #pragma once
 #include "tc_common.cuh"
 
@@ -18,14 +17,14 @@ namespace tc {
 constexpr int KTB = 16;        // K extent of one B stage
 constexpr int NSTAGE = 4;
 constexpr uint32_t STAGE_BYTES = 2u * 128u * KTB * 4u;   // hi + lo for N = 128: 16 KB
-constexpr uint32_t B_SBO = KTB * 32u;                   // bytes between 8-row groups of a B tile
 
 struct Layer {        // D[128 x N] (+)= A[128 x K] * B[N x K]^T
   const unsigned char* gB;   // packed weights: per K-tile [hi: N x 16 canonical][lo: N x 16 canonical]
   uint32_t a_hi, a_lo;       // shared-memory addresses of the A operand (canonical, 8-row groups a_sbo bytes apart)
   uint32_t a_sbo;
-  int nkt;                   // K / 16
+  int nkt;                   // K / ktile
   int N;                     // multiple of 16, <= 128
+  int ktile;                 // K extent of one weight tile: 2048 / N (16, 32 or 64), so that a tile is always 16 KB
   uint32_t tmem_col;         // accumulator column offset inside the CTA's TMEM allocation
   uint32_t flags;            // WAIT_A | SIGNAL_D | ACCUM
 };
@@ -102,61 +101,117 @@ __device__ __forceinline__ void wait_d(SyncT<NS>& sy, uint32_t& parity) {
   fence_after_sync();
 }
 
-// controller lane: runs `nlayers` GEMMs back to back
+// D[tmem] (+)= A * B^T for one K = 8 step; descriptors passed as (low, high) words so the issuer only adds to the low word
+__device__ __forceinline__ void mma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                           uint32_t idesc, bool accumulate) {
+  if (accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .b64 da, db;\n"
+        ".reg .pred p;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.eq.u32 p, 1, 1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .b64 da, db;\n"
+        ".reg .pred p;\n"
+        "mov.b64 da, {%1, %2};\n"
+        "mov.b64 db, {%3, %4};\n"
+        "setp.eq.u32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+  }
+}
+
+// One elected lane of a converged warp (PTX elect.sync).  The service warps run their loops warp-uniformly and predicate only
+// the tcgen05 / bulk-copy instructions with this, so descriptor words live in uniform registers - inside an `if (lane == 0)`
+// region the compiler has to wrap every UTCHMMA in an R2UR waterfall loop instead.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
+
+// producer warp (warp 9, all lanes): streams every weight tile of the GEMM list through the stage ring, as far ahead as the ring allows
 template <int NS>
-__device__ __forceinline__ void controller(SyncT<NS>& sy, unsigned char* stages, uint32_t tmem, const Layer* L, int nlayers) {
-  int total = 0;
-  for (int i = 0; i < nlayers; ++i) total += L[i].nkt;
-  int c_layer = 0, c_kt = 0, copied = 0;
-  int m_layer = 0, m_kt = 0, issued = 0;
-  uint32_t full_par = 0, empty_par = 0, a_par = 0;
-  auto copy_next = [&]() {
-    const int s = copied % NS;
-    if (copied >= NS) {
-      mbar_wait(&sy.empty[s], (empty_par >> s) & 1u);
-      empty_par ^= 1u << s;
+__device__ __forceinline__ void producer(SyncT<NS>& sy, unsigned char* stages, const Layer* L, int nlayers) {
+  uint32_t empty_par = 0;
+  int i = 0;
+  for (int l = 0; l < nlayers; ++l) {
+    const uint32_t bytes = 2u * (uint32_t)L[l].N * (uint32_t)L[l].ktile * 4u;
+    for (int kt = 0; kt < L[l].nkt; ++kt, ++i) {
+      const int s = i % NS;
+      if (i >= NS) {
+        mbar_wait(&sy.empty[s], (empty_par >> s) & 1u);
+        empty_par ^= 1u << s;
+      }
+      if (elect_one()) {
+        mbar_expect_tx(&sy.full[s], bytes);
+        bulk_copy(stages + (size_t)s * STAGE_BYTES, L[l].gB + (size_t)kt * bytes, bytes, &sy.full[s]);
+      }
+      __syncwarp();
     }
-    const uint32_t bytes = 2u * (uint32_t)L[c_layer].N * KTB * 4u;
-    mbar_expect_tx(&sy.full[s], bytes);
-    bulk_copy(stages + (size_t)s * STAGE_BYTES, L[c_layer].gB + (size_t)c_kt * bytes, bytes, &sy.full[s]);
-    ++copied;
-    if (++c_kt == L[c_layer].nkt) { c_kt = 0; ++c_layer; }
-  };
-  while (copied < total && copied < NS - 1) copy_next();
-  while (issued < total) {
-    const Layer& l = L[m_layer];
-    if (m_kt == 0 && (l.flags & WAIT_A)) {
+  }
+}
+
+// MMA warp (warp 8, all lanes; one elected lane issues): issues the 3xTF32 sequence of every tile and the completion commits
+template <int NS>
+__device__ __forceinline__ void mma_issuer(SyncT<NS>& sy, unsigned char* stages, uint32_t tmem, const Layer* L, int nlayers) {
+  uint32_t full_par = 0, a_par = 0;
+  int i = 0;
+  const uint32_t stage0 = smem_u32(stages);
+  for (int l = 0; l < nlayers; ++l) {
+    const Layer lay = L[l];
+    if (lay.flags & WAIT_A) {
       mbar_wait(&sy.a_ready, a_par);
       a_par ^= 1u;
     }
-    const int s = issued % NS;
-    mbar_wait(&sy.full[s], (full_par >> s) & 1u);
-    full_par ^= 1u << s;
-    fence_after_sync();
-    const uint32_t idesc = idesc_tf32(128, l.N);
-    const uint32_t b_hi = smem_u32(stages + (size_t)s * STAGE_BYTES);
-    const uint32_t b_lo = b_hi + (uint32_t)l.N * KTB * 4u;
-    const uint32_t d = tmem + l.tmem_col;
+    const uint32_t idesc = idesc_tf32(128, lay.N);
+    const uint32_t d = tmem + lay.tmem_col;
+    const uint32_t a_hi32 = ((lay.a_sbo >> 4) & 0x3FFFu) | (1u << 14);
+    const uint32_t b_hi32 = (((uint32_t)lay.ktile * 32u >> 4) & 0x3FFFu) | (1u << 14);
+    const uint32_t lbo = (128u >> 4) << 16;
+    const uint32_t a_lo_hi = ((lay.a_hi & 0x3FFFFu) >> 4) | lbo;   // low word of the descriptor of the A-hi tile
+    const uint32_t a_lo_lo = ((lay.a_lo & 0x3FFFFu) >> 4) | lbo;
+    const uint32_t half_tile = (uint32_t)lay.N * (uint32_t)lay.ktile * 4u;
+    const int ksteps = lay.ktile / 8;
+    bool acc = (lay.flags & ACCUM) != 0;
+    for (int kt = 0; kt < lay.nkt; ++kt, ++i) {
+      const int s = i % NS;
+      mbar_wait(&sy.full[s], (full_par >> s) & 1u);
+      full_par ^= 1u << s;
+      fence_after_sync();
+      const uint32_t b_base = stage0 + (uint32_t)s * STAGE_BYTES;
+      const uint32_t b_lo_hi = ((b_base & 0x3FFFFu) >> 4) | lbo;
+      const uint32_t b_lo_lo = (((b_base + half_tile) & 0x3FFFFu) >> 4) | lbo;
+      const uint32_t a_step = (uint32_t)(kt * (lay.ktile / 4)) * 8u;   // (k/4)*128 bytes >> 4
+      if (elect_one()) {
 #pragma unroll
-    for (int pass = 0; pass < 3; ++pass) {
-      const uint32_t a = pass == 0 ? l.a_lo : l.a_hi;   // lo*hi, hi*lo, hi*hi
-      const uint32_t b = pass == 1 ? b_lo : b_hi;
-#pragma unroll
-      for (int ks = 0; ks < KTB / 8; ++ks) {
-        const uint64_t ad = smem_desc(a + (uint32_t)(m_kt * (KTB / 4) + ks * 2) * 128u, 128u, l.a_sbo);
-        const uint64_t bd = smem_desc(b + (uint32_t)ks * 256u, 128u, B_SBO);
-        mma_tf32(d, ad, bd, idesc, ((m_kt | pass | ks) != 0 || (l.flags & ACCUM)) ? 1u : 0u);
+        for (int pass = 0; pass < 3; ++pass) {                  // lo*hi, hi*lo, hi*hi
+          const uint32_t al = (pass == 0 ? a_lo_lo : a_lo_hi) + a_step;
+          const uint32_t bl = pass == 1 ? b_lo_lo : b_lo_hi;
+          for (int ks = 0; ks < ksteps; ++ks)
+            mma_tf32_w(d, al + (uint32_t)ks * 16u, a_hi32, bl + (uint32_t)ks * 16u, b_hi32, idesc, acc || pass > 0 || ks > 0);
+        }
+        mma_commit(&sy.empty[s]);
       }
+      __syncwarp();
+      acc = true;
     }
-    mma_commit(&sy.empty[s]);
-    if (++m_kt == l.nkt) {
-      if (l.flags & SIGNAL_D) mma_commit(&sy.d_ready);
-      if (l.flags & SIGNAL_AUX) mma_commit(&sy.d_aux);
-      m_kt = 0;
-      ++m_layer;
+    if (elect_one()) {
+      if (lay.flags & SIGNAL_D) mma_commit(&sy.d_ready);
+      if (lay.flags & SIGNAL_AUX) mma_commit(&sy.d_aux);
     }
-    ++issued;
-    if (copied < total) copy_next();
+    __syncwarp();
   }
 }
 
