@@ -29,6 +29,11 @@ F_SAMPLE = 2880640 + 38912 * V          # algorithmic matmul+conv FLOP per sampl
 F_KERNEL = {"aggregate": 201e3 + 176e3 * V / 8, "neighbor": 1108e3 + 1081e3 + 264e3, "ray": 270e3 + 82e3 + 9e3, "knn": 0.0}
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes;
+# None until a capture of the current build exists
+TRAFFIC = {"aggregate": 4.06e9, "ray": 4.07e9, "knn": 0.18e9}  # profiles/r1d_ncu_metrics.json, per launch of 18,944 rays
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -257,7 +262,8 @@ def run_b200(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "640x480 query, 128 samples/ray, 8 ref views, full conditional render (configs[1])",
                    "rays_per_step": R_total, "samples_per_ray": S, "views": V, "support_points": int(model.support_neural_points["fine"]["xyz"].shape[0]),
-                   "chunk_rays": args.chunk, "mma_mode": "fp32-FFMA",
+                   "chunk_rays": args.chunk,
+                   "mma_mode": "3xTF32 tcgen05 (neighbour MLP, RayUnet, feat/blend layers) + fp32 FFMA (aggregator, small per-sample GEMMs)",
                    "l2": "working set per step (scene 294 MB + >1 GB of per-chunk intermediates) exceeds the 126 MB L2",
                    "parallelism": f"ray-shard x{world}" + (" + NCCL all-gather of feat[R,192]" if world > 1 else ""),
                    "per_frame_setup_ms": setup_ms},
@@ -267,8 +273,11 @@ def run_b200(args):
         "clocks": sampler.summary(),
         "kernels_ms_per_step": {n: kern[n]["ms"] for n in names},
         "roofline": {"bound": "tensor", "kernel": dom + "_kernel", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                     "frac": ach / tf_peak, "traffic": None, "peak_source": which + " bf16 sustained",
-                     "whole_step_achieved": F_SAMPLE * R_total * S / (ms_step * 1e-3) / 1e12},
+                     "frac": ach / tf_peak, "traffic": TRAFFIC.get(dom), "peak_source": which + " bf16 sustained",
+                     "whole_step_achieved": F_SAMPLE * R_total * S / (ms_step * 1e-3) / 1e12,
+                     "per_kernel": {n: {"achieved": (F_KERNEL[n] * samples_rank / (kern[n]["ms"] * 1e-3) / 1e12) if kern[n]["ms"] > 0 else 0.0,
+                                        "frac": (F_KERNEL[n] * samples_rank / (kern[n]["ms"] * 1e-3) / 1e12 / tf_peak) if kern[n]["ms"] > 0 else 0.0}
+                                    for n in names if F_KERNEL[n] > 0}},
     }
     if args.cpu_rays > 0 and world == 1:
         torch.set_num_threads(os.cpu_count() or 1)
