@@ -112,6 +112,79 @@ def cpu_sample(ro, rd, n):
     return ro[idx].contiguous(), rd[idx].contiguous(), idx
 
 
+def matcher_frame(N3=4096, hc=60, wc=80, seed=1234):
+    """Synthetic matching inputs of SURVEY.md section 8(d): 4096 3D descriptors vs the 60x80 coarse / 120x160 fine maps of
+    a 640x480 query, 2048 planted pairs."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    Mc = hc * wc
+    d2 = torch.randn(Mc, 192, generator=g)
+    d3 = torch.randn(N3, 192, generator=g)
+    P = min(N3 // 2, Mc)
+    cells = torch.randperm(Mc, generator=g)[:P]
+    d3[:P] = d2[cells] + 0.05 * torch.randn(P, 192, generator=g)
+    kps3d = torch.rand(N3, 3, generator=g) * 2
+    freqs = 2.0 ** torch.linspace(0.0, 31.0, steps=32)
+    pe3 = torch.cat([f(kps3d * fr) for fr in freqs for f in (torch.sin, torch.cos)], -1)
+    ys = (torch.arange(1, hc + 1, dtype=torch.float32) - 0.5) / (hc + 1e-6)
+    xs = (torch.arange(1, wc + 1, dtype=torch.float32) - 0.5) / (wc + 1e-6)
+    p = torch.stack([xs[None, :].expand(hc, wc), ys[:, None].expand(hc, wc)], -1)
+    bases = [i + 1 for i in range(48)]
+    pe2 = torch.cat([torch.sin(i * math.pi * p) for i in bases] + [torch.cos(i * math.pi * p) for i in bases], -1).reshape(Mc, -1)
+    gy, gx = torch.meshgrid(torch.arange(hc), torch.arange(wc), indexing="ij")
+    return dict(desc_3d=d3, pos_emd_3d=pe3, desc_2d_coarse=d2, pos_emd_2d=pe2, kps3d=kps3d,
+                kps2d=torch.stack([gx, gy], -1).view(-1, 2).float(),
+                feat_fine=torch.randn(1, hc * 2, wc * 2, 192, generator=g), feat_coarse=torch.randn(1, hc, wc, 192, generator=g),
+                desc_3d_fine=torch.randn(N3, 192, generator=g), stride_coarse=8, stride_fine=4)
+
+
+def bench_matcher(dev, cpu_n3):
+    """Match ms/frame (BASELINE.json metric, second half): Matcher.forward at configs[2] size on the device, and the CPU port on a
+    bounded sample (fewer 3D points, same 2D maps)."""
+    from nerf_loc_b200 import params, synthetic as syn
+    from nerf_loc_b200.config import default_args
+    from nerf_loc_b200.matcher import Matcher
+    sd = syn.synthetic_state_dict(params.matcher_shapes(), 99)
+    m = Matcher(default_args(), 192, 192, 192).eval()
+    m.load_state_dict(sd)
+    m = m.to(dev)
+    data = matcher_frame()
+    dd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+    with torch.no_grad():
+        for _ in range(2):
+            out = m(dict(dd))
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            out = m(dict(dd))
+        e1.record()
+        torch.cuda.synchronize()
+        # the S2D kernel alone
+        d3t, d2t = m.coarse_transformer(dd["desc_3d"][None], dd["pos_emd_3d"][None], dd["desc_2d_coarse"][None], dd["pos_emd_2d"][None])
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(3):
+            m.s2d(d3t[0], d2t[0], 0.2)
+        f1.record()
+        torch.cuda.synchronize()
+    res = {"ms_per_frame": e0.elapsed_time(e1) / 3, "s2d_ms": f0.elapsed_time(f1) / 3, "n3": 4096, "mc": 4800,
+           "matches": int(out["i_ids"].numel()),
+           "s2d_tflops_algorithmic": 82368.0 * 4096 * 4800 / (f0.elapsed_time(f1) / 3 * 1e-3) / 1e12}
+    if cpu_n3 > 0:
+        from oracle import matcher_oracle as MO
+        small = matcher_frame(N3=cpu_n3)
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            ref = MO.matcher_forward(sd, small)
+            dt = time.perf_counter() - t0
+            got = m({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in small.items()})
+        res["cpu_port"] = {"ms": dt * 1e3, "n3": cpu_n3, "mc": 4800, "cores": torch.get_num_threads(),
+                           "sample": f"oracle/ matcher_forward with {cpu_n3} of the 4096 3D points, full 60x80 / 120x160 maps"}
+        res["parity_on_sample"] = {"score_matrix": float((got["score_matrix"].cpu() - ref["score_matrix"]).abs().max() / ref["score_matrix"].abs().max())}
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -297,6 +370,7 @@ def run_b200(args):
         out = step_device()
         err = {k: float((out[k][idx.to(dev)].cpu() - ref[k]).abs().max() / ref[k].abs().max()) for k in ("rgb", "depth", "feat", "weights")}
         line["parity_on_sample"] = err
+        line["match"] = bench_matcher(dev, args.cpu_match_n3)
     else:
         line["cpu_baseline"] = None
     print(json.dumps(line), flush=True)
@@ -312,6 +386,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=0, help="debug: render only the first N rays of the frame")
     ap.add_argument("--chunk", type=int, default=18944, help="rays per kernel wave (148 SMs x 128)")
+    ap.add_argument("--cpu-match-n3", type=int, default=256, help="3D points in the CPU matcher sample (0 = skip)")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays in the CPU-baseline sample (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
