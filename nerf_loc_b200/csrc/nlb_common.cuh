@@ -211,7 +211,7 @@ __device__ __forceinline__ void tile_gemm_frag(const ASrc A, const int rows, con
 // accumulators), reads its weight column straight from L2 (a warp reads 128 contiguous bytes per k, no staging, no
 // barrier per K-tile) and the 256 threads split K in NT/COLS slices that are reduced through `red`
 // (>= (NT/COLS)*16*COLS floats of shared scratch).  arow(r, c) -> shared-memory pointer to row r as seen by column c.
-template <int COLS, class ARow, class Epi>
+template <int COLS, int R = 16, class ARow, class Epi>
 __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__ Wt, const int ldb, const int K, float* red,
                                             Epi epi) {
   constexpr int KSPLIT = NT / COLS;
@@ -219,16 +219,16 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
   const int c = tid % COLS, ks = tid / COLS;
   const int kper = K / KSPLIT;
   const int k0 = ks * kper;
-  float acc[16];
+  float acc[R];
 #pragma unroll
-  for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
   const float* wp = Wt + (size_t)k0 * ldb + c;
   for (int k = 0; k < kper; k += 8) {
     float b[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) b[j] = (k + j < kper) ? __ldg(wp + (size_t)(k + j) * ldb) : 0.f;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
+    for (int r = 0; r < R; ++r) {
       const float* ap = arow(r, c) + k0 + k;
       const float4 a0 = *reinterpret_cast<const float4*>(ap);
       acc[r] = fmaf(a0.x, b[0], acc[r]); acc[r] = fmaf(a0.y, b[1], acc[r]);
@@ -242,16 +242,16 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
   }
   if (KSPLIT == 1) {
 #pragma unroll
-    for (int r = 0; r < 16; ++r) epi(r, c, acc[r]);
+    for (int r = 0; r < R; ++r) epi(r, c, acc[r]);
   } else {
     cta_sync();  // `red` may alias a buffer an earlier phase still reads
 #pragma unroll
-    for (int r = 0; r < 16; ++r) red[(ks * 16 + r) * COLS + c] = acc[r];
+    for (int r = 0; r < R; ++r) red[(ks * R + r) * COLS + c] = acc[r];
     cta_sync();
-    for (int i = tid; i < 16 * COLS; i += NT) {
+    for (int i = tid; i < R * COLS; i += NT) {
       float v = 0.f;
 #pragma unroll
-      for (int q = 0; q < KSPLIT; ++q) v += red[q * 16 * COLS + i];
+      for (int q = 0; q < KSPLIT; ++q) v += red[q * R * COLS + i];
       epi(i / COLS, i % COLS, v);
     }
   }

@@ -78,29 +78,37 @@ constexpr int LDF = 228;   // rgb_feat rows: 195 + vis + ray_diff(4) + zero pad 
 constexpr int LDH = 132;
 constexpr int LDX = 36;
 constexpr int LDG = 420;   // 393 -> 416 (+4)
-constexpr int TP_MAX = 16;
+#ifndef AGG_ROWS
+#define AGG_ROWS 64
+#endif
 
-constexpr int AGG_SMEM_FLOATS = STAGE_FLOATS + 128 * LDF + TP_MAX * LDG + TP_MAX * 68 + 128 * RI_N + 128 * 8 + TP_MAX * 4;
+// ROWS = (sample, view) rows per CTA.  128 rows fill the SM with one CTA; 64 rows fit two CTAs per SM (112 KB each), which
+// doubles the resident warps for the latency-bound gather phases.
+template <int ROWS>
+constexpr int agg_smem_floats() {
+  return STAGE_FLOATS + ROWS * LDF + (ROWS / 8) * LDG + (ROWS / 8) * 68 + ROWS * RI_N + (ROWS / 8) * 4;
+}
 
-__global__ void __launch_bounds__(NT, 1)
+template <int ROWS>
+__global__ void __launch_bounds__(NT, 128 / ROWS)
 aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int with_blend,
                  float* __restrict__ agg_out, float* __restrict__ partial_out, float* __restrict__ rgbvis_out,
                  unsigned char* __restrict__ nvalid_out, float* __restrict__ mvf_out, float* __restrict__ mvv_out) {
   extern __shared__ __align__(16) float smem[];
   float* sB = smem;
   float* arena = sB + STAGE_FLOATS;
-  float* sG = arena + 128 * LDF;
+  constexpr int TP_MAX = ROWS / 8;
+  float* sG = arena + ROWS * LDF;
   float* sO1 = sG + TP_MAX * LDG;
   float* sRI = sO1 + TP_MAX * 68;
-  float* sDec = sRI + 128 * RI_N;
-  float* sPt = sDec + 128 * 8;
-  float* sX = arena;               // [128][LDX]
-  float* sH = arena + 128 * LDX;   // [128][LDH]
-  float* sF = arena;               // [128][LDF] (after the decoder is done)
+  float* sPt = sRI + ROWS * RI_N;
+  float* sX = arena;                // [ROWS][LDX]
+  float* sH = arena + ROWS * LDX;   // [ROWS][LDH]
+  float* sF = arena;                // [ROWS][LDF] (after the decoder is done)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = sc.V;
-  const int TP = min(TP_MAX, 128 / V);
+  const int TP = min(TP_MAX, ROWS / V);
   const int64_t n0 = (int64_t)blockIdx.x * TP;
   const int np = (int)min((int64_t)TP, N - n0);
   const int rows = np * V;
@@ -117,7 +125,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   cp_async_commit();
 
   // ---- phase 1: projections, one thread per (sample, view) row -----------------------------------------------
-  if (tid < 128) {
+  if (tid < ROWS) {
     float* ri = sRI + tid * RI_N;
     if (tid < rows) {
       const int p = tid / V, v = tid - p * V;
@@ -170,7 +178,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   // ---- phase 2: 32-channel visibility features (border padding), one warp per row ------------------------------
   // All four taps of two rows are requested before any is consumed (addresses clamped into the map, taps outside
   // carry weight 0), so a warp keeps 8 independent loads in flight instead of one.
-  for (int rb = warp; rb < 128; rb += 2 * (NT / 32)) {
+  for (int rb = warp; rb < ROWS; rb += 2 * (NT / 32)) {
     float q[2][4], wgt[2][4], valid[2];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
@@ -212,16 +220,17 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   cta_sync();  // decoder weights landed, sX complete
   AGG_STAMP(9);
   {
-    // layer 1 of the four heads at once: [128 x 32] -> [128 x 128], 8 x 8 register tile
-    const int tc = tid & 15, r0 = (tid >> 4) * 8;
-    float acc[8][8];
+    // layer 1 of the four heads at once: [ROWS x 32] -> [ROWS x 128], (ROWS/16) x 8 register tile
+    constexpr int TM1 = ROWS / 16;
+    const int tc = tid & 15, r0 = (tid >> 4) * TM1;
+    float acc[TM1][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < TM1; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    gemm_resident<8, 8>(sX + r0 * LDX, LDX, sB, 128, tc * 4, 64, 32, acc);
+    gemm_resident<TM1, 8>(sX + r0 * LDX, LDX, sB, 128, tc * 4, 64, 32, acc);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < TM1; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = (j >> 2) * 64 + tc * 4 + (j & 3);
@@ -231,17 +240,18 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   cta_sync();
   AGG_STAMP(10);
   {
-    // layer 2, block diagonal: head h maps columns [32h, 32h+32) to themselves; 16 x 4 register tile inside one head
-    const int cg = tid & 31, r0 = (tid >> 5) * 16, hd = cg >> 3;
-    float acc[16][4];
+    // layer 2, block diagonal: head h maps columns [32h, 32h+32) to themselves; (ROWS/8) x 4 register tile inside one head
+    constexpr int TM2 = ROWS / 8;
+    const int cg = tid & 31, r0 = (tid >> 5) * TM2, hd = cg >> 3;
+    float acc[TM2][4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < TM2; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    gemm_resident<16, 4>(sH + r0 * LDH + 32 * hd, LDH, sB + 4096, 128, cg * 4, 0, 32, acc);
+    gemm_resident<TM2, 4>(sH + r0 * LDH + 32 * hd, LDH, sB + 4096, 128, cg * 4, 0, 32, acc);
     cta_sync();  // every thread has read its inputs: write in place
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
+    for (int i = 0; i < TM2; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int c = cg * 4 + j;
@@ -310,7 +320,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
   // features: a warp handles two rows per iteration and requests all 2 x 4 taps x 3 chunks (24 independent 8-byte loads
   // per lane) before it consumes any; addresses are clamped into the map and taps outside carry weight 0.
-  for (int rb = warp; rb < 128; rb += 2 * (NT / 32)) {
+  for (int rb = warp; rb < ROWS; rb += 2 * (NT / 32)) {
     float2 q[2][4][3];
     float wt[2][4];
 #pragma unroll
@@ -355,7 +365,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
     }
   }
-  for (int r = warp; r < 128; r += NT / 32) {
+  for (int r = warp; r < ROWS; r += NT / 32) {
     float* frow = sF + r * LDF;
     if (r < rows) {
       const float* ri = sRI + r * RI_N;
@@ -430,17 +440,17 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   AGG_STAMP(6);
   // ---- phase 7: out_fc 393 -> 64 -> 128 (ELU) --------------------------------------------------------------------
   cta_sync();  // sG complete
-  rows16_gemm<64>([&](int r, int) { return sG + r * LDG; }, w.fc1, 64, 416, sB,
+  rows16_gemm<64, TP_MAX>([&](int r, int) { return sG + r * LDG; }, w.fc1, 64, 416, sB,
                   [&](int r, int c, float v) { sO1[r * 68 + c] = elu(v + __ldg(w.fc1_b + c)); });
   cta_sync();
-  rows16_gemm<128>([&](int r, int) { return sO1 + r * 68; }, w.fc2, 128, 64, sB, [&](int r, int c, float v) {
+  rows16_gemm<128, TP_MAX>([&](int r, int) { return sO1 + r * 68; }, w.fc2, 128, 64, sB, [&](int r, int c, float v) {
     if (r < np) agg_out[(n0 + r) * W_HID + c] = elu(v + __ldg(w.fc2_b + c));
   });
 
   AGG_STAMP(7);
   // ---- phase 8: per-view half of the colour-blend first layer ----------------------------------------------------
   if (with_blend) {
-    tile_gemm<4, 4, 32, false>(plainA(sF, LDF), 128, w.bl1v, 32, 224, sB, [&](int r, int c, float v) {
+    tile_gemm<ROWS / 32, 4, 32, false>(plainA(sF, LDF), ROWS, w.bl1v, 32, 224, sB, [&](int r, int c, float v) {
       if (r < rows) partial_out[(n0 * V + r) * 32 + c] = v + __ldg(w.bl1_b + c);
     });
   }
@@ -500,11 +510,12 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
                      float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, cudaStream_t st) {
   if (N <= 0) return 0;
   if (sc.V < 1 || sc.V > 16) return set_error("aggregate: number of reference views must be in 1..16");
-  const size_t smem = AGG_SMEM_FLOATS * sizeof(float);
-  if (set_smem(aggregate_kernel, smem)) return 1;
-  const int TP = TP_MAX < 128 / sc.V ? TP_MAX : 128 / sc.V;
+  constexpr int ROWS = AGG_ROWS;
+  const size_t smem = agg_smem_floats<ROWS>() * sizeof(float);
+  if (set_smem(aggregate_kernel<ROWS>, smem)) return 1;
+  const int TP = ROWS / 8 < ROWS / sc.V ? ROWS / 8 : ROWS / sc.V;
   const unsigned grid = (unsigned)((N + TP - 1) / TP);
-  aggregate_kernel<<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
+  aggregate_kernel<ROWS><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
   return check_launch("aggregate_kernel");
 }
 
