@@ -142,6 +142,17 @@ int nlb_fine_windows(const float* packed_match_weights, int C, const float* feat
 int nlb_fine_match(const float* packed_match_weights, int C, const float* f0, const float* f1, int64_t Mm,
                    const float* mkps2d_c, float* expec_f, float* mkps2d_f, void* stream);
 
+/* ---- absolute pose from the 2D-3D matches (models/nerf_pose_estimator.py:557-583) ---------------------------------------
+ * Replaces `pycolmap.absolute_pose_estimation(p2d, p3d, {PINHOLE, [fx, fy, cx, cy]}, ransac_thresh)` (line 574; COLMAP is a
+ * third-party dependency outside the reference tree - parity unpinned, validated against known poses): P3P-RANSAC with an
+ * MSAC score and Levenberg-Marquardt local optimisation on the inliers, fp64, all on the device.
+ * p2d [M,2] pixels, p3d [M,3] world points (device); camera = {fx, fy, cx, cy} (HOST); pose_w2c [12] doubles (device):
+ * R row-major then t, x_cam = R x_world + t; inliers [M] 0/1; result [2] = {success, number of inliers}. */
+size_t nlb_pnp_scratch_bytes(int iters);
+int nlb_pnp_ransac(const float* p2d, const float* p3d, int64_t M, const float* camera, float thresh_px, int iters,
+                   uint64_t seed, int lo_rounds, double* pose_w2c, uint8_t* inliers, int32_t* result, void* scratch,
+                   size_t scratch_bytes, void* stream);
+
 /* ---- self-test of the tcgen05 building blocks: C[128,128] = A[128,K] * W[128,K]^T, K multiple of 8 <= 64;
  * mode 0 = single-pass tf32, 1 = 3xTF32 (fp32-equivalent) -------------------------------------------------------------- */
 /* clock64() phase stamps of block 0 of the last neighbor_kernel launch (debug aid) */

@@ -11,6 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnerfloc_b200.so")
 
 c_void_p, c_int, c_int64, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float
+c_uint64 = ctypes.c_uint64
 
 
 class NlbScene(ctypes.Structure):
@@ -60,6 +61,9 @@ SIGNATURES = {
                                  c_void_p, c_void_p]),
     "nlb_fine_match": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
+    "nlb_pnp_scratch_bytes": (c_size_t, [c_int]),
+    "nlb_pnp_ransac": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_float, c_int, c_uint64, c_int, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_size_t, c_void_p]),
 }
 
 _lib = None

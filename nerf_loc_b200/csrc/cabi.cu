@@ -187,8 +187,9 @@ int nlb_confidence_head(const float* packed_weights, int S, const float* aggrega
 
 size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
   const size_t n = (size_t)(chunk_rays < 1 ? 1 : chunk_rays) * S;
+  const size_t slabs = S > 128 ? align256((size_t)RL_MAX_GRID * ray_long_slab_floats(S) * 4) : 0;
   return align256(n * KNN_K * 4) * 2 + align256(n * W_HID * 4) * 2 + align256(n * V * 32 * 4) + align256(n * V * 16) +
-         align256(n) + 2048;
+         align256(n) + slabs + 2048;
 }
 
 int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays) {
@@ -205,7 +206,7 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
   if (R <= 0) return 0;
   if (!packed_weights || !rays_o || !rays_d || !z_vals || !rgb || !depth || !weights || !mask || !depth_uncertainty)
     return set_error("nlb_render_rays: NULL pointer");
-  if (S % 8 != 0 || S < 8 || S > 128) return set_error("nlb_render_rays: S must be a multiple of 8 in [8, 128]");
+  if (S % 8 != 0 || S < 8 || S > 256) return set_error("nlb_render_rays: S must be a multiple of 8 in [8, 256]");
   if (chunk_rays < 1) chunk_rays = R;
   if (chunk_rays > R) chunk_rays = R;
   cudaStream_t st = (cudaStream_t)stream;
@@ -219,6 +220,7 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
   float* partial = c.take<float>(n * V * 32);
   float* rgbvis = c.take<float>(n * V * 4);
   unsigned char* nvalid = c.take<unsigned char>(n);
+  float* slabs = S > 128 ? c.take<float>((size_t)RL_MAX_GRID * ray_long_slab_floats(S)) : nullptr;
   if (!c.ok) return set_error("nlb_render_rays: scratch too small (see nlb_render_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
@@ -237,10 +239,16 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
     prof.mark();
     if (launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)) return 1;
     prof.mark();
-    if (launch_ray(sc, w, z_vals, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
-                   weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
-                   dbg_sigma ? dbg_sigma + r0 * S : nullptr, st))
+    if (S <= 128) {
+      if (launch_ray(sc, w, z_vals, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
+                     weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
+                     dbg_sigma ? dbg_sigma + r0 * S : nullptr, st))
+        return 1;
+    } else if (launch_ray_long(sc, w, z_vals, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
+                               weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
+                               dbg_sigma ? dbg_sigma + r0 * S : nullptr, slabs, st)) {
       return 1;
+    }
     prof.mark();
     prof.flush(4);
   }
@@ -255,6 +263,18 @@ void nlb_profile_enable(int on) {
 int nlb_profile_read(double* ms, int64_t* launches, int n) {
   for (int i = 0; i < n && i < 8; ++i) { ms[i] = g_prof_ms[i]; launches[i] = g_prof_n[i]; }
   return 0;
+}
+
+size_t nlb_pnp_scratch_bytes(int iters) { return pnp_scratch_bytes(iters); }
+
+int nlb_pnp_ransac(const float* p2d, const float* p3d, int64_t M, const float* camera, float thresh_px, int iters,
+                   uint64_t seed, int lo_rounds, double* pose_w2c, uint8_t* inliers, int32_t* result, void* scratch,
+                   size_t scratch_bytes, void* stream) {
+  if (!p2d || !p3d || !camera || !pose_w2c || !inliers || !result || !scratch) return set_error("nlb_pnp_ransac: NULL pointer");
+  if (scratch_bytes < pnp_scratch_bytes(iters)) return set_error("nlb_pnp_ransac: scratch too small (see nlb_pnp_scratch_bytes)");
+  if (!(thresh_px > 0.f)) return set_error("nlb_pnp_ransac: threshold must be positive");
+  return launch_pnp(p2d, p3d, M, camera, thresh_px, iters, seed, lo_rounds < 0 ? 0 : lo_rounds, pose_w2c, inliers, result,
+                    scratch, (cudaStream_t)stream);
 }
 
 size_t nlb_match_weights_floats(int C) { return match_weights_floats(C); }

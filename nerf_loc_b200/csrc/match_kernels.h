@@ -35,4 +35,9 @@ __global__ void pack_t_kernel(float* dst, const float* __restrict__ src, int Kp,
                               int src_off, int Kv);
 __global__ void pack_copy_kernel(float* dst, const float* __restrict__ src, int n);
 
+// absolute pose (pnp.cu)
+size_t pnp_scratch_bytes(int iters);
+int launch_pnp(const float* p2d, const float* p3d, int64_t M, const float* cam, float thresh, int iters, uint64_t seed,
+               int lo_rounds, double* pose_out, unsigned char* inliers, int* result, void* scratch, cudaStream_t st);
+
 }  // namespace nlb

@@ -20,6 +20,19 @@ namespace nlb {
 __device__ long long g_prof[32];
 #define NLB_STAMP(i) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) g_prof[i] = clock64(); } while (0)
 
+// sin / cos with a two-term Cody-Waite reduction to [-pi/4, pi/4] and the hardware approximations there: absolute error
+// ~4e-7 (the library sincosf costs ~45 instructions per call; the positional encoding needs 60 per row).
+__device__ __forceinline__ void fast_sincos(float x, float& s, float& c) {
+  const float k = rintf(x * 0.63661977236758134f);
+  float r = fmaf(-k, 1.5707963705062866f, x);
+  r = fmaf(-k, -4.3711388286737929e-8f, r);
+  const int q = (int)k;
+  const float sr = __sinf(r), cr = __cosf(r);
+  const float a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
+  s = (q & 2) ? -a : a;
+  c = ((q + 1) & 2) ? -b : b;
+}
+
 constexpr int NB_LDH = 132;
 constexpr int NB_TP = 16;                      // samples per CTA
 constexpr uint32_t NB_SBO1 = 96u * 32u;        // A operand of layer 1: K = 96
@@ -87,7 +100,8 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     cp_async_commit();
 
     // ---- phase 0: per (sample, neighbour) geometry -> A operand of layer 1 (PE 63 | ray_diff_fc 27 | 0 x 6) ----------
-    // two threads per row: threads 0..127 do the positional encoding, threads 128..255 the ray-difference MLP
+    // two threads per row, each with half of the work: positional-encoding octaves 0-4 / 5-9 and ray_diff_fc outputs
+    // 0-13 / 14-26
     float* sW = sQ;  // ray_diff_fc weights: rd1 [16][4] | b1 [16] | rd2 [27][16] | b2 [27]  (sQ is free until the q GEMM)
     for (int i = tid; i < 64 + 16 + 432 + 27; i += NT)
       sW[i] = i < 64 ? __ldg(w.rd1 + i) : (i < 80 ? __ldg(w.rd1_b + i - 64) : (i < 512 ? __ldg(w.rd2 + i - 80) : __ldg(w.rd2_b + i - 512)));
@@ -112,18 +126,16 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           y = __fadd_rn(ps.rays_o[r * 3 + 1], __fmul_rn(ps.rays_d[r * 3 + 1], t));
           z = __fadd_rn(ps.rays_o[r * 3 + 2], __fmul_rn(ps.rays_d[r * 3 + 2], t));
         }
-        if (half == 1) {
-          if (ps.dirs) {
-            dx = ps.dirs[n * 3]; dy = ps.dirs[n * 3 + 1]; dz = ps.dirs[n * 3 + 2];
-          } else if (ps.rays_d && !ps.xyz) {
-            const int64_t r = n / ps.S;
-            dx = ps.rays_d[r * 3]; dy = ps.rays_d[r * 3 + 1]; dz = ps.rays_d[r * 3 + 2];
-          } else {  // direction=None: the nearest neighbour's own direction (model.py:391-392)
-            const int id0 = knn_idx[n * K];
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8));
-            const float4 h1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8 + 4));
-            dx = h0.w; dy = h1.x; dz = h1.y;
-          }
+        if (ps.dirs) {
+          dx = ps.dirs[n * 3]; dy = ps.dirs[n * 3 + 1]; dz = ps.dirs[n * 3 + 2];
+        } else if (ps.rays_d && !ps.xyz) {
+          const int64_t r = n / ps.S;
+          dx = ps.rays_d[r * 3]; dy = ps.rays_d[r * 3 + 1]; dz = ps.rays_d[r * 3 + 2];
+        } else {  // direction=None: the nearest neighbour's own direction (model.py:391-392)
+          const int id0 = knn_idx[n * K];
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8));
+          const float4 h1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8 + 4));
+          dx = h0.w; dy = h1.x; dz = h1.y;
         }
       }
       cta_sync();  // sW loaded
@@ -134,6 +146,8 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         *reinterpret_cast<float*>(actHi + o) = hi;
         *reinterpret_cast<float*>(actLo + o) = lo;
       };
+      const float off[3] = {live ? __fdiv_rn(__fsub_rn(x, g0.x), range) : 0.f, live ? __fdiv_rn(__fsub_rn(y, g0.y), range) : 0.f,
+                            live ? __fdiv_rn(__fsub_rn(z, g0.z), range) : 0.f};
       if (half == 0) {
         if (live) {
           sD[rowp] = knn_d2[(n0 + p) * K + k];
@@ -142,23 +156,28 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           sD[rowp] = 1.f; sD[128 + rowp] = 0.f;
         }
         sIdx[rowp] = id;
-        const float off[3] = {live ? __fdiv_rn(__fsub_rn(x, g0.x), range) : 0.f, live ? __fdiv_rn(__fsub_rn(y, g0.y), range) : 0.f,
-                              live ? __fdiv_rn(__fsub_rn(z, g0.z), range) : 0.f};
         put(0, off[0]); put(1, off[1]); put(2, off[2]);
-        float f = 1.f;
-#pragma unroll
-        for (int i = 0; i < 10; ++i) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float sn = 0.f, co = 0.f;
-            if (live) sincosf(off[c] * f, &sn, &co);
-            put(3 + i * 6 + c, sn);
-            put(3 + i * 6 + 3 + c, co);
-          }
-          f *= 2.f;
-        }
       } else {
-        // ray difference (model.py:396-399) and ray_diff_fc (4 -> 16 -> 27, LeakyReLU)
+#pragma unroll
+        for (int c = 90; c < 96; ++c) put(c, 0.f);
+      }
+      // positional encoding (utils.py:5-53): octaves 5*half .. 5*half+4
+      float f = half ? 32.f : 1.f;
+#pragma unroll
+      for (int ii = 0; ii < 5; ++ii) {
+        const int i = half * 5 + ii;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float sn = 0.f, co = 0.f;
+          if (live) fast_sincos(off[c] * f, sn, co);
+          put(3 + i * 6 + c, sn);
+          put(3 + i * 6 + 3 + c, co);
+        }
+        f *= 2.f;
+      }
+      {
+        // ray difference (model.py:396-399) and ray_diff_fc (4 -> 16 -> 27, LeakyReLU): hidden layer on both threads,
+        // output rows split between them
         const float nx = g0.w, ny = g1.x, nz = g1.y;
         const float rx = dx - nx, ry = dy - ny, rz = dz - nz;
         const float rn = sqrtf(rx * rx + ry * ry + rz * rz) + 1e-8f;
@@ -171,15 +190,14 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           for (int c = 0; c < 4; ++c) a = fmaf(sW[o * 4 + c], rd[c], a);
           h1[o] = leaky(a);
         }
-#pragma unroll
-        for (int o = 0; o < 27; ++o) {
+        const int o0 = half ? 14 : 0, o1 = half ? 27 : 14;
+#pragma unroll 2
+        for (int o = o0; o < o1; ++o) {
           float a = sW[512 + o];
 #pragma unroll
           for (int c = 0; c < 16; ++c) a = fmaf(sW[80 + o * 16 + c], h1[c], a);
           put(63 + o, live ? leaky(a) : 0.f);
         }
-#pragma unroll
-        for (int c = 90; c < 96; ++c) put(c, 0.f);
       }
     }
     cp_async_wait<0>();  // the agg tile requested at kernel start

@@ -5,6 +5,8 @@
 #include "neighbor_tc.cu"
 #include "render_point.cu"
 #include "render_ray.cu"
+#include "render_ray_long.cu"
 #include "match.cu"
+#include "pnp.cu"
 #include "tc_test.cu"
 #include "cabi.cu"

@@ -223,20 +223,22 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
 #pragma unroll
   for (int r = 0; r < R; ++r) acc[r] = 0.f;
   const float* wp = Wt + (size_t)k0 * ldb + c;
-  for (int k = 0; k < kper; k += 8) {
-    float b[8];
+  // weight loads in flight per thread: with few rows there are registers to spare and the loop is L2-latency bound
+  constexpr int KB = R <= 8 ? 16 : 8;
+  for (int k = 0; k < kper; k += KB) {
+    float b[KB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) b[j] = (k + j < kper) ? __ldg(wp + (size_t)(k + j) * ldb) : 0.f;
+    for (int j = 0; j < KB; ++j) b[j] = (k + j < kper) ? __ldg(wp + (size_t)(k + j) * ldb) : 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float* ap = arow(r, c) + k0 + k;
-      const float4 a0 = *reinterpret_cast<const float4*>(ap);
-      acc[r] = fmaf(a0.x, b[0], acc[r]); acc[r] = fmaf(a0.y, b[1], acc[r]);
-      acc[r] = fmaf(a0.z, b[2], acc[r]); acc[r] = fmaf(a0.w, b[3], acc[r]);
-      if (k + 4 < kper) {
-        const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
-        acc[r] = fmaf(a1.x, b[4], acc[r]); acc[r] = fmaf(a1.y, b[5], acc[r]);
-        acc[r] = fmaf(a1.z, b[6], acc[r]); acc[r] = fmaf(a1.w, b[7], acc[r]);
+#pragma unroll
+      for (int g = 0; g < KB / 4; ++g) {
+        if (k + 4 * g < kper) {
+          const float4 a = *reinterpret_cast<const float4*>(ap + 4 * g);
+          acc[r] = fmaf(a.x, b[4 * g], acc[r]); acc[r] = fmaf(a.y, b[4 * g + 1], acc[r]);
+          acc[r] = fmaf(a.z, b[4 * g + 2], acc[r]); acc[r] = fmaf(a.w, b[4 * g + 3], acc[r]);
+        }
       }
     }
   }
@@ -259,12 +261,12 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
 
 // Register-tile GEMM against a weight tile that is ALREADY resident in shared memory (no staging, no barriers):
 // acc[i][j] += sum_k A[r0+i][k] * Bs[k*ldb + col(j)], columns col(j) = (j/4)*gstride + c0 + (j%4).
-template <int TM, int TN>
+template <int TM, int TN, int UNROLL = 2>
 __device__ __forceinline__ void gemm_resident(const float* __restrict__ arow, const int lda, const float* __restrict__ Bs,
                                               const int ldb, const int c0, const int gstride, const int K,
                                               float (&acc)[TM][TN]) {
   constexpr int NG = TN / 4;
-#pragma unroll 2
+#pragma unroll UNROLL
   for (int kk = 0; kk < K; kk += 4) {
     float4 a[TM];
 #pragma unroll

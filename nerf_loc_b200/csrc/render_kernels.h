@@ -26,4 +26,12 @@ int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_
                float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
                cudaStream_t st);
 
+// rays with 128 < S <= 256 samples (render_ray_long.cu): persistent CTAs, activations in per-CTA global slabs
+constexpr int RL_MAX_GRID = 296;
+size_t ray_long_slab_floats(int S);
+int launch_ray_long(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t R, int S, int white_bkgd,
+                    const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
+                    float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
+                    float* slabs, cudaStream_t st);
+
 }  // namespace nlb

@@ -228,7 +228,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     for (int i = 0; i < TM1; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    gemm_resident<TM1, 8>(sX + r0 * LDX, LDX, sB, 128, tc * 4, 64, 32, acc);
+    gemm_resident<TM1, 8, 4>(sX + r0 * LDX, LDX, sB, 128, tc * 4, 64, 32, acc);
 #pragma unroll
     for (int i = 0; i < TM1; ++i)
 #pragma unroll
@@ -248,7 +248,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     for (int i = 0; i < TM2; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    gemm_resident<TM2, 4>(sH + r0 * LDH + 32 * hd, LDH, sB + 4096, 128, cg * 4, 0, 32, acc);
+    gemm_resident<TM2, 4, 4>(sH + r0 * LDH + 32 * hd, LDH, sB + 4096, 128, cg * 4, 0, 32, acc);
     cta_sync();  // every thread has read its inputs: write in place
 #pragma unroll
     for (int i = 0; i < TM2; ++i)
@@ -260,16 +260,32 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   }
   cta_sync();
   AGG_STAMP(11);
+  // head outputs: (row, j) dot products of length 32 spread over all threads, then one thread per row for the scalar tail
+  for (int i = tid; i < rows * 6; i += NT) {
+    const int r = i / 6, j = i - r * 6;
+    const int hd = j < 2 ? 0 : (j < 4 ? 1 : (j == 4 ? 2 : 3));
+    const float* hrow = sH + r * LDH + 32 * hd;
+    const float* wj = w.dec3 + j * 32;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; k += 4) {
+      const float4 h4 = *reinterpret_cast<const float4*>(hrow + k);
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wj + k));
+      a0 = fmaf(w4.x, h4.x, a0); a1 = fmaf(w4.y, h4.y, a1); a2 = fmaf(w4.z, h4.z, a2); a3 = fmaf(w4.w, h4.w, a3);
+    }
+    sO1[i] = ((a0 + a1) + (a2 + a3)) + __ldg(w.dec3_b + j);
+  }
+  // the colour-blend per-view weights (28 KB) take over the staging ring: the decoder weights are dead, the ring is not
+  // used again before out_fc; they are consumed right after the feature gather
+  cta_sync();
+  if (with_blend) {
+    for (int i = tid; i < 224 * 8; i += NT) cp_async16(sB + i * 4, w.bl1v + i * 4);
+    cp_async_commit();
+  }
   if (tid < rows) {
-    const float* hrow = sH + tid * LDH;
     float o[6];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
-      const int hd = j < 2 ? 0 : (j < 4 ? 1 : (j == 4 ? 2 : 3));
-      float a = 0.f;
-      for (int k = 0; k < 32; ++k) a = fmaf(__ldg(w.dec3 + j * 32 + k), hrow[32 * hd + k], a);
-      o[j] = a + __ldg(w.dec3_b + j);
-    }
+    for (int j = 0; j < 6; ++j) o[j] = sO1[tid * 6 + j];
     const float m0 = softplus(o[0]), m1 = softplus(o[1]);
     const float v0 = softplus(o[2]) + 0.05f, v1 = softplus(o[3]) + 0.05f;
     const float aw = sigmoidf(o[4]), vs = sigmoidf(o[5]);
@@ -289,30 +305,25 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
 
   AGG_STAMP(3);
   // ---- phase 4: per-sample view weights --------------------------------------------------------------------------
-  if (tid < np) {
-    float sum = 0.f;
-    for (int v = 0; v < V; ++v) sum += sRI[(tid * V + v) * RI_N + RI_VIS];
-    const float den = sum + 1e-8f;
-    float ddm = 0.f, wsum = 0.f;
-    int nval = 0;
-    for (int v = 0; v < V; ++v) {
-      float* ri = sRI + (tid * V + v) * RI_N;
-      const float wv = ri[RI_VIS] / den;
-      ri[RI_W] = wv;
-      ddm += ri[RI_DD] * wv;
-      wsum += wv;
-      nval += ri[RI_MASK] != 0.f;
+  for (int p = warp; p < np; p += NT / 32) {
+    // one warp per sample, lane = view
+    const bool on = lane < V;
+    float* ri = sRI + (p * V + (on ? lane : 0)) * RI_N;
+    const float vis = on ? ri[RI_VIS] : 0.f, dd = on ? ri[RI_DD] : 0.f;
+    const float den = warp_sum(vis) + 1e-8f;
+    const float wv = vis / den;
+    if (on) ri[RI_W] = wv;
+    const float ddm = warp_sum(dd * wv);
+    const float wsum = warp_sum(wv);
+    const unsigned nval = __popc(__ballot_sync(0xffffffffu, on && ri[RI_MASK] != 0.f));
+    const float d = dd - ddm;
+    const float ddv = warp_sum(wv * (d * d));
+    float* g = sG + p * LDG;
+    if (lane == 0) {
+      g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
+      if (nvalid_out) nvalid_out[n0 + p] = (unsigned char)nval;
     }
-    float ddv = 0.f;
-    for (int v = 0; v < V; ++v) {
-      const float* ri = sRI + (tid * V + v) * RI_N;
-      const float d = ri[RI_DD] - ddm;
-      ddv += ri[RI_W] * (d * d);
-    }
-    float* g = sG + tid * LDG;
-    g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
-    for (int k = 393; k < 416; ++k) g[k] = 0.f;
-    if (nvalid_out) nvalid_out[n0 + tid] = (unsigned char)nval;
+    if (lane < 23) g[393 + lane] = 0.f;
   }
   cta_sync();  // sH (arena) is dead from here on
 
@@ -422,22 +433,52 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   }
 
   AGG_STAMP(5);
+  // ---- phase 8 (runs before the mean/variance): per-view half of the colour-blend first layer ---------------------------
+  if (with_blend) {
+    // [ROWS x 224] . [224 x 32] against the weights parked in the staging ring; no barriers inside
+    constexpr int TMB = ROWS / 32;
+    cp_async_wait<0>();
+    cta_sync();
+    const int tc = tid & 7, r0 = (tid >> 3) * TMB;
+    float acc[TMB][4];
+#pragma unroll
+    for (int i = 0; i < TMB; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    gemm_resident<TMB, 4, 4>(sF + r0 * LDF, LDF, sB, 32, tc * 4, 0, 224, acc);
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.bl1_b + tc * 4));
+#pragma unroll
+    for (int i = 0; i < TMB; ++i)
+      if (r0 + i < rows)
+        *reinterpret_cast<float4*>(partial_out + (n0 * V + r0 + i) * 32 + tc * 4) =
+            make_float4(acc[i][0] + b4.x, acc[i][1] + b4.y, acc[i][2] + b4.z, acc[i][3] + b4.w);
+  }
+  AGG_STAMP(6);
   // ---- phase 6: visibility-weighted mean / variance over views (ibrnet.py:8-12) ---------------------------------
-  for (int i = tid; i < np * C_RGBF; i += NT) {
-    const int p = i / C_RGBF, c = i - p * C_RGBF;
-    float m = 0.f;
-    for (int v = 0; v < V; ++v) m += sF[(p * V + v) * LDF + c] * sRI[(p * V + v) * RI_N + RI_W];
-    float var = 0.f;
-    for (int v = 0; v < V; ++v) {
-      const float d = sF[(p * V + v) * LDF + c] - m;
-      var += sRI[(p * V + v) * RI_N + RI_W] * (d * d);
+  for (int p = warp; p < np; p += NT / 32) {
+    // one warp per sample, lanes over channels; the view weights are read once
+    float wv[16];
+#pragma unroll
+    for (int v = 0; v < 16; ++v) wv[v] = v < V ? sRI[(p * V + v) * RI_N + RI_W] : 0.f;
+    const float* f0 = sF + (p * V) * LDF;
+#pragma unroll 1
+    for (int c = lane; c < C_RGBF; c += 32) {
+      float f[16];
+#pragma unroll
+      for (int v = 0; v < 16; ++v) f[v] = v < V ? f0[v * LDF + c] : 0.f;
+      float m = 0.f;
+#pragma unroll
+      for (int v = 0; v < 16; ++v) if (v < V) m += f[v] * wv[v];
+      float var = 0.f;
+#pragma unroll
+      for (int v = 0; v < 16; ++v) if (v < V) { const float d = f[v] - m; var += wv[v] * (d * d); }
+      sG[p * LDG + c] = m;
+      sG[p * LDG + C_RGBF + c] = var;
     }
-    sG[p * LDG + c] = m;
-    sG[p * LDG + C_RGBF + c] = var;
   }
   for (int i = tid; i < (TP_MAX - np) * LDG; i += NT) sG[np * LDG + i] = 0.f;
 
-  AGG_STAMP(6);
+  AGG_STAMP(7);
   // ---- phase 7: out_fc 393 -> 64 -> 128 (ELU) --------------------------------------------------------------------
   cta_sync();  // sG complete
   rows16_gemm<64, TP_MAX>([&](int r, int) { return sG + r * LDG; }, w.fc1, 64, 416, sB,
@@ -447,13 +488,6 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     if (r < np) agg_out[(n0 + r) * W_HID + c] = elu(v + __ldg(w.fc2_b + c));
   });
 
-  AGG_STAMP(7);
-  // ---- phase 8: per-view half of the colour-blend first layer ----------------------------------------------------
-  if (with_blend) {
-    tile_gemm<ROWS / 32, 4, 32, false>(plainA(sF, LDF), ROWS, w.bl1v, 32, 224, sB, [&](int r, int c, float v) {
-      if (r < rows) partial_out[(n0 * V + r) * 32 + c] = v + __ldg(w.bl1_b + c);
-    });
-  }
   AGG_STAMP(8);
 }
 

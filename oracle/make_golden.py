@@ -23,6 +23,7 @@ RENDER_CASES = {
     # name: (S, H, W, V, n_rays, weight seed, scene seed)
     "render_s16": (16, 64, 96, 3, 24, 1234, 1234),
     "render_s64": (64, 64, 96, 4, 12, 4321, 77),
+    "render_s192": (192, 64, 96, 3, 6, 555, 99),   # long rays (BASELINE configs[3]: 192 samples per ray)
 }
 
 
@@ -108,6 +109,9 @@ def matcher_case():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
+    only = sys.argv[1:]
     for n in RENDER_CASES:
-        render_case(n)
-    matcher_case()
+        if not only or n in only:
+            render_case(n)
+    if not only or "matcher_small" in only:
+        matcher_case()

@@ -12,6 +12,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 RENDER_CASES = {
     "render_s16": (16, 64, 96, 3, 24, 1234, 1234),
     "render_s64": (64, 64, 96, 4, 12, 4321, 77),
+    "render_s192": (192, 64, 96, 3, 6, 555, 99),   # long rays (BASELINE configs[3]: 192 samples per ray)
 }
 
 

@@ -148,3 +148,27 @@ def test_render_image_shapes_and_white_background():
     img2 = model.render_image(data)
     wsum = img["weights"].sum(-1, keepdim=True)
     assert relerr(img2["rgb"].cpu(), (img["rgb"] + (1 - wsum)).cpu()) < 1e-5
+
+
+def test_render_256_samples_vs_oracle():
+    """Long rays (128 < S <= 256) take the slab kernel of render_ray_long.cu; S = 256 is the top of BASELINE's sweep."""
+    from nerf_loc_b200 import params, synthetic as syn
+    S, H, W, V, R, wseed, sseed = 256, 64, 96, 3, 5, 31, 13
+    sc = syn.make_scene(H, W, V, seed=sseed)
+    ro, rd = syn.pixel_rays(sc["K"], sc["pose"], syn.random_pixels(H, W, R))
+    model, sd = cuda_model(S, wseed)
+    data = setup_frame(model, sc)
+    rays = {"rays_o": ro.cuda(), "rays_d": rd.cuda(), "depth_range": data["depth_range"][0]}
+    out = model.render_rays(data, rays, _debug=True)
+    sup = oracle_support(sd, sc)
+    scene = dict(Ks=sc["topk_Ks"], c2ws=sc["topk_poses"], images=sc["topk_images"], vis_maps=sc["vis_featmaps"],
+                 depth_range=sc["depth_range"][0])
+    with torch.no_grad():
+        ref = O.render_rays(sd, scene, sup["fine"], sc["feat_fine_src"].permute(0, 3, 1, 2), ro, rd, sc["pose"], S,
+                            return_debug=True)
+    report = {k: relerr(out[k].cpu(), ref[k]) for k in ("feature_agg", "sigma", "rgb", "depth", "weights",
+                                                         "depth_uncertainty", "feat")}
+    print(report)
+    for k, v in report.items():
+        assert v < TOL, (k, report)
+    assert torch.equal(out["mask"].cpu(), ref["mask"])

@@ -25,7 +25,7 @@ for i in range(12):
     print(f"{names[i]:32s} {v[i+1]-v[i]:8d} clk")
 print("total", v[12] - v[0])
 
-an = ["proj", "vis gather", "decoder GEMMs+heads", "view weights", "rgb/feat gather", "mean/var", "out_fc", "blend partial"]
+an = ["proj", "vis gather", "decoder GEMMs+heads", "view weights", "rgb/feat gather", "blend partial", "mean/var", "out_fc"]
 for i in range(8):
     print(f"agg {an[i]:28s} {v[17+i]-v[16+i]:8d} clk")
 print("agg total", v[24] - v[16])
