@@ -89,3 +89,34 @@ def test_matcher_mirror_loads_reference_state_dict_and_transformer_matches():
     assert relerr(m0, r0) < 2e-5 and relerr(m1, r1) < 2e-5 and relerr(o0, r0) < 2e-5 and relerr(o1, r1) < 2e-5
     pe = PositionEmbeddingSine(96, normalize=True)(torch.zeros(2, 7, 7))
     assert torch.equal(pe, R.PositionEmbeddingSine(96, normalize=True, sine_type="lin_sine")(torch.zeros(2, 7, 7)))
+
+
+@pytest.mark.skipif(not rh.available(), reason="/root/reference not present")
+def test_top_level_front_end_matches_reference_modules():
+    """Backbone2D / appearance layers of nerf_loc_b200.nerf_pose_estimator against COTR/backbone2d.py and
+    appearance_embedding.py: same parameter names, same outputs under the same weights."""
+    import importlib
+    import types
+    rh.load()
+    from nerf_loc_b200 import nerf_pose_estimator as NPE
+    bb = importlib.import_module("nerf_loc.models.COTR.backbone2d")
+    torch.manual_seed(0)
+    ref = bb.Backbone(['conv1', 'layer1', 'layer2'], train_backbone=True, use_fpn=True, fpn_dim=192).eval()
+    mine = NPE.Backbone2D(fpn_dim=192).eval()
+    assert set(mine.state_dict()) == set(ref.state_dict())
+    mine.load_state_dict(ref.state_dict())
+    x = torch.rand(2, 3, 64, 96)
+    with torch.no_grad():
+        a, b = ref(x), mine(x)
+    for k in ('conv1', 'layer1', 'layer2'):
+        assert a[k].shape == b[k].shape and torch.allclose(a[k], b[k], atol=1e-5), k
+    assert mine.layer_to_channels['layer1'] == 192 and mine.layer_to_stride['layer2'] == 8
+    ap = importlib.import_module("nerf_loc.models.appearance_embedding")
+    args = types.SimpleNamespace(appearance_emb_dim=128)
+    r_ad, m_ad = ap.AppearanceAdaptLayer(args, 192), NPE.AppearanceAdaptLayer(args, 192)
+    m_ad.load_state_dict(r_ad.state_dict())
+    feats = {'conv1': torch.randn(3, 64, 8, 12)}
+    e_r, e_m = ap.AppearanceEmbedding(args)(None, feats), NPE.AppearanceEmbedding(args)(None, feats)
+    assert torch.allclose(e_r, e_m, atol=1e-6)
+    xf = torch.randn(3, 4, 5, 192)
+    assert torch.allclose(r_ad(xf, e_r, e_r[:1]), m_ad(xf, e_m, e_m[:1]), atol=1e-6)
