@@ -91,16 +91,28 @@ int nlb_descriptor_head(const float* packed_weights, int S, int level, const flo
 int nlb_confidence_head(const float* packed_weights, int S, const float* aggregated, int64_t N, float* conf,
                         float* scratch, void* stream);
 
-/* ---- ConditionalNeRF.render_rays (conditional_nerf/model.py:472-600), N_importance == 0 --------------------------
- * rays_o, rays_d [R,3] (unit directions, as conditional_nerf/utils.py:56-70 produces them), z_vals [S] (sample_depths,
- * model.py:451-458).  Outputs: rgb [R,3], depth [R], weights [R,S], mask [R] (uint8 0/1), depth_uncertainty [R],
+/* ---- ConditionalNeRF.render_rays (conditional_nerf/model.py:472-600) ---------------------------------------------------
+ * rays_o, rays_d [R,3] (unit directions, as conditional_nerf/utils.py:56-70 produces them); z_vals [S] with z_stride = 0
+ * (sample_depths, model.py:451-458, shared by all rays) or [R,S] with z_stride = S (per-ray depths from
+ * nlb_hierarchical_depths when N_importance > 0).  S in [8, 256], multiple of 8.  Outputs: rgb [R,3], depth [R], weights [R,S], mask [R] (uint8 0/1), depth_uncertainty [R],
  * feat [R,192] (NULL to skip render_feature).  Optional debug outputs (NULL to skip): feature_agg [R*S,128],
  * sigma [R*S].  Rays are processed in chunks of `chunk_rays`; scratch: nlb_render_scratch_bytes(chunk_rays, S, V). */
 size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V);
 int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
-                    const float* rays_d, const float* z_vals, int64_t R, int white_bkgd, int64_t chunk_rays,
+                    const float* rays_d, const float* z_vals, int64_t z_stride, int64_t R, int white_bkgd,
+                    int64_t chunk_rays,
                     float* rgb, float* depth, float* weights, uint8_t* mask, float* depth_uncertainty, float* feat,
                     float* dbg_feature_agg, float* dbg_sigma, void* scratch, size_t scratch_bytes, void* stream);
+/* ---- hierarchical sampling, render.N_importance > 0 (model.py:486-496; multiview_aggregator.py:95-154; utils.py:73-112) ---
+ * center [3] (HOST) and dirs [R,3] (device): the query camera centre and the UN-normalised NeuRay ray directions
+ * (depth_fusion.py:9-30) of the pixels; z_coarse [64] and z_regular [n_samples] from sample_depths; u [R,n_importance] the
+ * uniform draws (torch.rand in the reference, utils.py:97).  Outputs: z_out [R, n_samples + n_importance] sorted per ray
+ * (feed to nlb_render_rays with z_stride = S_total), depth_coarse [R], inds [R,n_importance] (the searchsorted indices,
+ * NULL to skip).  The packed weights are the ones of S_total = n_samples + n_importance (model.py:81). */
+int nlb_hierarchical_depths(const nlb_scene* scene, const float* packed_weights, int S_total, const float* center,
+                            const float* dirs, int64_t R, const float* z_coarse, int n_samples, const float* z_regular,
+                            const float* u, int n_importance, float* z_out, float* depth_coarse, int64_t* inds, void* stream);
+
 /* number of kernels nlb_render_rays launches for R rays (bench.py's gpu_launches claim) */
 int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays);
 

@@ -43,10 +43,12 @@ SIGNATURES = {
     "nlb_descriptor_head": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "nlb_confidence_head": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "nlb_render_scratch_bytes": (c_size_t, [c_int64, c_int, c_int]),
-    "nlb_render_rays": (c_int, [ctypes.POINTER(NlbScene), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64,
+    "nlb_render_rays": (c_int, [ctypes.POINTER(NlbScene), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                 c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "nlb_render_launch_count": (c_int64, [c_int64, c_int64]),
+    "nlb_hierarchical_depths": (c_int, [ctypes.POINTER(NlbScene), c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                                        c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nlb_debug_read_prof": (c_int, [c_void_p, c_int]),
     "nlb_debug_tc_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "nlb_profile_enable": (None, [c_int]),

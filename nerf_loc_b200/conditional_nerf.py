@@ -400,16 +400,45 @@ class ConditionalNeRF(nn.Module):
         return 1 / (1 / near * (1 - z_steps) + 1 / far * z_steps)
 
     @torch.no_grad()
-    def render_rays(self, data, rays, _debug=False):
+    def hierarchical_depths(self, data, rays, u=None):
+        """model.py:486-496 on the device: (z_vals [R, N_samples + N_importance] sorted, depth_coarse [R], searchsorted
+        indices [R, N_importance]).  `u` [R, N_importance] overrides the uniform draws (torch.rand in the reference)."""
         L = _lib.load()
-        if self.args.render.N_importance > 0:
-            raise NotImplementedError("render.N_importance > 0 (hierarchical sampling) is not implemented yet")
         near, far = rays['depth_range']
-        S = self.args.render.N_samples
+        S0, NI = self.args.render.N_samples, self.args.render.N_importance
+        sc, maps, sup = self._level_scene(data, 'fine', query_pose=data['pose'])
+        px = _lib.f32(rays['pixel_coordinates'])
+        dev, R = px.device, px.shape[0]
+        # coords2rays of the query camera (depth_fusion.py:9-30): un-normalised directions K^-1 [u, v, 1] in the world frame
+        w2c = rays['pose'].float().to(dev).inverse()[:3]
+        rot = w2c[:, :3].t()
+        trans = -rot @ w2c[:, 3:]
+        cam = torch.inverse(rays['K'].float().to(dev)) @ torch.cat([px, torch.ones(R, 1, device=dev)], 1).t()
+        dirs = ((rot @ cam + trans).t() - trans.t()).contiguous()
+        center = (ctypes.c_float * 3)(*[float(v) for v in trans[:, 0].cpu()])
+        zc, zr = _lib.f32(self.sample_depths(64, near, far)), _lib.f32(self.sample_depths(S0, near, far))
+        u = torch.rand(R, NI, device=dev) if u is None else _lib.f32(u, dev)
+        z = torch.empty(R, S0 + NI, device=dev)
+        depth_coarse = torch.empty(R, device=dev)
+        inds = torch.empty(R, NI, dtype=torch.int64, device=dev)
+        _lib.check(L.nlb_hierarchical_depths(ctypes.byref(sc), _lib.ptr(self.packed_weights()), S0 + NI, center, _lib.ptr(dirs), R,
+                                             _lib.ptr(zc), S0, _lib.ptr(zr), _lib.ptr(u), NI, _lib.ptr(z), _lib.ptr(depth_coarse),
+                                             _lib.ptr(inds), _lib.stream()))
+        return z, depth_coarse, inds
+
+    @torch.no_grad()
+    def render_rays(self, data, rays, _debug=False, _u=None):
+        L = _lib.load()
+        near, far = rays['depth_range']
+        S = self.n_samples
         sc, maps, sup = self._level_scene(data, 'fine', query_pose=data['pose'])
         ro, rd = _lib.f32(rays['rays_o']), _lib.f32(rays['rays_d'])
         dev, R = ro.device, ro.shape[0]
-        z = _lib.f32(self.sample_depths(S, near, far))
+        depth_coarse = None
+        if self.args.render.N_importance > 0:
+            z, depth_coarse, _ = self.hierarchical_depths(data, rays, _u)
+        else:
+            z = _lib.f32(self.sample_depths(S, near, far))
         out = {'rgb': torch.empty(R, 3, device=dev), 'depth': torch.empty(R, device=dev),
                'weights': torch.empty(R, S, device=dev), 'mask': torch.empty(R, dtype=torch.uint8, device=dev),
                'depth_uncertainty': torch.empty(R, device=dev)}
@@ -423,13 +452,15 @@ class ConditionalNeRF(nn.Module):
             self._frame[key] = torch.empty(nb, dtype=torch.uint8, device=dev)
         white = 1 if data.get('white_bkgd', self.args.render.white_bkgd) else 0
         _lib.check(L.nlb_render_rays(ctypes.byref(sc), _lib.ptr(self.packed_weights()), S, _lib.ptr(ro), _lib.ptr(rd),
-                                     _lib.ptr(z), R, white, chunk, _lib.ptr(out['rgb']), _lib.ptr(out['depth']),
+                                     _lib.ptr(z), S if z.dim() == 2 else 0, R, white, chunk, _lib.ptr(out['rgb']), _lib.ptr(out['depth']),
                                      _lib.ptr(out['weights']), _lib.ptr(out['mask']), _lib.ptr(out['depth_uncertainty']),
                                      _lib.ptr(feat), _lib.ptr(dbg_fa), _lib.ptr(dbg_sig), _lib.ptr(self._frame[key]), nb,
                                      _lib.stream()))
         out['mask'] = out['mask'].bool()
         if feat is not None:
             out['feat'] = feat
+        if depth_coarse is not None:
+            out['depth_coarse'] = depth_coarse
         if _debug:
             out['feature_agg'], out['sigma'] = dbg_fa, dbg_sig.view(R, S)
         return out

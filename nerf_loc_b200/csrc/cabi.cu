@@ -151,7 +151,7 @@ int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S,
   if (!c.ok) return set_error("nlb_query_points: scratch too small (see nlb_query_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
-  PointSrc ps{xyz, direction, nullptr, nullptr, nullptr, 1};
+  PointSrc ps{xyz, direction, nullptr, nullptr, nullptr, 1, 0};
   if (knn_query(sc.knn, xyz, N, K, nullptr, idx, d2, st)) return 1;
   if (launch_aggregate(sc, w, ps, N, 0, agg, nullptr, nullptr, nullptr, mv_feature, mv_visibility, st)) return 1;
   return launch_neighbor(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, st);
@@ -164,7 +164,7 @@ int nlb_aggregate_points(const nlb_scene* scene, const float* packed_weights, in
   if (!packed_weights || !xyz || !aggregated) return set_error("nlb_aggregate_points: NULL pointer");
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
-  PointSrc ps{xyz, nullptr, nullptr, nullptr, nullptr, 1};
+  PointSrc ps{xyz, nullptr, nullptr, nullptr, nullptr, 1, 0};
   return launch_aggregate(sc, w, ps, N, 0, aggregated, nullptr, nullptr, nullptr, mv_feature, mv_visibility,
                           (cudaStream_t)stream);
 }
@@ -199,7 +199,7 @@ int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays) {
 }
 
 int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
-                    const float* rays_d, const float* z_vals, int64_t R, int white_bkgd, int64_t chunk_rays,
+                    const float* rays_d, const float* z_vals, int64_t z_stride, int64_t R, int white_bkgd, int64_t chunk_rays,
                     float* rgb, float* depth, float* weights, uint8_t* mask, float* depth_uncertainty, float* feat,
                     float* dbg_feature_agg, float* dbg_sigma, void* scratch, size_t scratch_bytes, void* stream) {
   if (check_scene(scene)) return 1;
@@ -207,6 +207,7 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
   if (!packed_weights || !rays_o || !rays_d || !z_vals || !rgb || !depth || !weights || !mask || !depth_uncertainty)
     return set_error("nlb_render_rays: NULL pointer");
   if (S % 8 != 0 || S < 8 || S > 256) return set_error("nlb_render_rays: S must be a multiple of 8 in [8, 256]");
+  if (z_stride != 0 && z_stride != S) return set_error("nlb_render_rays: z_stride must be 0 (shared depths) or S (per-ray depths)");
   if (chunk_rays < 1) chunk_rays = R;
   if (chunk_rays > R) chunk_rays = R;
   cudaStream_t st = (cudaStream_t)stream;
@@ -230,21 +231,22 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
     const int64_t nc = rc * S;
     const float* ro = rays_o + r0 * 3;
     const float* rd = rays_d + r0 * 3;
-    PointSrc ps{nullptr, nullptr, ro, rd, z_vals, S};
+    const float* zc = z_vals + r0 * z_stride;
+    PointSrc ps{nullptr, nullptr, ro, rd, zc, S, z_stride};
     float* fa = dbg_feature_agg ? dbg_feature_agg + r0 * S * W_HID : fagg;
     prof.mark();
-    if (knn_query_rays(sc.knn, ro, rd, z_vals, sc.sup_geo, rc, S, idx, d2, st)) return 1;
+    if (knn_query_rays(sc.knn, ro, rd, zc, z_stride, sc.sup_geo, rc, S, idx, d2, st)) return 1;
     prof.mark();
     if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, st)) return 1;
     prof.mark();
     if (launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)) return 1;
     prof.mark();
     if (S <= 128) {
-      if (launch_ray(sc, w, z_vals, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
+      if (launch_ray(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                      weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
                      dbg_sigma ? dbg_sigma + r0 * S : nullptr, st))
         return 1;
-    } else if (launch_ray_long(sc, w, z_vals, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
+    } else if (launch_ray_long(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                                weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
                                dbg_sigma ? dbg_sigma + r0 * S : nullptr, slabs, st)) {
       return 1;
@@ -253,6 +255,19 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
     prof.flush(4);
   }
   return 0;
+}
+
+int nlb_hierarchical_depths(const nlb_scene* scene, const float* packed_weights, int S_total, const float* center,
+                            const float* dirs, int64_t R, const float* z_coarse, int n_samples, const float* z_regular,
+                            const float* u, int n_importance, float* z_out, float* depth_coarse, int64_t* inds, void* stream) {
+  if (check_scene(scene)) return 1;
+  if (!packed_weights || !center || !dirs || !z_coarse || !z_regular || !u || !z_out || !depth_coarse)
+    return set_error("nlb_hierarchical_depths: NULL pointer");
+  if (n_samples + n_importance != S_total) return set_error("nlb_hierarchical_depths: S_total must be n_samples + n_importance");
+  const SceneDev sc = to_dev(scene);
+  const RenderW w = render_weights_view(packed_weights, S_total);
+  return launch_hier_sample(sc, w, center, dirs, R, z_coarse, z_regular, n_samples, u, n_importance, z_out, depth_coarse, inds,
+                            (cudaStream_t)stream);
 }
 
 void nlb_profile_enable(int on) {

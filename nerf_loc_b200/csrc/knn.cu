@@ -361,7 +361,7 @@ template <int K>
 __global__ void __launch_bounds__(128) knn_query_rays_kernel(const void* __restrict__ index, const float* __restrict__ rays_o,
                                                              const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                                                              const float* __restrict__ sup_geo, int64_t R, int S, int SEG,
-                                                             int* idx32, float* dist2) {
+                                                             int64_t zs, int* idx32, float* dist2) {
   __shared__ KnnTree tree;
   if (threadIdx.x == 0) tree = load_tree(index);
   __syncthreads();
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(128) knn_query_rays_kernel(const void* __restr
   TopK<K> best;
   bool have_prev = false;
   for (int s = s0; s < min(S, s0 + SEG); ++s) {
-    const float z = z_vals[s];
+    const float z = z_vals[r * zs + s];
     const float qx = __fadd_rn(ox, __fmul_rn(dx, z));
     const float qy = __fadd_rn(oy, __fmul_rn(dy, z));
     const float qz = __fadd_rn(oz, __fmul_rn(dz, z));
@@ -417,14 +417,14 @@ int knn_query(const void* index, const float* p1, int64_t N, int K, int64_t* idx
   return check_launch("knn_query");
 }
 
-int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, const float* sup_geo,
-                   int64_t R, int S, int* idx32, float* dist2, cudaStream_t st) {
+int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, int64_t zs,
+                   const float* sup_geo, int64_t R, int S, int* idx32, float* dist2, cudaStream_t st) {
   if (R * S <= 0) return 0;
   const int T = 128;
   const int SEG = S >= 64 ? 16 : 8;
   const int64_t threads = R * ((S + SEG - 1) / SEG);
   knn_query_rays_kernel<8><<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(index, rays_o, rays_d, z_vals, sup_geo, R, S, SEG,
-                                                                           idx32, dist2);
+                                                                           zs, idx32, dist2);
   return check_launch("knn_query_rays");
 }
 

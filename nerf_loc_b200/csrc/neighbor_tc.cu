@@ -121,7 +121,7 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           x = ps.xyz[n * 3]; y = ps.xyz[n * 3 + 1]; z = ps.xyz[n * 3 + 2];
         } else {
           const int64_t r = n / ps.S;
-          const float t = ps.z[n - r * ps.S];
+          const float t = ps.z[r * ps.zs + (n - r * ps.S)];
           x = __fadd_rn(ps.rays_o[r * 3 + 0], __fmul_rn(ps.rays_d[r * 3 + 0], t));
           y = __fadd_rn(ps.rays_o[r * 3 + 1], __fmul_rn(ps.rays_d[r * 3 + 1], t));
           z = __fadd_rn(ps.rays_o[r * 3 + 2], __fmul_rn(ps.rays_d[r * 3 + 2], t));

@@ -6,6 +6,7 @@
 #include "render_point.cu"
 #include "render_ray.cu"
 #include "render_ray_long.cu"
+#include "hier_sample.cu"
 #include "match.cu"
 #include "pnp.cu"
 #include "tc_test.cu"

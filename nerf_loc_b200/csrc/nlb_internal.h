@@ -15,8 +15,8 @@ size_t knn_index_bytes(int64_t M);
 int knn_build(const float* xyz, int64_t M, void* buf, size_t bytes, cudaStream_t st);
 int knn_query(const void* index, const float* p1, int64_t N, int K, int64_t* idx64, int* idx32, float* dist2,
               cudaStream_t st);
-int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, const float* sup_geo,
-                   int64_t R, int S, int* idx32, float* dist2, cudaStream_t st);
+int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, int64_t zs,
+                   const float* sup_geo, int64_t R, int S, int* idx32, float* dist2, cudaStream_t st);
 
 // ---- packed weights of the render path (pack.cu) ------------------------------------------------------------
 // All matrices are stored transposed ("Wt": row = input feature k, column = output feature n), zero padded so

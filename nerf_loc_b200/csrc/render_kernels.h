@@ -10,8 +10,9 @@ struct PointSrc {
   const float* dirs;    // [N][3] viewing direction per point, or null
   const float* rays_o;  // [R][3]
   const float* rays_d;  // [R][3]
-  const float* z;       // [S]
+  const float* z;       // [S] shared by all rays (zs == 0) or [R][S] per ray (zs == S, hierarchical sampling)
   int S;
+  int64_t zs;
 };
 
 int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int with_blend, float* agg,
@@ -21,15 +22,19 @@ int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, in
 int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,
                   float* out, int ldo, cudaStream_t st);
 int launch_sup_geo(const float* xyz, const float* dir, const float* conf, int64_t M, float* out, cudaStream_t st);
-int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t R, int S, int white_bkgd,
+int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
                const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
                cudaStream_t st);
 
+// hierarchical sampling (hier_sample.cu)
+int launch_hier_sample(const SceneDev& sc, const RenderW& w, const float* center_host, const float* dirs, int64_t R,
+                       const float* z_coarse, const float* z_reg, int S, const float* u, int NI, float* z_out,
+                       float* depth_coarse, int64_t* inds, cudaStream_t st);
 // rays with 128 < S <= 256 samples (render_ray_long.cu): persistent CTAs, activations in per-CTA global slabs
 constexpr int RL_MAX_GRID = 296;
 size_t ray_long_slab_floats(int S);
-int launch_ray_long(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t R, int S, int white_bkgd,
+int launch_ray_long(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
                     const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                     float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
                     float* slabs, cudaStream_t st);

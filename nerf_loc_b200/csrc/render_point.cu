@@ -34,7 +34,7 @@ __device__ __forceinline__ void load_point(const PointSrc& ps, int64_t n, float&
   } else {
     // xyz = rays_o + rays_d * z, one rounding per op (model.py:498)
     const int64_t r = n / ps.S;
-    const float t = ps.z[n - r * ps.S];
+    const float t = ps.z[r * ps.zs + (n - r * ps.S)];
     x = __fadd_rn(ps.rays_o[r * 3 + 0], __fmul_rn(ps.rays_d[r * 3 + 0], t));
     y = __fadd_rn(ps.rays_o[r * 3 + 1], __fmul_rn(ps.rays_d[r * 3 + 1], t));
     z = __fadd_rn(ps.rays_o[r * 3 + 2], __fmul_rn(ps.rays_d[r * 3 + 2], t));

@@ -208,7 +208,7 @@ __device__ __forceinline__ void load_x(unsigned char* sm, const float* __restric
 }
 
 __global__ void __launch_bounds__(NT + 64, 1)
-ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals, const int S, const int white_bkgd,
+ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals, const int64_t zs, const int S, const int white_bkgd,
            const float* __restrict__ fagg, const float* __restrict__ partial, const float* __restrict__ rgbvis,
            const unsigned char* __restrict__ nvalid, float* __restrict__ rgb_out, float* __restrict__ depth_out,
            float* __restrict__ weights_out, unsigned char* __restrict__ mask_out, float* __restrict__ unc_out,
@@ -279,7 +279,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
 
     RAY_STAMP(0);
     load_x(sm, fagg, s0, S, tid);
-    if (tid < S) sZ[tid] = z_vals[tid];
+    if (tid < S) sZ[tid] = z_vals[ray * zs + tid];
     tc::a_ready(sy);                                                       // a#0: x
 
     // ---- colour blend (model.py:528-538) while conv1 runs on the tensor cores -----------------------------------------
@@ -494,7 +494,7 @@ int read_prof_ray(long long* out, int n) {
   return cudaMemcpyFromSymbol(out, g_prof_ray, sizeof(long long) * (n < 32 ? n : 32)) == cudaSuccess ? 0 : set_error("read_prof_ray failed");
 }
 
-int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t R, int S, int white_bkgd,
+int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
                const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
                cudaStream_t st) {
@@ -504,7 +504,7 @@ int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_
   if (sc.V > 16) return set_error("ray stage: at most 16 reference views");
   cudaError_t e = cudaFuncSetAttribute(ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RY_SMEM_BYTES);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-  ray_kernel<<<(unsigned)R, NT + 64, RY_SMEM_BYTES, st>>>(sc, w, z_vals, S, white_bkgd, fagg, partial, rgbvis, nvalid, rgb,
+  ray_kernel<<<(unsigned)R, NT + 64, RY_SMEM_BYTES, st>>>(sc, w, z_vals, zs, S, white_bkgd, fagg, partial, rgbvis, nvalid, rgb,
                                                         depth, weights, mask, depth_unc, feat, sigma_dbg);
   return check_launch("ray_kernel");
 }

@@ -91,7 +91,7 @@ __device__ __forceinline__ void dec_long(const float* in, int ldi, int rows, con
 }
 
 __global__ void __launch_bounds__(NT, 2)
-ray_long_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals, const int S, const int white_bkgd,
+ray_long_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals, const int64_t zs, const int S, const int white_bkgd,
                 const int64_t R, const float* __restrict__ fagg, const float* __restrict__ partial,
                 const float* __restrict__ rgbvis, const unsigned char* __restrict__ nvalid, float* __restrict__ rgb_out,
                 float* __restrict__ depth_out, float* __restrict__ weights_out, unsigned char* __restrict__ mask_out,
@@ -132,7 +132,7 @@ ray_long_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_
       const int s = i >> 5, c4 = i & 31;
       *reinterpret_cast<float4*>(X + s * RL_LDX + c4 * 4) = __ldg(reinterpret_cast<const float4*>(fagg + (s0 + s) * W_HID + c4 * 4));
     }
-    for (int i = tid; i < S; i += NT) sZ[i] = z_vals[i];
+    for (int i = tid; i < S; i += NT) sZ[i] = z_vals[ray * zs + i];
 
     // ---- colour blend (model.py:528-538) ----------------------------------------------------------------------------------
     tile_gemm<4, 4, 32, false>(plainA(X, RL_LDX), S, w.bl1a, 32, 128, sB, [&](int r, int c, float v) { sBl[r * 36 + c] = v; });
@@ -262,7 +262,7 @@ ray_long_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_
   }
 }
 
-int launch_ray_long(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t R, int S, int white_bkgd,
+int launch_ray_long(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
                     const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                     float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
                     float* slabs, cudaStream_t st) {
@@ -274,7 +274,7 @@ int launch_ray_long(const SceneDev& sc, const RenderW& w, const float* z_vals, i
   const size_t smem = (size_t)(STAGE_FLOATS + RL_MAX_S * (36 + 16 + 4 + 4) + 64) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(ray_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-  ray_long_kernel<<<(unsigned)ray_long_grid(R), NT, smem, st>>>(sc, w, z_vals, S, white_bkgd, R, fagg, partial, rgbvis, nvalid,
+  ray_long_kernel<<<(unsigned)ray_long_grid(R), NT, smem, st>>>(sc, w, z_vals, zs, S, white_bkgd, R, fagg, partial, rgbvis, nvalid,
                                                                 rgb, depth, weights, mask, depth_unc, feat, sigma_dbg, slabs,
                                                                 ray_long_slab_floats(S));
   return check_launch("ray_long_kernel");

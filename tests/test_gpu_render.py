@@ -172,3 +172,39 @@ def test_render_256_samples_vs_oracle():
     for k, v in report.items():
         assert v < TOL, (k, report)
     assert torch.equal(out["mask"].cpu(), ref["mask"])
+
+
+def test_hierarchical_sampling_vs_oracle():
+    """render.N_importance > 0 (model.py:486-496): nlb_hierarchical_depths + per-ray depths through nlb_render_rays.  The
+    uniform draws are shared with the oracle; the searchsorted indices must agree exactly."""
+    from nerf_loc_b200 import params, synthetic as syn
+    from nerf_loc_b200.config import default_args
+    from nerf_loc_b200.conditional_nerf import ConditionalNeRF
+    S0, NI, H, W, V, R = 16, 16, 32, 64, 3, 12
+    sd = syn.synthetic_state_dict(params.conditional_nerf_shapes(S0 + NI), 5)
+    model = ConditionalNeRF(default_args(S0, NI)).eval()
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda()
+    sc = syn.make_scene(H, W, V, seed=8)
+    data = setup_frame(model, sc)
+    px = syn.random_pixels(H, W, R)
+    ro, rd = syn.pixel_rays(sc["K"], sc["pose"], px)
+    rays = {"rays_o": ro.cuda(), "rays_d": rd.cuda(), "depth_range": data["depth_range"][0], "pixel_coordinates": px.float().cuda(),
+            "K": data["K"], "pose": data["pose"], "H": H, "W": W}
+    u = torch.rand(R, NI, generator=torch.Generator().manual_seed(3))
+    z, dc, inds = model.hierarchical_depths(data, rays, u)
+    scene = dict(Ks=sc["topk_Ks"], c2ws=sc["topk_poses"], images=sc["topk_images"], vis_maps=sc["vis_featmaps"],
+                 depth_range=sc["depth_range"][0])
+    with torch.no_grad():
+        z_ref, dc_ref, inds_ref = O.hierarchical_depths(sd, scene, px.float(), sc["K"], sc["pose"], S0, NI, u=u)
+        sup = oracle_support(sd, sc)
+        ref = O.render_rays(sd, scene, sup["fine"], sc["feat_fine_src"].permute(0, 3, 1, 2), ro, rd, sc["pose"], S0, z_vals=z_ref)
+    assert torch.equal(inds.cpu(), inds_ref)
+    assert relerr(z.cpu(), z_ref) < 1e-5 and relerr(dc.cpu(), dc_ref) < TOL
+    out = model.render_rays(data, rays, _u=u)
+    assert tuple(out["weights"].shape) == (R, S0 + NI) and relerr(out["depth_coarse"].cpu(), dc_ref) < TOL
+    report = {k: relerr(out[k].cpu(), ref[k]) for k in ("rgb", "depth", "weights", "depth_uncertainty", "feat")}
+    print(report)
+    for k, v in report.items():
+        assert v < TOL, (k, report)
+    assert torch.equal(out["mask"].cpu(), ref["mask"])
