@@ -57,7 +57,16 @@ typedef struct nlb_scene {
   const float* sup_geo;      /* [M,8]   from nlb_support_prepare */
   const void* knn_index;     /* from nlb_knn_build over the support xyz */
   float query_center[3];     /* camera centre of the query pose (render only) */
+  const float* featmaps_blend; /* [V,h,w,32] from nlb_blend_prepare (render only; may be NULL for query / aggregate) */
 } nlb_scene;
+
+/* Per-frame pre-projection of the reference feature maps through the map-feature columns of the colour-blend MLP's first
+ * layer (rgb_blending_mlp.0, conditional_nerf/model.py:90-96,532-535).  That layer is linear and so is the bilinear fetch of
+ * the 192 map channels (ibrnet/ibrnet.py:194-231), so W f(x) = sum_t b_t (W f_t): a rendered sample gathers 32 projected
+ * channels per view instead of multiplying its 195 fetched channels by a [195 x 32] matrix.
+ * featmaps [n_pixels,192] (n_pixels = V*h*w) -> featmaps_blend [n_pixels,32]. */
+int nlb_blend_prepare(const float* packed_weights, int S, const float* featmaps, int64_t n_pixels, float* featmaps_blend,
+                      void* stream);
 
 /* Per-frame precompute over the support points (conditional_nerf/model.py:372-375,404-405):
  * sup_pre = base_mlp.0.weight[:, :195] * feature + bias, sup_geo = (xyz, direction[:3], confidence). */

@@ -19,7 +19,7 @@ class NlbScene(ctypes.Structure):
                 ("w", ctypes.c_int32), ("vh", ctypes.c_int32), ("vw", ctypes.c_int32), ("near_plane", c_float), ("far_plane", c_float),
                 ("images", c_void_p), ("featmaps", c_void_p), ("vis_maps", c_void_p), ("cams", c_void_p),
                 ("M", c_int64), ("sup_pre", c_void_p), ("sup_geo", c_void_p), ("knn_index", c_void_p),
-                ("query_center", c_float * 3)]
+                ("query_center", c_float * 3), ("featmaps_blend", c_void_p)]
 
 
 # name -> (restype, argtypes); mirrors include/nerfloc_b200.h one to one
@@ -34,6 +34,7 @@ SIGNATURES = {
     "nlb_render_pack_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "nlb_support_prepare": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
                                     c_void_p, c_void_p]),
+    "nlb_blend_prepare": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "nlb_query_scratch_bytes": (c_size_t, [c_int64, c_int]),
     "nlb_query_points": (c_int, [ctypes.POINTER(NlbScene), c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

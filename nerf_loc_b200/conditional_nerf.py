@@ -117,6 +117,7 @@ class _Maps:
         cams[:, 24:27] = c2ws[:, :3, 3]
         self.cams = cams.contiguous()
         self.near, self.far = float(depth_range[0]), float(depth_range[1])
+        self.featb = None  # [V*h*w, 32], filled by ConditionalNeRF._level_scene when a frame is rendered
 
     def fill(self, sc):
         sc.V, sc.H, sc.W, sc.h, sc.w = self.V, self.H, self.W, self.h, self.w
@@ -244,6 +245,12 @@ class ConditionalNeRF(nn.Module):
         maps.fill(sc)
         self._frame[key].fill(sc)
         if query_pose is not None:
+            # rendering: the colour-blend layer-1 projection of the feature maps, once per frame and level
+            if maps.featb is None:
+                maps.featb = torch.empty(maps.V * maps.h * maps.w, 32, device=maps.feat.device)
+                _lib.check(_lib.load().nlb_blend_prepare(_lib.ptr(self.packed_weights()), self.n_samples, _lib.ptr(maps.feat),
+                                                         maps.V * maps.h * maps.w, _lib.ptr(maps.featb), _lib.stream()))
+            sc.featmaps_blend = maps.featb.data_ptr()
             c = query_pose[:3, 3].detach().float().cpu()
             sc.query_center[0], sc.query_center[1], sc.query_center[2] = float(c[0]), float(c[1]), float(c[2])
         return sc, maps, self._frame[key]

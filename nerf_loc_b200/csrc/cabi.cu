@@ -30,6 +30,7 @@ static SceneDev to_dev(const nlb_scene* s) {
   d.near_ = s->near_plane; d.far_ = s->far_plane;
   d.M = s->M; d.sup_pre = s->sup_pre; d.sup_geo = s->sup_geo; d.knn = s->knn_index;
   d.qc[0] = s->query_center[0]; d.qc[1] = s->query_center[1]; d.qc[2] = s->query_center[2];
+  d.featb = s->featmaps_blend;
   return d;
 }
 
@@ -130,6 +131,13 @@ int nlb_support_prepare(const float* packed_weights, int S, const float* xyz, co
   return launch_sup_geo(xyz, direction, confidence, M, sup_geo, (cudaStream_t)stream);
 }
 
+int nlb_blend_prepare(const float* packed_weights, int S, const float* featmaps, int64_t n_pixels, float* featmaps_blend,
+                      void* stream) {
+  if (!packed_weights || !featmaps || !featmaps_blend) return set_error("nlb_blend_prepare: NULL pointer");
+  const RenderW w = render_weights_view(packed_weights, S);
+  return launch_blend_project(featmaps, n_pixels, w.bl1v, featmaps_blend, (cudaStream_t)stream);
+}
+
 size_t nlb_query_scratch_bytes(int64_t N, int K) {
   if (N < 1) N = 1;
   return align256((size_t)N * K * 4) + align256((size_t)N * K * 4) + align256((size_t)N * W_HID * 4) + 1024;
@@ -206,6 +214,7 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
   if (R <= 0) return 0;
   if (!packed_weights || !rays_o || !rays_d || !z_vals || !rgb || !depth || !weights || !mask || !depth_uncertainty)
     return set_error("nlb_render_rays: NULL pointer");
+  if (!scene->featmaps_blend) return set_error("nlb_render_rays: scene.featmaps_blend is NULL (call nlb_blend_prepare once per frame)");
   if (S % 8 != 0 || S < 8 || S > 256) return set_error("nlb_render_rays: S must be a multiple of 8 in [8, 256]");
   if (z_stride != 0 && z_stride != S) return set_error("nlb_render_rays: z_stride must be 0 (shared depths) or S (per-ray depths)");
   if (chunk_rays < 1) chunk_rays = R;

@@ -99,7 +99,7 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     }
     cp_async_commit();
 
-    // ---- phase 0: per (sample, neighbour) geometry -> A operand of layer 1 (PE 63 | ray_diff_fc 27 | 0 x 6) ----------
+    // ---- phase 0: per (sample, neighbour) geometry -> A operand of layer 1 (PE 63 | ray_diff_fc 27 | 0 x 6, permuted) --
     // two threads per row, each with half of the work: positional-encoding octaves 0-4 / 5-9 and ray_diff_fc outputs
     // 0-13 / 14-26
     float* sW = sQ;  // ray_diff_fc weights: rd1 [16][4] | b1 [16] | rd2 [27][16] | b2 [27]  (sQ is free until the q GEMM)
@@ -139,13 +139,9 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         }
       }
       cta_sync();  // sW loaded
-      auto put = [&](int c, float v) {
-        float hi, lo;
-        tc::split_tf32(v, hi, lo);
-        const uint32_t o = tc::a_off(rowp, c, NB_SBO1);
-        *reinterpret_cast<float*>(actHi + o) = hi;
-        *reinterpret_cast<float*>(actLo + o) = lo;
-      };
+      // this thread's 48 consecutive columns of the layer-1 operand (K order: see pack.cu::tcb_src_index), stored as 12
+      // conflict-free float4s (8 consecutive rows of a core-matrix column are one 128-byte run)
+      float vals[48];
       const float off[3] = {live ? __fdiv_rn(__fsub_rn(x, g0.x), range) : 0.f, live ? __fdiv_rn(__fsub_rn(y, g0.y), range) : 0.f,
                             live ? __fdiv_rn(__fsub_rn(z, g0.z), range) : 0.f};
       if (half == 0) {
@@ -156,22 +152,21 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           sD[rowp] = 1.f; sD[128 + rowp] = 0.f;
         }
         sIdx[rowp] = id;
-        put(0, off[0]); put(1, off[1]); put(2, off[2]);
+        vals[0] = off[0]; vals[1] = off[1]; vals[2] = off[2]; vals[3] = 0.f;
       } else {
 #pragma unroll
-        for (int c = 90; c < 96; ++c) put(c, 0.f);
+        for (int c = 43; c < 48; ++c) vals[c] = 0.f;
       }
       // positional encoding (utils.py:5-53): octaves 5*half .. 5*half+4
       float f = half ? 32.f : 1.f;
 #pragma unroll
       for (int ii = 0; ii < 5; ++ii) {
-        const int i = half * 5 + ii;
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           float sn = 0.f, co = 0.f;
           if (live) fast_sincos(off[c] * f, sn, co);
-          put(3 + i * 6 + c, sn);
-          put(3 + i * 6 + 3 + c, co);
+          if (half == 0) { vals[4 + ii * 6 + c] = sn; vals[4 + ii * 6 + 3 + c] = co; }
+          else { vals[ii * 6 + c] = sn; vals[ii * 6 + 3 + c] = co; }
         }
         f *= 2.f;
       }
@@ -190,15 +185,22 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           for (int c = 0; c < 4; ++c) a = fmaf(sW[o * 4 + c], rd[c], a);
           h1[o] = leaky(a);
         }
-        const int o0 = half ? 14 : 0, o1 = half ? 27 : 14;
-#pragma unroll 2
-        for (int o = o0; o < o1; ++o) {
-          float a = sW[512 + o];
 #pragma unroll
-          for (int c = 0; c < 16; ++c) a = fmaf(sW[80 + o * 16 + c], h1[c], a);
-          put(63 + o, live ? leaky(a) : 0.f);
+        for (int oo = 0; oo < 14; ++oo) {
+          const int o = half ? 14 + oo : oo;   // half 1 has 13 outputs (14..26)
+          if (o < 27) {
+            float a = sW[512 + o];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) a = fmaf(sW[80 + o * 16 + c], h1[c], a);
+            const float v = live ? leaky(a) : 0.f;
+            if (half == 0) vals[34 + oo] = v; else vals[30 + oo] = v;
+          }
         }
       }
+#pragma unroll
+      for (int c4 = 0; c4 < 12; ++c4)
+        tc::store_split4(actHi, actLo, rowp, half * 48 + c4 * 4, NB_SBO1, vals[c4 * 4], vals[c4 * 4 + 1], vals[c4 * 4 + 2],
+                         vals[c4 * 4 + 3]);
     }
     cp_async_wait<0>();  // the agg tile requested at kernel start
     tc::a_ready(sy);
@@ -264,9 +266,9 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const int hd = hp * 2 + hh;
-        float acc[16];
+        float acc[16][2];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+        for (int r = 0; r < 16; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
         const float* wp = w.wk + (size_t)(32 * hd) * 128 + c;
 #pragma unroll
         for (int k = 0; k < 32; k += 8) {
@@ -278,14 +280,14 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
             const float* ap = sQ + r * NB_LDH + 32 * hd + k;
             const float4 a0 = *reinterpret_cast<const float4*>(ap);
             const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
-            acc[r] = fmaf(a0.x, b[0], acc[r]); acc[r] = fmaf(a0.y, b[1], acc[r]);
-            acc[r] = fmaf(a0.z, b[2], acc[r]); acc[r] = fmaf(a0.w, b[3], acc[r]);
-            acc[r] = fmaf(a1.x, b[4], acc[r]); acc[r] = fmaf(a1.y, b[5], acc[r]);
-            acc[r] = fmaf(a1.z, b[6], acc[r]); acc[r] = fmaf(a1.w, b[7], acc[r]);
+            fma2_v(acc[r][0], acc[r][1], a0.x, a0.y, b[0], b[1]);
+            fma2_v(acc[r][0], acc[r][1], a0.z, a0.w, b[2], b[3]);
+            fma2_v(acc[r][0], acc[r][1], a1.x, a1.y, b[4], b[5]);
+            fma2_v(acc[r][0], acc[r][1], a1.z, a1.w, b[6], b[7]);
           }
         }
 #pragma unroll
-        for (int r = 0; r < 16; ++r) sQT[(r * 4 + hd) * NB_LDH + c] = acc[r];
+        for (int r = 0; r < 16; ++r) sQT[(r * 4 + hd) * NB_LDH + c] = acc[r][0] + acc[r][1];
       }
     }
     cta_sync();
@@ -296,14 +298,15 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
       const int p = i >> 5, hd = (i >> 3) & 3, k = i & 7;
       const float* qv = sQT + (p * 4 + hd) * NB_LDH;
       const float* kv = sA + (p * 8 + k) * NB_LDH;
-      float a = 0.f;
+      float a = 0.f, a1 = 0.f;
 #pragma unroll 8
       for (int c = 0; c < 128; c += 4) {
         const float4 q4 = *reinterpret_cast<const float4*>(qv + c);
         const float4 k4 = *reinterpret_cast<const float4*>(kv + c);
-        a = fmaf(q4.x, k4.x, a); a = fmaf(q4.y, k4.y, a); a = fmaf(q4.z, k4.z, a); a = fmaf(q4.w, k4.w, a);
+        fma2_v(a, a1, q4.x, q4.y, k4.x, k4.y);
+        fma2_v(a, a1, q4.z, q4.w, k4.z, k4.w);
       }
-      a *= 0.17677669529663687f;  // 1/sqrt(d_k = 32)
+      a = (a + a1) * 0.17677669529663687f;  // 1/sqrt(d_k = 32)
       if (k >= K) a = -FLT_MAX;
       float m = a;
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
@@ -332,8 +335,8 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 v4 = *reinterpret_cast<const float4*>(kv + 16 * j);
-          acc[j].x = fmaf(a, v4.x, acc[j].x); acc[j].y = fmaf(a, v4.y, acc[j].y);
-          acc[j].z = fmaf(a, v4.z, acc[j].z); acc[j].w = fmaf(a, v4.w, acc[j].w);
+          fma2_s(acc[j].x, acc[j].y, a, v4.x, v4.y);
+          fma2_s(acc[j].z, acc[j].w, a, v4.z, v4.w);
         }
       }
 #pragma unroll

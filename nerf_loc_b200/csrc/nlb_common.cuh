@@ -32,6 +32,18 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// Packed fp32 FMA (FFMA2, sm_100+): two independent IEEE fused multiply-adds in one issue slot, bit-identical to two fmaf.
+// The FFMA GEMMs here are issue-bound (ncu: issue active 55 %, FMA pipe 31 % in aggregate_kernel), so halving the FMA
+// instruction count is what matters.  A scalar operand is broadcast by the instruction itself (SASS `Rn.F32`).
+__device__ __forceinline__ void fma2_s(float& c0, float& c1, const float a, const float b0, const float b1) {  // c += a * (b0, b1)
+  asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %2};\nmov.b64 rb, {%3, %4};\nmov.b64 rc, {%0, %1};\n"
+      "fma.rn.f32x2 rc, ra, rb, rc;\nmov.b64 {%0, %1}, rc;\n}" : "+f"(c0), "+f"(c1) : "f"(a), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void fma2_v(float& c0, float& c1, const float a0, const float a1, const float b0, const float b1) {  // c += (a0, a1) * (b0, b1)
+  asm("{\n.reg .b64 ra, rb, rc;\nmov.b64 ra, {%2, %3};\nmov.b64 rb, {%4, %5};\nmov.b64 rc, {%0, %1};\n"
+      "fma.rn.f32x2 rc, ra, rb, rc;\nmov.b64 {%0, %1}, rc;\n}" : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
 // ELU(alpha=1).  exp(x) - 1 with the hardware exponential: absolute error ~1e-7 for x < 0 (the library expm1f costs ~40
 // instructions per element and was 15 % of aggregate_kernel's samples); far inside the 1e-4 parity bar.
@@ -146,7 +158,7 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
           for (int i = 0; i < TM; ++i) {
             const float av = k4 == 0 ? a[i].x : (k4 == 1 ? a[i].y : (k4 == 2 ? a[i].z : a[i].w));
 #pragma unroll
-            for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av, b[j], acc[i][j]);
+            for (int j = 0; j < TN; j += 2) fma2_s(acc[i][j], acc[i][j + 1], av, b[j], b[j + 1]);
           }
         }
       }
@@ -219,16 +231,21 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
   const int c = tid % COLS, ks = tid / COLS;
   const int kper = K / KSPLIT;
   const int k0 = ks * kper;
-  float acc[R];
+  // even-k / odd-k partial sums per row: one FFMA2 covers two consecutive k (the a pair comes out of the float4 fragment, the
+  // b pair out of two adjacent weight loads); the halves are added once at the end
+  float acc[R][2];
 #pragma unroll
-  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  for (int r = 0; r < R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
   const float* wp = Wt + (size_t)k0 * ldb + c;
-  // weight loads in flight per thread: with few rows there are registers to spare and the loop is L2-latency bound
+  // weight loads in flight per thread: the batch for step k+KB is requested before the FMAs of step k (the loop is
+  // L2-latency bound otherwise); with few rows there are registers to spare for a deeper batch
   constexpr int KB = R <= 8 ? 16 : 8;
-  for (int k = 0; k < kper; k += KB) {
-    float b[KB];
+  float b[KB], bn[KB];
 #pragma unroll
-    for (int j = 0; j < KB; ++j) b[j] = (k + j < kper) ? __ldg(wp + (size_t)(k + j) * ldb) : 0.f;
+  for (int j = 0; j < KB; ++j) b[j] = (j < kper) ? __ldg(wp + (size_t)j * ldb) : 0.f;
+  for (int k = 0; k < kper; k += KB) {
+#pragma unroll
+    for (int j = 0; j < KB; ++j) bn[j] = (k + KB + j < kper) ? __ldg(wp + (size_t)(k + KB + j) * ldb) : 0.f;
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float* ap = arow(r, c) + k0 + k;
@@ -236,19 +253,21 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
       for (int g = 0; g < KB / 4; ++g) {
         if (k + 4 * g < kper) {
           const float4 a = *reinterpret_cast<const float4*>(ap + 4 * g);
-          acc[r] = fmaf(a.x, b[4 * g], acc[r]); acc[r] = fmaf(a.y, b[4 * g + 1], acc[r]);
-          acc[r] = fmaf(a.z, b[4 * g + 2], acc[r]); acc[r] = fmaf(a.w, b[4 * g + 3], acc[r]);
+          fma2_v(acc[r][0], acc[r][1], a.x, a.y, b[4 * g], b[4 * g + 1]);
+          fma2_v(acc[r][0], acc[r][1], a.z, a.w, b[4 * g + 2], b[4 * g + 3]);
         }
       }
     }
+#pragma unroll
+    for (int j = 0; j < KB; ++j) b[j] = bn[j];
   }
   if (KSPLIT == 1) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) epi(r, c, acc[r]);
+    for (int r = 0; r < R; ++r) epi(r, c, acc[r][0] + acc[r][1]);
   } else {
     cta_sync();  // `red` may alias a buffer an earlier phase still reads
 #pragma unroll
-    for (int r = 0; r < R; ++r) red[(ks * R + r) * COLS + c] = acc[r];
+    for (int r = 0; r < R; ++r) red[(ks * R + r) * COLS + c] = acc[r][0] + acc[r][1];
     cta_sync();
     for (int i = tid; i < R * COLS; i += NT) {
       float v = 0.f;
@@ -283,7 +302,7 @@ __device__ __forceinline__ void gemm_resident(const float* __restrict__ arow, co
       for (int i = 0; i < TM; ++i) {
         const float av = k4 == 0 ? a[i].x : (k4 == 1 ? a[i].y : (k4 == 2 ? a[i].z : a[i].w));
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av, b[j], acc[i][j]);
+        for (int j = 0; j < TN; j += 2) fma2_s(acc[i][j], acc[i][j + 1], av, b[j], b[j + 1]);
       }
     }
   }

@@ -89,6 +89,7 @@ struct SceneDev {
   const float* sup_geo;  // [M][8]: xyz, dir, conf, pad
   const void* knn;       // KNN index
   float qc[3];           // query camera centre (colour-blend ray_diff); unused by query()
+  const float* featb;    // [V][h][w][32] feature maps pre-projected through rgb_blending_mlp.0 (render only; null for query)
 };
 
 }  // namespace nlb

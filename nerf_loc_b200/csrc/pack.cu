@@ -119,12 +119,26 @@ __global__ void pack_conv_kernel(float* dst, const float* __restrict__ src, int 
 
 // tensor-core B operand: W [N][K] -> per K-tile of `ktile` = 2048 / N columns (a 16 KB tile): hi tile then lo tile, each the
 // canonical no-swizzle K-major layout (8-row core matrices of 16 bytes, 8-row groups ktile*32 bytes apart); 3xTF32 split.
+// perm == 1: K order of the neighbour MLP's per-pair layer-1 operand as neighbor_kernel writes it (two threads per row, each
+// storing 48 consecutive columns as float4s): [offset xyz, 0 | PE octaves 0-4 | ray_diff_fc 0-13] [PE octaves 5-9 |
+// ray_diff_fc 14-26 | 0 x 5]; the source order is [offset xyz | PE octaves 0-9 | ray_diff_fc 0-26].
+__device__ __forceinline__ int tcb_src_index(int k, int perm) {
+  if (perm == 0) return k;
+  if (k < 3) return k;
+  if (k == 3) return -1;
+  if (k < 34) return k - 1;
+  if (k < 48) return k + 29;
+  if (k < 78) return k - 15;
+  if (k < 91) return k - 1;
+  return -1;
+}
 __global__ void pack_tcb_kernel(float* dst, const float* __restrict__ src, int N, int Kp, int src_ld, int src_off, int Kv,
-                                int src_ks, int ktile) {
+                                int src_ks, int ktile, int perm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * Kp) return;
   const int n = i / Kp, k = i % Kp;
-  const float x = k < Kv ? src[(size_t)n * src_ld + src_off + (size_t)k * src_ks] : 0.f;
+  const int ks = tcb_src_index(k, perm);
+  const float x = (ks >= 0 && ks < Kv) ? src[(size_t)n * src_ld + src_off + (size_t)ks * src_ks] : 0.f;
   const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   const float lo = x - hi;
   const int kt = k / ktile, kl = k % ktile;
@@ -147,10 +161,10 @@ struct Packer {
     pack_copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst) + dst_off, p[src], n);
   }
   // B[n][k] = src[n*src_ld + src_off + k*src_ks]
-  void tcb(const float* dst, int src, int N, int Kp, int src_ld, int src_off, int Kv, int src_ks = 1) {
+  void tcb(const float* dst, int src, int N, int Kp, int src_ld, int src_off, int Kv, int src_ks = 1, int perm = 0) {
     const int n = N * Kp;
     pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv, src_ks,
-                                                     2048 / N);
+                                                     2048 / N, perm);
   }
   void conv(const float* dst, int src, int Cin, int Cout, int ntaps, int t0, int t1, int t2, bool tr) {
     const int n = ntaps * Cin * Cout;
@@ -202,7 +216,7 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
   k.t(w.wv, AT_V, 128, 128, 128, 0, 128);
   k.t(w.wfc, AT_FC, 128, 128, 128, 0, 128);
   k.c(w.ln_g, AT_LNG, 128);  k.c(w.ln_b, AT_LNB, 128);
-  k.tcb(w.tc_w1b, BM0_W, 128, 96, 285, 195, 90);
+  k.tcb(w.tc_w1b, BM0_W, 128, 96, 285, 195, 90, 1, 1);
   k.tcb(w.tc_w2, BM2_W, 128, 128, 128, 0, 128);
   k.tcb(w.tc_w3, BM4_W, 128, 128, 128, 0, 128);
   // --- RayUnet ---

@@ -19,6 +19,7 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
                      float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, cudaStream_t st);
 int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
                     const float* d2, const float* agg, float* fagg, float* feature, float* weights, cudaStream_t st);
+int launch_blend_project(const float* feat, int64_t P, const float* bl1v, float* out, cudaStream_t st);
 int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,
                   float* out, int ldo, cudaStream_t st);
 int launch_sup_geo(const float* xyz, const float* dir, const float* conf, int64_t M, float* out, cudaStream_t st);

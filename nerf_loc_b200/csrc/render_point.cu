@@ -72,9 +72,10 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int w, int h, bool
 }
 
 // row info slots
-enum { RI_FX = 0, RI_FY, RI_IX, RI_IY, RI_VX, RI_VY, RI_DEPTH, RI_VALID, RI_MASK, RI_VIS, RI_DD, RI_W, RI_N };
+enum { RI_FX = 0, RI_FY, RI_IX, RI_IY, RI_VX, RI_VY, RI_DEPTH, RI_VALID, RI_MASK, RI_VIS, RI_DD, RI_W,
+       RI_RD0, RI_RD1, RI_RD2, RI_RD3, RI_N };
 
-constexpr int LDF = 228;   // rgb_feat rows: 195 + vis + ray_diff(4) + zero pad to 224 (+4)
+constexpr int LDF = 196;   // rgb_feat rows: 195 (+1)
 constexpr int LDH = 132;
 constexpr int LDX = 36;
 constexpr int LDG = 420;   // 393 -> 416 (+4)
@@ -82,11 +83,34 @@ constexpr int LDG = 420;   // 393 -> 416 (+4)
 #define AGG_ROWS 64
 #endif
 
-// ROWS = (sample, view) rows per CTA.  128 rows fill the SM with one CTA; 64 rows fit two CTAs per SM (112 KB each), which
+// ROWS = (sample, view) rows per CTA.  128 rows fill the SM with one CTA; 64 rows fit two CTAs per SM (about 110 KB each), which
 // doubles the resident warps for the latency-bound gather phases.
 template <int ROWS>
 constexpr int agg_smem_floats() {
   return STAGE_FLOATS + ROWS * LDF + (ROWS / 8) * LDG + (ROWS / 8) * 68 + ROWS * RI_N + (ROWS / 8) * 4;
+}
+
+// visibility-weighted mean / variance over the views of one sample (ibrnet.py:8-12): one warp, lanes over channels
+template <int VM>
+__device__ __forceinline__ void mean_var_rows(const float* __restrict__ f0, const float* __restrict__ ri0, const int V,
+                                              const int lane, float* __restrict__ g) {
+  float wv[VM];
+#pragma unroll
+  for (int v = 0; v < VM; ++v) wv[v] = v < V ? ri0[v * RI_N + RI_W] : 0.f;
+#pragma unroll 2
+  for (int c = lane; c < C_RGBF; c += 32) {
+    float f[VM];
+#pragma unroll
+    for (int v = 0; v < VM; ++v) f[v] = v < V ? f0[v * LDF + c] : 0.f;
+    float m = 0.f;
+#pragma unroll
+    for (int v = 0; v < VM; ++v) m += f[v] * wv[v];
+    float var = 0.f;
+#pragma unroll
+    for (int v = 0; v < VM; ++v) { const float d = f[v] - m; var += wv[v] * (d * d); }
+    g[c] = m;
+    g[C_RGBF + c] = var;
+  }
 }
 
 template <int ROWS>
@@ -98,6 +122,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   float* sB = smem;
   float* arena = sB + STAGE_FLOATS;
   constexpr int TP_MAX = ROWS / 8;
+  constexpr int PARTS = NT / ROWS;  // threads per row in the per-row scalar phases
   float* sG = arena + ROWS * LDF;
   float* sO1 = sG + TP_MAX * LDG;
   float* sRI = sO1 + TP_MAX * 68;
@@ -124,64 +149,82 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   }
   cp_async_commit();
 
-  // ---- phase 1: projections, one thread per (sample, view) row -----------------------------------------------
-  if (tid < ROWS) {
-    float* ri = sRI + tid * RI_N;
-    if (tid < rows) {
-      const int p = tid / V, v = tid - p * V;
+  // ---- phase 1: projections; PARTS threads per (sample, view) row share the three independent pieces -------------
+  {
+    const int r = tid % ROWS, part = tid / ROWS;
+    float* ri = sRI + r * RI_N;
+    if (r < rows) {
+      const int p = r / V, v = r - p * V;
       float x, y, z;
       load_point(ps, n0 + p, x, y, z);
-      if (v == 0) { sPt[p * 4] = x; sPt[p * 4 + 1] = y; sPt[p * 4 + 2] = z; }
       const float* cam = sc.cams + v * 32;
-      // IBRNet convention
-      const float ph0 = fmaf(cam[2], z, fmaf(cam[1], y, cam[0] * x)) + cam[3];
-      const float ph1 = fmaf(cam[6], z, fmaf(cam[5], y, cam[4] * x)) + cam[7];
-      const float ph2 = fmaf(cam[10], z, fmaf(cam[9], y, cam[8] * x)) + cam[11];
-      const float zc = fmaxf(ph2, 1e-8f);
-      float px = ph0 / zc, py = ph1 / zc;
-      px = fminf(fmaxf(px, -1e6f), 1e6f);
-      py = fminf(fmaxf(py, -1e6f), 1e6f);
-      const bool inb = px <= (float)(sc.W - 1) && px >= 0.f && py <= (float)(sc.H - 1) && py >= 0.f;
-      ri[RI_MASK] = (inb && ph2 > 0.f) ? 1.f : 0.f;
-      const float gx = 2.f * px / (float)(sc.W - 1) - 1.f, gy = 2.f * py / (float)(sc.H - 1) - 1.f;
-      ri[RI_IX] = ((gx + 1.f) / 2.f) * (float)(sc.W - 1);
-      ri[RI_IY] = ((gy + 1.f) / 2.f) * (float)(sc.H - 1);
-      ri[RI_FX] = ((gx + 1.f) / 2.f) * (float)(sc.w - 1);
-      ri[RI_FY] = ((gy + 1.f) / 2.f) * (float)(sc.h - 1);
-      // NeuRay convention
-      const float* kr = cam + 12;
-      const float c0 = fmaf(kr[2], z, fmaf(kr[1], y, kr[0] * x)) + kr[3];
-      const float c1 = fmaf(kr[6], z, fmaf(kr[5], y, kr[4] * x)) + kr[7];
-      float dep = fmaf(kr[10], z, fmaf(kr[9], y, kr[8] * x)) + kr[11];
-      const bool bad = fabsf(dep) < 1e-4f;
-      if (bad) dep = 1e-3f;
-      const float qx = c0 / dep, qy = c1 / dep;
-      const bool outside = qx < -0.5f || qx >= (float)sc.W - 0.5f || qy < -0.5f || qy >= (float)sc.H - 0.5f;
-      ri[RI_VALID] = (!bad && !outside) ? 1.f : 0.f;
-      ri[RI_DEPTH] = dep;
-      const float xn = qx / (float)(sc.W - 1) * 2.f - 1.f, yn = qy / (float)(sc.H - 1) * 2.f - 1.f;
-      if (sc.vh == sc.H && sc.vw == sc.W) {  // align_corners=True only when the map has the image size
-        ri[RI_VX] = ((xn + 1.f) / 2.f) * (float)(sc.vw - 1);
-        ri[RI_VY] = ((yn + 1.f) / 2.f) * (float)(sc.vh - 1);
-      } else {
-        ri[RI_VX] = ((xn + 1.f) * (float)sc.vw - 1.f) / 2.f;
-        ri[RI_VY] = ((yn + 1.f) * (float)sc.vh - 1.f) / 2.f;
+      for (int job = part; job < 3; job += PARTS) {
+        if (job == 0) {
+          if (v == 0) { sPt[p * 4] = x; sPt[p * 4 + 1] = y; sPt[p * 4 + 2] = z; }
+          // IBRNet convention
+          const float ph0 = fmaf(cam[2], z, fmaf(cam[1], y, cam[0] * x)) + cam[3];
+          const float ph1 = fmaf(cam[6], z, fmaf(cam[5], y, cam[4] * x)) + cam[7];
+          const float ph2 = fmaf(cam[10], z, fmaf(cam[9], y, cam[8] * x)) + cam[11];
+          const float zc = fmaxf(ph2, 1e-8f);
+          float px = ph0 / zc, py = ph1 / zc;
+          px = fminf(fmaxf(px, -1e6f), 1e6f);
+          py = fminf(fmaxf(py, -1e6f), 1e6f);
+          const bool inb = px <= (float)(sc.W - 1) && px >= 0.f && py <= (float)(sc.H - 1) && py >= 0.f;
+          ri[RI_MASK] = (inb && ph2 > 0.f) ? 1.f : 0.f;
+          const float gx = 2.f * px / (float)(sc.W - 1) - 1.f, gy = 2.f * py / (float)(sc.H - 1) - 1.f;
+          ri[RI_IX] = ((gx + 1.f) / 2.f) * (float)(sc.W - 1);
+          ri[RI_IY] = ((gy + 1.f) / 2.f) * (float)(sc.H - 1);
+          ri[RI_FX] = ((gx + 1.f) / 2.f) * (float)(sc.w - 1);
+          ri[RI_FY] = ((gy + 1.f) / 2.f) * (float)(sc.h - 1);
+        } else if (job == 1) {
+          // NeuRay convention
+          const float* kr = cam + 12;
+          const float c0 = fmaf(kr[2], z, fmaf(kr[1], y, kr[0] * x)) + kr[3];
+          const float c1 = fmaf(kr[6], z, fmaf(kr[5], y, kr[4] * x)) + kr[7];
+          float dep = fmaf(kr[10], z, fmaf(kr[9], y, kr[8] * x)) + kr[11];
+          const bool bad = fabsf(dep) < 1e-4f;
+          if (bad) dep = 1e-3f;
+          const float qx = c0 / dep, qy = c1 / dep;
+          const bool outside = qx < -0.5f || qx >= (float)sc.W - 0.5f || qy < -0.5f || qy >= (float)sc.H - 0.5f;
+          ri[RI_VALID] = (!bad && !outside) ? 1.f : 0.f;
+          ri[RI_DEPTH] = dep;
+          const float xn = qx / (float)(sc.W - 1) * 2.f - 1.f, yn = qy / (float)(sc.H - 1) * 2.f - 1.f;
+          if (sc.vh == sc.H && sc.vw == sc.W) {  // align_corners=True only when the map has the image size
+            ri[RI_VX] = ((xn + 1.f) / 2.f) * (float)(sc.vw - 1);
+            ri[RI_VY] = ((yn + 1.f) / 2.f) * (float)(sc.vh - 1);
+          } else {
+            ri[RI_VX] = ((xn + 1.f) * (float)sc.vw - 1.f) / 2.f;
+            ri[RI_VY] = ((yn + 1.f) * (float)sc.vh - 1.f) / 2.f;
+          }
+        } else {
+          // colour-blend ray difference (ibrnet.py:144-167) between the query camera and view v
+          const float* cc = cam + 24;
+          float ax = sc.qc[0] - x, ay = sc.qc[1] - y, az = sc.qc[2] - z;
+          const float an = sqrtf(ax * ax + ay * ay + az * az) + 1e-6f;
+          ax /= an; ay /= an; az /= an;
+          float bx = cc[0] - x, by = cc[1] - y, bz = cc[2] - z;
+          const float bn = sqrtf(bx * bx + by * by + bz * bz) + 1e-6f;
+          bx /= bn; by /= bn; bz /= bn;
+          const float dx = ax - bx, dy = ay - by, dz = az - bz;
+          const float dn = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);
+          ri[RI_RD0] = dx / dn; ri[RI_RD1] = dy / dn; ri[RI_RD2] = dz / dn;
+          ri[RI_RD3] = ax * bx + ay * by + az * bz;
+        }
       }
     } else {
-#pragma unroll
-      for (int i = 0; i < RI_N; ++i) ri[i] = 0.f;
+      for (int i = part; i < RI_N; i += PARTS) ri[i] = 0.f;
     }
   }
   cta_sync();
 
   AGG_STAMP(1);
   // ---- phase 2: 32-channel visibility features (border padding), one warp per row ------------------------------
-  // All four taps of two rows are requested before any is consumed (addresses clamped into the map, taps outside
-  // carry weight 0), so a warp keeps 8 independent loads in flight instead of one.
-  for (int rb = warp; rb < ROWS; rb += 2 * (NT / 32)) {
-    float q[2][4], wgt[2][4], valid[2];
+  // All four taps of four rows are requested before any is consumed (addresses clamped into the map, taps outside
+  // carry weight 0), so a warp keeps 16 independent loads in flight instead of one.
+  for (int rb = warp; rb < ROWS; rb += 4 * (NT / 32)) {
+    float q[4][4], wgt[4][4], valid[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int r = rb + u * (NT / 32);
       valid[u] = 0.f;
 #pragma unroll
@@ -203,13 +246,15 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int r = rb + u * (NT / 32);
-      float a = q[u][0] * wgt[u][0];
-      a += q[u][1] * wgt[u][1];
-      a += q[u][2] * wgt[u][2];
-      a += q[u][3] * wgt[u][3];
-      sX[r * LDX + lane] = a * valid[u];
+      if (r < ROWS) {
+        float a = q[u][0] * wgt[u][0];
+        a += q[u][1] * wgt[u][1];
+        a += q[u][2] * wgt[u][2];
+        a += q[u][3] * wgt[u][3];
+        sX[r * LDX + lane] = a * valid[u];
+      }
     }
   }
   // (tile_gemm starts with a __syncthreads)
@@ -229,13 +274,16 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
     gemm_resident<TM1, 8, 4>(sX + r0 * LDX, LDX, sB, 128, tc * 4, 64, 32, acc);
+    float bias[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) bias[j] = __ldg(w.dec1_b + (j >> 2) * 64 + tc * 4 + (j & 3));
 #pragma unroll
     for (int i = 0; i < TM1; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = (j >> 2) * 64 + tc * 4 + (j & 3);
-        sH[(r0 + i) * LDH + c] = elu(acc[i][j] + __ldg(w.dec1_b + c));
-      }
+      for (int g = 0; g < 2; ++g)
+        *reinterpret_cast<float4*>(sH + (r0 + i) * LDH + g * 64 + tc * 4) =
+            make_float4(elu(acc[i][g * 4] + bias[g * 4]), elu(acc[i][g * 4 + 1] + bias[g * 4 + 1]),
+                        elu(acc[i][g * 4 + 2] + bias[g * 4 + 2]), elu(acc[i][g * 4 + 3] + bias[g * 4 + 3]));
   }
   cta_sync();
   AGG_STAMP(10);
@@ -250,17 +298,17 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     gemm_resident<TM2, 4, 4>(sH + r0 * LDH + 32 * hd, LDH, sB + 4096, 128, cg * 4, 0, 32, acc);
     cta_sync();  // every thread has read its inputs: write in place
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.dec2_b + cg * 4));
 #pragma unroll
     for (int i = 0; i < TM2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int c = cg * 4 + j;
-        sH[(r0 + i) * LDH + c] = elu(acc[i][j] + __ldg(w.dec2_b + c));
-      }
+      *reinterpret_cast<float4*>(sH + (r0 + i) * LDH + cg * 4) =
+          make_float4(elu(acc[i][0] + b4.x), elu(acc[i][1] + b4.y), elu(acc[i][2] + b4.z), elu(acc[i][3] + b4.w));
   }
   cta_sync();
   AGG_STAMP(11);
-  // head outputs: (row, j) dot products of length 32 spread over all threads, then one thread per row for the scalar tail
+  // head outputs: (row, j) dot products of length 32 spread over all threads, each followed by its own output activation
+  // (softplus for the two means, softplus + 0.05 for the two scales, sigmoid for the mixture / visibility weights);
+  // then one thread per row for the short scalar tail
   for (int i = tid; i < rows * 6; i += NT) {
     const int r = i / 6, j = i - r * 6;
     const int hd = j < 2 ? 0 : (j < 4 ? 1 : (j == 4 ? 2 : 3));
@@ -273,22 +321,13 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       const float4 w4 = __ldg(reinterpret_cast<const float4*>(wj + k));
       a0 = fmaf(w4.x, h4.x, a0); a1 = fmaf(w4.y, h4.y, a1); a2 = fmaf(w4.z, h4.z, a2); a3 = fmaf(w4.w, h4.w, a3);
     }
-    sO1[i] = ((a0 + a1) + (a2 + a3)) + __ldg(w.dec3_b + j);
+    const float o = ((a0 + a1) + (a2 + a3)) + __ldg(w.dec3_b + j);
+    sO1[i] = j < 2 ? softplus(o) : (j < 4 ? softplus(o) + 0.05f : sigmoidf(o));
   }
-  // the colour-blend per-view weights (28 KB) take over the staging ring: the decoder weights are dead, the ring is not
-  // used again before out_fc; they are consumed right after the feature gather
   cta_sync();
-  if (with_blend) {
-    for (int i = tid; i < 224 * 8; i += NT) cp_async16(sB + i * 4, w.bl1v + i * 4);
-    cp_async_commit();
-  }
   if (tid < rows) {
-    float o[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) o[j] = sO1[tid * 6 + j];
-    const float m0 = softplus(o[0]), m1 = softplus(o[1]);
-    const float v0 = softplus(o[2]) + 0.05f, v1 = softplus(o[3]) + 0.05f;
-    const float aw = sigmoidf(o[4]), vs = sigmoidf(o[5]);
+    const float m0 = sO1[tid * 6], m1 = sO1[tid * 6 + 1], v0 = sO1[tid * 6 + 2], v1 = sO1[tid * 6 + 3];
+    const float aw = sO1[tid * 6 + 4], vs = sO1[tid * 6 + 5];
     float* ri = sRI + tid * RI_N;
     const float dep = ri[RI_DEPTH];
     const float near_inv = -1.f / near_, far_inv = -1.f / far_;
@@ -300,6 +339,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     const float cdf1 = (0.5f + 0.5f * tanhf((dn - m1) * v1)) * vs;
     const float vis = (1.f - cdf0) * aw + (1.f - cdf1) * (1.f - aw);
     ri[RI_VIS] = vis * ri[RI_VALID];
+    if (mvv_out) mvv_out[n0 * V + tid] = ri[RI_VIS];
   }
   cta_sync();
 
@@ -376,53 +416,81 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
     }
   }
-  for (int r = warp; r < ROWS; r += NT / 32) {
-    float* frow = sF + r * LDF;
-    if (r < rows) {
-      const float* ri = sRI + r * RI_N;
-      const int p = r / V, v = r - p * V;
-      // rgb: lanes 0..3 fetch one tap each
-      const Taps ti = make_taps(ri[RI_IX], ri[RI_IY], sc.W, sc.H, true);
-      float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (lane < 4 && ti.w[lane] != 0.f) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(
-            sc.images + (((size_t)v * sc.H + ti.y0 + (lane >> 1)) * sc.W + ti.x0 + (lane & 1)) * 4));
-        c.x = q.x * ti.w[lane]; c.y = q.y * ti.w[lane]; c.z = q.z * ti.w[lane];
-      }
-      c.x += __shfl_xor_sync(0xffffffffu, c.x, 1); c.y += __shfl_xor_sync(0xffffffffu, c.y, 1); c.z += __shfl_xor_sync(0xffffffffu, c.z, 1);
-      c.x += __shfl_xor_sync(0xffffffffu, c.x, 2); c.y += __shfl_xor_sync(0xffffffffu, c.y, 2); c.z += __shfl_xor_sync(0xffffffffu, c.z, 2);
-      if (lane == 0) {
-        frow[0] = c.x; frow[1] = c.y; frow[2] = c.z;
-        if (rgbvis_out) {
-          float4 o = make_float4(c.x, c.y, c.z, ri[RI_VIS]);
-          *reinterpret_cast<float4*>(rgbvis_out + ((n0 + p) * V + v) * 4) = o;
+  // rgb (lanes 0..3 fetch one tap each) and, for rendering, the per-view half of the colour-blend first layer
+  // (model.py:532-535).  That layer is linear, and so is the bilinear fetch: W f(x) = sum_t b_t (W f_t), so the 192 map
+  // channels are pre-projected once per frame (sc.featb, [V][h][w][32]) and a row gathers 32 more channels instead of
+  // running a [224 x 32] GEMM; the remaining inputs (rgb, visibility, ray difference) are 8 FMAs per output.
+  // Four rows per iteration, all loads requested before any is consumed.
+  {
+    float wb[8], bias = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wb[i] = 0.f;
+    if (with_blend) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) wb[i] = __ldg(w.bl1v + i * 32 + lane);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) wb[3 + i] = __ldg(w.bl1v + (195 + i) * 32 + lane);
+      bias = __ldg(w.bl1_b + lane);
+    }
+    for (int rb = warp; rb < ROWS; rb += 4 * (NT / 32)) {
+      float4 cq[4];
+      float bq[4][4], bw[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * (NT / 32);
+        cq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) { bq[u][t] = 0.f; bw[u][t] = 0.f; }
+        if (r < rows) {
+          const float* ri = sRI + r * RI_N;
+          const int v = r % V;
+          const Taps ti = make_taps(ri[RI_IX], ri[RI_IY], sc.W, sc.H, true);
+          if (lane < 4 && ti.w[lane] != 0.f) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(
+                sc.images + (((size_t)v * sc.H + ti.y0 + (lane >> 1)) * sc.W + ti.x0 + (lane & 1)) * 4));
+            cq[u] = make_float4(q.x * ti.w[lane], q.y * ti.w[lane], q.z * ti.w[lane], 0.f);
+          }
+          if (with_blend) {
+            const Taps tf = make_taps(ri[RI_FX], ri[RI_FY], sc.w, sc.h, true);
+            const float* bb = sc.featb + ((size_t)v * sc.h * sc.w) * 32 + lane;
+            const int fx0 = min(max(tf.x0, 0), sc.w - 1), fx1 = min(max(tf.x0 + 1, 0), sc.w - 1);
+            const int fy0 = min(max(tf.y0, 0), sc.h - 1), fy1 = min(max(tf.y0 + 1, 0), sc.h - 1);
+            bq[u][0] = __ldg(bb + ((size_t)fy0 * sc.w + fx0) * 32);
+            bq[u][1] = __ldg(bb + ((size_t)fy0 * sc.w + fx1) * 32);
+            bq[u][2] = __ldg(bb + ((size_t)fy1 * sc.w + fx0) * 32);
+            bq[u][3] = __ldg(bb + ((size_t)fy1 * sc.w + fx1) * 32);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) bw[u][t] = tf.w[t];
+          }
         }
       }
-      if (lane < 28) frow[200 + lane] = 0.f;
-    } else {
-      for (int k = lane; k < LDF; k += 32) frow[k] = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r = rb + u * (NT / 32);
+        if (r < rows) {   // warp-uniform
+          float4 c = cq[u];
+          c.x += __shfl_xor_sync(0xffffffffu, c.x, 1); c.y += __shfl_xor_sync(0xffffffffu, c.y, 1); c.z += __shfl_xor_sync(0xffffffffu, c.z, 1);
+          c.x += __shfl_xor_sync(0xffffffffu, c.x, 2); c.y += __shfl_xor_sync(0xffffffffu, c.y, 2); c.z += __shfl_xor_sync(0xffffffffu, c.z, 2);
+          c.x = __shfl_sync(0xffffffffu, c.x, 0); c.y = __shfl_sync(0xffffffffu, c.y, 0); c.z = __shfl_sync(0xffffffffu, c.z, 0);
+          const float* ri = sRI + r * RI_N;
+          float* frow = sF + r * LDF;
+          const int p = r / V, v = r - p * V;
+          if (lane == 0) {
+            frow[0] = c.x; frow[1] = c.y; frow[2] = c.z;
+            if (rgbvis_out) *reinterpret_cast<float4*>(rgbvis_out + ((n0 + p) * V + v) * 4) = make_float4(c.x, c.y, c.z, ri[RI_VIS]);
+          }
+          if (with_blend) {
+            float a = 0.f;
+#pragma unroll
+            for (int t = 0; t < 4; ++t) a = fmaf(bq[u][t], bw[u][t], a);
+            a = fmaf(c.x, wb[0], a); a = fmaf(c.y, wb[1], a); a = fmaf(c.z, wb[2], a);
+            a = fmaf(ri[RI_VIS], wb[3], a);
+            a = fmaf(ri[RI_RD0], wb[4], a); a = fmaf(ri[RI_RD1], wb[5], a); a = fmaf(ri[RI_RD2], wb[6], a); a = fmaf(ri[RI_RD3], wb[7], a);
+            partial_out[((n0 + p) * V + v) * 32 + lane] = a + bias;
+          }
+        }
+      }
     }
-  }
-  // per-row scalars, one thread per row: visibility column and the colour-blend ray difference (ibrnet.py:144-167)
-  // between the query camera and view v
-  if (tid < rows) {
-    const float* ri = sRI + tid * RI_N;
-    float* frow = sF + tid * LDF;
-    const int p = tid / V, v = tid - p * V;
-    frow[195] = ri[RI_VIS];
-    const float x = sPt[p * 4], y = sPt[p * 4 + 1], z = sPt[p * 4 + 2];
-    const float* cc = sc.cams + v * 32 + 24;
-    float ax = sc.qc[0] - x, ay = sc.qc[1] - y, az = sc.qc[2] - z;
-    const float an = sqrtf(ax * ax + ay * ay + az * az) + 1e-6f;
-    ax /= an; ay /= an; az /= an;
-    float bx = cc[0] - x, by = cc[1] - y, bz = cc[2] - z;
-    const float bn = sqrtf(bx * bx + by * by + bz * bz) + 1e-6f;
-    bx /= bn; by /= bn; bz /= bn;
-    const float dx = ax - bx, dy = ay - by, dz = az - bz;
-    const float dn = fmaxf(sqrtf(dx * dx + dy * dy + dz * dz), 1e-6f);
-    frow[196] = dx / dn; frow[197] = dy / dn; frow[198] = dz / dn;
-    frow[199] = ax * bx + ay * by + az * bz;
-    if (mvv_out) mvv_out[(n0 + p) * V + v] = ri[RI_VIS];
   }
   cta_sync();
   if (mvf_out) {
@@ -433,48 +501,11 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   }
 
   AGG_STAMP(5);
-  // ---- phase 8 (runs before the mean/variance): per-view half of the colour-blend first layer ---------------------------
-  if (with_blend) {
-    // [ROWS x 224] . [224 x 32] against the weights parked in the staging ring; no barriers inside
-    constexpr int TMB = ROWS / 32;
-    cp_async_wait<0>();
-    cta_sync();
-    const int tc = tid & 7, r0 = (tid >> 3) * TMB;
-    float acc[TMB][4];
-#pragma unroll
-    for (int i = 0; i < TMB; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    gemm_resident<TMB, 4, 4>(sF + r0 * LDF, LDF, sB, 32, tc * 4, 0, 224, acc);
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.bl1_b + tc * 4));
-#pragma unroll
-    for (int i = 0; i < TMB; ++i)
-      if (r0 + i < rows)
-        *reinterpret_cast<float4*>(partial_out + (n0 * V + r0 + i) * 32 + tc * 4) =
-            make_float4(acc[i][0] + b4.x, acc[i][1] + b4.y, acc[i][2] + b4.z, acc[i][3] + b4.w);
-  }
   AGG_STAMP(6);
   // ---- phase 6: visibility-weighted mean / variance over views (ibrnet.py:8-12) ---------------------------------
   for (int p = warp; p < np; p += NT / 32) {
-    // one warp per sample, lanes over channels; the view weights are read once
-    float wv[16];
-#pragma unroll
-    for (int v = 0; v < 16; ++v) wv[v] = v < V ? sRI[(p * V + v) * RI_N + RI_W] : 0.f;
-    const float* f0 = sF + (p * V) * LDF;
-#pragma unroll 1
-    for (int c = lane; c < C_RGBF; c += 32) {
-      float f[16];
-#pragma unroll
-      for (int v = 0; v < 16; ++v) f[v] = v < V ? f0[v * LDF + c] : 0.f;
-      float m = 0.f;
-#pragma unroll
-      for (int v = 0; v < 16; ++v) if (v < V) m += f[v] * wv[v];
-      float var = 0.f;
-#pragma unroll
-      for (int v = 0; v < 16; ++v) if (v < V) { const float d = f[v] - m; var += wv[v] * (d * d); }
-      sG[p * LDG + c] = m;
-      sG[p * LDG + C_RGBF + c] = var;
-    }
+    if (V <= 8) mean_var_rows<8>(sF + (p * V) * LDF, sRI + (p * V) * RI_N, V, lane, sG + p * LDG);
+    else mean_var_rows<16>(sF + (p * V) * LDF, sRI + (p * V) * RI_N, V, lane, sG + p * LDG);
   }
   for (int i = tid; i < (TP_MAX - np) * LDG; i += NT) sG[np * LDG + i] = 0.f;
 
@@ -489,6 +520,28 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   });
 
   AGG_STAMP(8);
+}
+
+// Per-frame pre-projection of the reference feature maps through the map-feature rows of the colour-blend first layer
+// (rgb_blending_mlp.0, model.py:90-96,532-535): out[p][n] = sum_c feat[p][c] * Wt[3 + c][n], Wt = RenderW::bl1v [224][32].
+// One warp per pixel, lane = output channel.
+__global__ void __launch_bounds__(256) blend_project_kernel(const float* __restrict__ feat, const int64_t P,
+                                                            const float* __restrict__ Wt, float* __restrict__ out) {
+  __shared__ float sW[C_FEAT * 32];
+  for (int i = threadIdx.x; i < C_FEAT * 32; i += blockDim.x) sW[i] = Wt[3 * 32 + i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t p = (int64_t)blockIdx.x * 8 + warp; p < P; p += (int64_t)gridDim.x * 8) {
+    float f[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) f[j] = __ldg(feat + p * C_FEAT + j * 32 + lane);
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+#pragma unroll
+      for (int l = 0; l < 32; ++l) a = fmaf(__shfl_sync(0xffffffffu, f[j], l), sW[(j * 32 + l) * 32 + lane], a);
+    out[p * 32 + lane] = a;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -544,6 +597,7 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
                      float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, cudaStream_t st) {
   if (N <= 0) return 0;
   if (sc.V < 1 || sc.V > 16) return set_error("aggregate: number of reference views must be in 1..16");
+  if (with_blend && !sc.featb) return set_error("aggregate: scene.featmaps_blend is NULL (call nlb_blend_prepare once per frame)");
   constexpr int ROWS = AGG_ROWS;
   const size_t smem = agg_smem_floats<ROWS>() * sizeof(float);
   if (set_smem(aggregate_kernel<ROWS>, smem)) return 1;
@@ -551,6 +605,13 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   const unsigned grid = (unsigned)((N + TP - 1) / TP);
   aggregate_kernel<ROWS><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
   return check_launch("aggregate_kernel");
+}
+
+int launch_blend_project(const float* feat, int64_t P, const float* bl1v, float* out, cudaStream_t st) {
+  if (P <= 0) return 0;
+  const int64_t blocks = (P + 7) / 8;
+  blend_project_kernel<<<(unsigned)(blocks < 148 * 8 ? blocks : 148 * 8), 256, 0, st>>>(feat, P, bl1v, out);
+  return check_launch("blend_project_kernel");
 }
 
 int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,
