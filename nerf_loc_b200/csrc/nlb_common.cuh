@@ -218,34 +218,33 @@ __device__ __forceinline__ void tile_gemm_frag(const ASrc A, const int rows, con
   gemm_core<TM, TN, COLS, SCALE>(A, f.r0, f.active, Wt, ldb, K, sB, kscale, f.acc);
 }
 
-// Small-M GEMM: out[r][c] = sum_k A_r[k] * Wt[k*ldb + c] for r < 16, c < COLS.  A tile GEMM would give every thread one
-// row and re-read the staged weight tile 16 times; here a thread owns one output COLUMN for all 16 rows (16 independent
-// accumulators), reads its weight column straight from L2 (a warp reads 128 contiguous bytes per k, no staging, no
-// barrier per K-tile) and the 256 threads split K in NT/COLS slices that are reduced through `red`
-// (>= (NT/COLS)*16*COLS floats of shared scratch).  arow(r, c) -> shared-memory pointer to row r as seen by column c.
+// Small-M GEMM: out[r][c] = sum_k A_r[k] * Wt[k*ldb + c] for r < R (<= 16), c < COLS.  A tile GEMM would give every thread one
+// row and re-read the staged weight tile R times; here a thread owns two adjacent output COLUMNS for all R rows (R FFMA2
+// accumulator pairs), reads its weight pair straight from L2 (a warp reads 256 contiguous bytes per k, no staging, no
+// barrier per K-tile) and the 256 threads split K in 2*NT/COLS slices that are reduced through `red`
+// (>= (2*NT/COLS)*R*COLS floats of shared scratch).  Many K slices keep the number of dependent L2 round trips per thread
+// small - the loop is latency bound.  arow(r, c) -> shared-memory pointer to row r as seen by column c (c even).
 template <int COLS, int R = 16, class ARow, class Epi>
 __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__ Wt, const int ldb, const int K, float* red,
                                             Epi epi) {
-  constexpr int KSPLIT = NT / COLS;
+  constexpr int KSPLIT = 2 * NT / COLS;
   const int tid = threadIdx.x;
-  const int c = tid % COLS, ks = tid / COLS;
-  const int kper = K / KSPLIT;
+  const int c = (tid % (COLS / 2)) * 2, ks = tid / (COLS / 2);
+  const int kper = K / KSPLIT;       // multiple of 4
   const int k0 = ks * kper;
-  // even-k / odd-k partial sums per row: one FFMA2 covers two consecutive k (the a pair comes out of the float4 fragment, the
-  // b pair out of two adjacent weight loads); the halves are added once at the end
   float acc[R][2];
 #pragma unroll
   for (int r = 0; r < R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
   const float* wp = Wt + (size_t)k0 * ldb + c;
-  // weight loads in flight per thread: the batch for step k+KB is requested before the FMAs of step k (the loop is
-  // L2-latency bound otherwise); with few rows there are registers to spare for a deeper batch
-  constexpr int KB = R <= 8 ? 16 : 8;
-  float b[KB], bn[KB];
+  // weight loads in flight per thread: the batch for step k+KB is requested before the FMAs of step k
+  constexpr int KB = 8;
+  float2 b[KB], bn[KB];
 #pragma unroll
-  for (int j = 0; j < KB; ++j) b[j] = (j < kper) ? __ldg(wp + (size_t)j * ldb) : 0.f;
+  for (int j = 0; j < KB; ++j) b[j] = (j < kper) ? __ldg(reinterpret_cast<const float2*>(wp + (size_t)j * ldb)) : make_float2(0.f, 0.f);
   for (int k = 0; k < kper; k += KB) {
 #pragma unroll
-    for (int j = 0; j < KB; ++j) bn[j] = (k + KB + j < kper) ? __ldg(wp + (size_t)(k + KB + j) * ldb) : 0.f;
+    for (int j = 0; j < KB; ++j)
+      bn[j] = (k + KB + j < kper) ? __ldg(reinterpret_cast<const float2*>(wp + (size_t)(k + KB + j) * ldb)) : make_float2(0.f, 0.f);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float* ap = arow(r, c) + k0 + k;
@@ -253,28 +252,25 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
       for (int g = 0; g < KB / 4; ++g) {
         if (k + 4 * g < kper) {
           const float4 a = *reinterpret_cast<const float4*>(ap + 4 * g);
-          fma2_v(acc[r][0], acc[r][1], a.x, a.y, b[4 * g], b[4 * g + 1]);
-          fma2_v(acc[r][0], acc[r][1], a.z, a.w, b[4 * g + 2], b[4 * g + 3]);
+          fma2_s(acc[r][0], acc[r][1], a.x, b[4 * g].x, b[4 * g].y);
+          fma2_s(acc[r][0], acc[r][1], a.y, b[4 * g + 1].x, b[4 * g + 1].y);
+          fma2_s(acc[r][0], acc[r][1], a.z, b[4 * g + 2].x, b[4 * g + 2].y);
+          fma2_s(acc[r][0], acc[r][1], a.w, b[4 * g + 3].x, b[4 * g + 3].y);
         }
       }
     }
 #pragma unroll
     for (int j = 0; j < KB; ++j) b[j] = bn[j];
   }
-  if (KSPLIT == 1) {
+  cta_sync();  // `red` may alias a buffer an earlier phase still reads
 #pragma unroll
-    for (int r = 0; r < R; ++r) epi(r, c, acc[r][0] + acc[r][1]);
-  } else {
-    cta_sync();  // `red` may alias a buffer an earlier phase still reads
+  for (int r = 0; r < R; ++r) *reinterpret_cast<float2*>(red + (ks * R + r) * COLS + c) = make_float2(acc[r][0], acc[r][1]);
+  cta_sync();
+  for (int i = tid; i < R * COLS; i += NT) {
+    float v = 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r) red[(ks * R + r) * COLS + c] = acc[r][0] + acc[r][1];
-    cta_sync();
-    for (int i = tid; i < R * COLS; i += NT) {
-      float v = 0.f;
-#pragma unroll
-      for (int q = 0; q < KSPLIT; ++q) v += red[q * R * COLS + i];
-      epi(i / COLS, i % COLS, v);
-    }
+    for (int q = 0; q < KSPLIT; ++q) v += red[q * R * COLS + i];
+    epi(i / COLS, i % COLS, v);
   }
 }
 
