@@ -191,16 +191,16 @@ __device__ __forceinline__ void dec_epilogue(const RayCtx& c, const uint32_t tme
 }
 
 __device__ __forceinline__ void load_x(unsigned char* sm, const float* __restrict__ fagg, int64_t s0, int S, int tid) {
-  // four independent 16-byte loads in flight per thread before the first split / store
-  for (int i0 = tid; i0 < S * 32; i0 += 4 * NT) {
-    float4 v[4];
+  // eight independent 16-byte loads in flight per thread before the first split / store
+  for (int i0 = tid; i0 < S * 32; i0 += 8 * NT) {
+    float4 v[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int i = i0 + u * NT;
       v[u] = i < S * 32 ? __ldg(reinterpret_cast<const float4*>(fagg + (s0 + (i >> 5)) * W_HID + (i & 31) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int i = i0 + u * NT;
       if (i < S * 32) tc::store_split4(sm + RY_X_HI, sm + RY_X_LO, i >> 5, (i & 31) * 4, SBO128, v[u].x, v[u].y, v[u].z, v[u].w);
     }
@@ -312,10 +312,15 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
       float logit = sW2[544];
 #pragma unroll 4
       for (int o = 0; o < 16; ++o) {
-        float a = sW2[512 + o];
+        // even-k / odd-k partial sums: one FFMA2 per two k, weights read as float4 (broadcast)
+        float a = sW2[512 + o], a1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < 32; ++k) a = fmaf(sW2[o * 32 + k], h1[k], a);
-        logit = fmaf(sW2[528 + o], leaky(a), logit);
+        for (int k = 0; k < 32; k += 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(sW2 + o * 32 + k);
+          fma2_v(a, a1, w4.x, w4.y, h1[k], h1[k + 1]);
+          fma2_v(a, a1, w4.z, w4.w, h1[k + 2], h1[k + 3]);
+        }
+        logit = fmaf(sW2[528 + o], leaky(a + a1), logit);
       }
       const float vis = __ldg(rgbvis + (s0 * V + i) * 4 + 3);
       sLogit[i] = vis == 0.f ? -1e9f : logit;

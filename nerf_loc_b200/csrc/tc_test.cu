@@ -1,5 +1,5 @@
 // Self-test of the tcgen05 building blocks: C[128 x 128] = A[128 x K] * W[128 x K]^T for K <= 64 (one shot, no staging).
-// mode 0: single-pass tf32, mode 1: 3xTF32.  Exposed as nlb_debug_tc_gemm for tests/test_gpu_tc.py.
+// mode 0: single-pass tf32, mode 1: 3xTF32, mode 2: 3xTF32 with the A operand (hi and lo) in tensor memory.  Exposed as nlb_debug_tc_gemm for tests/test_gpu_tc.py.
 #include "nlb_internal.h"
 #include "tc_common.cuh"
 
@@ -17,7 +17,7 @@ tc_test_kernel(const float* __restrict__ A, const float* __restrict__ W, const i
   unsigned char* aLo = aHi + tile;
   unsigned char* bHi = aLo + tile;
   unsigned char* bLo = bHi + tile;
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 128);
+  if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
   if (tid == 32) tc::mbar_init(&mbar, 1);
   for (int i = tid; i < 128 * K; i += 256) {
     const int r = i / K, k = i - r * K;
@@ -34,7 +34,38 @@ tc_test_kernel(const float* __restrict__ A, const float* __restrict__ W, const i
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
-  if (tid == 0) {
+  if (mode == 2) {
+    // A hi -> TMEM columns [128, 128+K), A lo -> [192, 192+K); warp w < 4 owns lanes 32w .. 32w+31
+    if (warp < 4) {
+      const int row = warp * 32 + lane;
+      const uint32_t base = tmem + ((uint32_t)(warp * 32) << 16);
+      for (int k0 = 0; k0 < K; k0 += 8) {
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tc::split_tf32(A[row * K + k0 + j], hi[j], lo[j]);
+        tc::tmem_st8(base + 128u + (uint32_t)k0, hi);
+        tc::tmem_st8(base + 192u + (uint32_t)k0, lo);
+      }
+      tc::tmem_st_wait();
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    if (tid == 0) {
+      const uint32_t idesc = tc::idesc_tf32(128, 128);
+      uint32_t acc = 0;
+      for (int pass = 0; pass < 3; ++pass) {                       // lo*hi, hi*lo, hi*hi
+        const uint32_t a = tmem + (pass == 0 ? 192u : 128u);
+        const unsigned char* b = pass == 1 ? bLo : bHi;
+        for (int s = 0; s < K / 8; ++s) {
+          const uint64_t bd = tc::smem_desc(tc::smem_u32(b) + s * 256, 128, sbo);
+          tc::mma_tf32_ts(tmem, a + (uint32_t)(s * 8), bd, idesc, acc);
+          acc = 1;
+        }
+      }
+      tc::mma_commit(&mbar);
+    }
+  } else if (tid == 0) {
     const uint32_t idesc = tc::idesc_tf32(128, 128);
     uint32_t acc = 0;
     const int npass = mode ? 3 : 1;
@@ -64,7 +95,7 @@ tc_test_kernel(const float* __restrict__ A, const float* __restrict__ W, const i
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 128);
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
 int launch_tc_test(const float* A, const float* W, int K, int mode, float* C, cudaStream_t st) {

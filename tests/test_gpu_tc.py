@@ -15,11 +15,12 @@ def test_tc_gemm_modes(K):
     W = torch.randn(128, K, generator=g).cuda()
     ref = (A.double() @ W.double().t())
     errs = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2):
         C = torch.zeros(128, 128, device="cuda")
         _lib.check(L.nlb_debug_tc_gemm(_lib.ptr(A), _lib.ptr(W), K, mode, _lib.ptr(C), _lib.stream()))
         torch.cuda.synchronize()
         errs[mode] = float((C.double() - ref).abs().max() / ref.abs().max())
-    print("K", K, "tf32 err", errs[0], "3xTF32 err", errs[1])
+    print("K", K, "tf32 err", errs[0], "3xTF32 err", errs[1], "3xTF32 A-in-TMEM err", errs[2])
     assert errs[0] < 5e-3
     assert errs[1] < 2e-6
+    assert errs[2] < 2e-6   # A operand read from tensor memory (tcgen05.mma [d], [a], b-desc)
