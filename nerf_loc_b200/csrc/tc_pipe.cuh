@@ -127,6 +127,30 @@ __device__ __forceinline__ void mma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint3
   }
 }
 
+// Same with the A operand in tensor memory (lane = row, one 32-bit column per k)
+__device__ __forceinline__ void mma_tf32_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              bool accumulate) {
+  if (accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .b64 db;\n"
+        ".reg .pred p;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.eq.u32 p, 1, 1;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .b64 db;\n"
+        ".reg .pred p;\n"
+        "mov.b64 db, {%2, %3};\n"
+        "setp.eq.u32 p, 1, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n"
+        "}\n" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+  }
+}
+
 // One elected lane of a converged warp (PTX elect.sync).  The service warps run their loops warp-uniformly and predicate only
 // the tcgen05 / bulk-copy instructions with this, so descriptor words live in uniform registers - inside an `if (lane == 0)`
 // region the compiler has to wrap every UTCHMMA in an R2UR waterfall loop instead.

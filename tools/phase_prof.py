@@ -20,10 +20,11 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 64)()
 _lib.load().nlb_debug_read_prof(buf, 64)
 v = list(buf)
-names = ["phase0 (PE, rd_fc, A1 write)", "wait L1", "epi L1", "wait L2", "epi L2", "wait L3", "epi L3", "sync", "q + q~ GEMMs", "scores+softmax", "ctx", "o + fc GEMMs", "LN + out"]
-for i in range(12):
-    print(f"{names[i]:32s} {v[i+1]-v[i]:8d} clk")
-print("total", v[12] - v[0])
+names = ["P0(t): PE, rd_fc, A1 -> TMEM", "A(t-1): scores, softmax, ctx", "wait L1", "E1(t)", "B(t-1): wv + fc GEMMs", "wait L2", "E2(t)",
+         "C1(t-1): LN, weights, out", "C2(t): q + q~ GEMMs", "wait L3", "E3(t): pf -> smem"]
+for i in range(11):
+    print(f"{names[i]:36s} {v[i+1]-v[i]:8d} clk")
+print("slot total", v[11] - v[0])
 
 an = ["proj", "vis gather", "decoder GEMMs+heads", "view weights", "rgb/feat gather", "blend partial", "mean/var", "out_fc"]
 for i in range(8):
