@@ -154,6 +154,44 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     cta_sync();
     int64_t n0p = 0;   // previous tile
     int npp = 0;
+    // this thread's (sample, neighbour) record of a tile: neighbour id + geometry, sample position and viewing direction.
+    // Requested one slot ahead so that the dependent index -> geometry loads are off the critical path of phase 0.
+    struct RowRec { int id; bool live; float4 g0, g1; float x, y, z, dx, dy, dz; };
+    auto load_row = [&](const int64_t n0t, const int npt) {
+      RowRec q;
+      q.id = -1; q.g0 = make_float4(0.f, 0.f, 0.f, 0.f); q.g1 = q.g0;
+      q.x = q.y = q.z = q.dx = q.dy = q.dz = 0.f;
+      const int p = row >> 3, k = row & 7;
+      q.live = p < npt && k < K;
+      if (q.live) {
+        const int64_t n = n0t + p;
+        q.id = knn_idx[n * K + k];
+        q.g0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)q.id * 8));
+        q.g1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)q.id * 8 + 4));
+        if (ps.xyz) {
+          q.x = ps.xyz[n * 3]; q.y = ps.xyz[n * 3 + 1]; q.z = ps.xyz[n * 3 + 2];
+        } else {
+          const int64_t r = n / ps.S;
+          const float t = ps.z[r * ps.zs + (n - r * ps.S)];
+          q.x = __fadd_rn(ps.rays_o[r * 3 + 0], __fmul_rn(ps.rays_d[r * 3 + 0], t));
+          q.y = __fadd_rn(ps.rays_o[r * 3 + 1], __fmul_rn(ps.rays_d[r * 3 + 1], t));
+          q.z = __fadd_rn(ps.rays_o[r * 3 + 2], __fmul_rn(ps.rays_d[r * 3 + 2], t));
+        }
+        if (ps.dirs) {
+          q.dx = ps.dirs[n * 3]; q.dy = ps.dirs[n * 3 + 1]; q.dz = ps.dirs[n * 3 + 2];
+        } else if (ps.rays_d && !ps.xyz) {
+          const int64_t r = n / ps.S;
+          q.dx = ps.rays_d[r * 3]; q.dy = ps.rays_d[r * 3 + 1]; q.dz = ps.rays_d[r * 3 + 2];
+        } else {  // direction=None: the nearest neighbour's own direction (model.py:391-392)
+          const int id0 = knn_idx[n * K];
+          const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8));
+          const float4 h1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8 + 4));
+          q.dx = h0.w; q.dy = h1.x; q.dz = h1.y;
+        }
+      }
+      return q;
+    };
+    RowRec nxt = load_row((int64_t)blockIdx.x * NB_TP, (int)min((int64_t)NB_TP, N - (int64_t)blockIdx.x * NB_TP));
     for (int it = 0; it <= nmy; ++it) {
       const bool cur = it < nmy, prev = it > 0;
       const bool stamp = it == 1 && blockIdx.x == gridDim.x / 2 && tid == 0;
@@ -168,36 +206,10 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         // two threads per row, each with half of the work: positional-encoding octaves 0-4 / 5-9 and ray_diff_fc outputs
         // 0-13 / 14-26 (K order: pack.cu::tcb_src_index); the 48 columns go straight to tensor memory
         const int p = row >> 3, k = row & 7;
-        const bool live = p < np && k < K;
-        int id = -1;
-        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
-        float x = 0.f, y = 0.f, z = 0.f, dx = 0.f, dy = 0.f, dz = 0.f;
-        if (live) {
-          const int64_t n = n0 + p;
-          id = knn_idx[n * K + k];
-          g0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8));
-          g1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id * 8 + 4));
-          if (ps.xyz) {
-            x = ps.xyz[n * 3]; y = ps.xyz[n * 3 + 1]; z = ps.xyz[n * 3 + 2];
-          } else {
-            const int64_t r = n / ps.S;
-            const float t = ps.z[r * ps.zs + (n - r * ps.S)];
-            x = __fadd_rn(ps.rays_o[r * 3 + 0], __fmul_rn(ps.rays_d[r * 3 + 0], t));
-            y = __fadd_rn(ps.rays_o[r * 3 + 1], __fmul_rn(ps.rays_d[r * 3 + 1], t));
-            z = __fadd_rn(ps.rays_o[r * 3 + 2], __fmul_rn(ps.rays_d[r * 3 + 2], t));
-          }
-          if (ps.dirs) {
-            dx = ps.dirs[n * 3]; dy = ps.dirs[n * 3 + 1]; dz = ps.dirs[n * 3 + 2];
-          } else if (ps.rays_d && !ps.xyz) {
-            const int64_t r = n / ps.S;
-            dx = ps.rays_d[r * 3]; dy = ps.rays_d[r * 3 + 1]; dz = ps.rays_d[r * 3 + 2];
-          } else {  // direction=None: the nearest neighbour's own direction (model.py:391-392)
-            const int id0 = knn_idx[n * K];
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8));
-            const float4 h1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)id0 * 8 + 4));
-            dx = h0.w; dy = h1.x; dz = h1.y;
-          }
-        }
+        const bool live = nxt.live;
+        const int id = nxt.id;
+        const float4 g0 = nxt.g0, g1 = nxt.g1;
+        const float x = nxt.x, y = nxt.y, z = nxt.z, dx = nxt.dx, dy = nxt.dy, dz = nxt.dz;
         float vals[48];
         const float off[3] = {live ? __fdiv_rn(__fsub_rn(x, g0.x), range) : 0.f, live ? __fdiv_rn(__fsub_rn(y, g0.y), range) : 0.f,
                               live ? __fdiv_rn(__fsub_rn(z, g0.z), range) : 0.f};
@@ -351,10 +363,10 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
       if (prev) {
         // ---- B (tile t-1): o_h = Wv_h ctx_h ; fc + residual ------------------------------------------------------------------
         cta_sync();  // ctx complete
-        rows16_gemm<128>([&](int r, int c) { return sQT + (r * 4 + (c >> 5)) * NB_LDH; }, w.wv, 128, 128, sB,
+        rows16_gemm<128, 16, 128, 32>([&](int r, int c) { return sQT + (r * 4 + (c >> 5)) * NB_LDH; }, w.wv, 128, sB,
                          [&](int r, int c, float v) { sO[r * NB_LDH + c] = v; });
         cta_sync();
-        rows16_gemm<128>([&](int r, int) { return sO + r * NB_LDH; }, w.wfc, 128, 128, sB,
+        rows16_gemm<128, 16, 128, 32>([&](int r, int) { return sO + r * NB_LDH; }, w.wfc, 128, sB,
                          [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v + sAgg[r * NB_LDH + c]; });
       }
       cta_sync();  // sAgg of tile t-1 is dead
@@ -395,27 +407,25 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
 
       if (prev) {
         // ---- C1 (tile t-1): LayerNorm(eps 1e-6), neighbour weights, weighted sum -------------------------------------------------
-        if (tid < NB_TP) {
+        if (tid < NB_TP * 8) {
           // weights = (1/clamp(dist)) * softmax_K(corr) * conf, normalised (model.py:415-426); corr rows are identical
-          // across K, so softmax_K(corr) is exactly 1/K.
-          float wk[8], ssum = 0.f;
-          const float corr = 1.f / (float)K;
-          for (int k = 0; k < 8; ++k) {
-            float v = 0.f;
-            if (k < K) {
-              v = 1.f / fmaxf(sqrtf(sDp[tid * 8 + k]), 1e-8f);
-              v *= corr;
-              v *= sDp[128 + tid * 8 + k];
-            }
-            wk[k] = v; ssum += v;
+          // across K, so softmax_K(corr) is exactly 1/K.  One thread per (sample, neighbour), sum over the 8 lanes of a sample.
+          const int k = tid & 7;
+          float v = 0.f;
+          if (k < K) {
+            v = 1.f / fmaxf(sqrtf(sDp[tid]), 1e-8f);
+            v *= 1.f / (float)K;
+            v *= sDp[128 + tid];
           }
-          ssum = fmaxf(ssum, 1e-8f);
-          for (int k = 0; k < 8; ++k) {
-            wk[k] = wk[k] / ssum;
-            sSc[tid * 8 + k] = wk[k];
-            if (weights_out && tid < npp && k < K) weights_out[(n0p + tid) * K + k] = wk[k];
-          }
+          float ssum = v;
+          ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
+          ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
+          ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
+          const float wk = v / fmaxf(ssum, 1e-8f);
+          sSc[tid] = wk;
+          if (weights_out && (tid >> 3) < npp && k < K) weights_out[(n0p + (tid >> 3)) * K + k] = wk;
         }
+        if (stamp) g_prof[12] = clock64();
         for (int p = warp; p < NB_TP; p += NT / 32) {
           const float4 y = *reinterpret_cast<const float4*>(sQ + p * NB_LDH + lane * 4);
           const float mean = warp_sum(y.x + y.y + y.z + y.w) * (1.f / 128.f);
@@ -428,7 +438,9 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           f.x = d0 * rstd * g.x + b.x; f.y = d1 * rstd * g.y + b.y; f.z = d2 * rstd * g.z + b.z; f.w = d3 * rstd * g.w + b.w;
           *reinterpret_cast<float4*>(sO + p * NB_LDH + lane * 4) = f;
         }
+        if (stamp) g_prof[13] = clock64();
         cta_sync();
+        if (stamp) g_prof[14] = clock64();
         for (int i = tid; i < npp * W_HID; i += NT) {
           const int p = i >> 7, c = i & 127;
           const float f = sO[p * NB_LDH + c];
@@ -444,7 +456,7 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         // ---- C2 (tile t): q = Wq agg ; q~_h = Wk_h^T q_h ------------------------------------------------------------------------
         cp_async_wait<0>();
         cta_sync();  // every thread's part of the agg tile has landed
-        rows16_gemm<128>([&](int r, int) { return sAgg + r * NB_LDH; }, w.wq, 128, 128, sB,
+        rows16_gemm<128, 16, 128, 32>([&](int r, int) { return sAgg + r * NB_LDH; }, w.wq, 128, sB,
                          [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v; });
         cta_sync();
         {
@@ -481,6 +493,10 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
       }
       if (stamp) g_prof[9] = clock64();
 
+      if (it + 1 < nmy) {
+        const int64_t n0n = ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * NB_TP;
+        nxt = load_row(n0n, (int)min((int64_t)NB_TP, N - n0n));
+      }
       if (cur) {
         // ---- E3 (tile t): point features -> shared memory as plain fp32 rows (read by chunk A of the next slot) ---------------
         tc::wait_d(sy, d_par);

@@ -224,33 +224,36 @@ __device__ __forceinline__ void tile_gemm_frag(const ASrc A, const int rows, con
 // barrier per K-tile) and the 256 threads split K in 2*NT/COLS slices that are reduced through `red`
 // (>= (2*NT/COLS)*R*COLS floats of shared scratch).  Many K slices keep the number of dependent L2 round trips per thread
 // small - the loop is latency bound.  arow(r, c) -> shared-memory pointer to row r as seen by column c (c even).
-template <int COLS, int R = 16, class ARow, class Epi>
-__device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__ Wt, const int ldb, const int K, float* red,
-                                            Epi epi) {
+template <int COLS, int R, int K, int KB, class ARow, class Epi>
+__device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__ Wt, const int ldb, float* red, Epi epi) {
   constexpr int KSPLIT = 2 * NT / COLS;
+  constexpr int KPER = K / KSPLIT;                 // k per thread, multiple of 4
+  constexpr int NBATCH = (KPER + KB - 1) / KB;     // weight batches: batch n+1 is requested before the FMAs of batch n
+  static_assert(K % KSPLIT == 0 && KPER % 4 == 0 && KB % 4 == 0, "rows16_gemm: bad K split");
   const int tid = threadIdx.x;
   const int c = (tid % (COLS / 2)) * 2, ks = tid / (COLS / 2);
-  const int kper = K / KSPLIT;       // multiple of 4
-  const int k0 = ks * kper;
+  const int k0 = ks * KPER;
   float acc[R][2];
 #pragma unroll
   for (int r = 0; r < R; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
   const float* wp = Wt + (size_t)k0 * ldb + c;
-  // weight loads in flight per thread: the batch for step k+KB is requested before the FMAs of step k
-  constexpr int KB = 8;
   float2 b[KB], bn[KB];
 #pragma unroll
-  for (int j = 0; j < KB; ++j) b[j] = (j < kper) ? __ldg(reinterpret_cast<const float2*>(wp + (size_t)j * ldb)) : make_float2(0.f, 0.f);
-  for (int k = 0; k < kper; k += KB) {
+  for (int j = 0; j < KB; ++j) b[j] = (j < KPER) ? __ldg(reinterpret_cast<const float2*>(wp + (size_t)j * ldb)) : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int j = 0; j < KB; ++j)
-      bn[j] = (k + KB + j < kper) ? __ldg(reinterpret_cast<const float2*>(wp + (size_t)(k + KB + j) * ldb)) : make_float2(0.f, 0.f);
+  for (int nb = 0; nb < NBATCH; ++nb) {
+    const int k = nb * KB;
+    if (nb + 1 < NBATCH) {
+#pragma unroll
+      for (int j = 0; j < KB; ++j)
+        bn[j] = (k + KB + j < KPER) ? __ldg(reinterpret_cast<const float2*>(wp + (size_t)(k + KB + j) * ldb)) : make_float2(0.f, 0.f);
+    }
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const float* ap = arow(r, c) + k0 + k;
 #pragma unroll
       for (int g = 0; g < KB / 4; ++g) {
-        if (k + 4 * g < kper) {
+        if (k + 4 * g < KPER) {
           const float4 a = *reinterpret_cast<const float4*>(ap + 4 * g);
           fma2_s(acc[r][0], acc[r][1], a.x, b[4 * g].x, b[4 * g].y);
           fma2_s(acc[r][0], acc[r][1], a.y, b[4 * g + 1].x, b[4 * g + 1].y);
@@ -259,8 +262,10 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
         }
       }
     }
+    if (nb + 1 < NBATCH) {
 #pragma unroll
-    for (int j = 0; j < KB; ++j) b[j] = bn[j];
+      for (int j = 0; j < KB; ++j) b[j] = bn[j];
+    }
   }
   cta_sync();  // `red` may alias a buffer an earlier phase still reads
 #pragma unroll

@@ -72,8 +72,17 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int w, int h, bool
 }
 
 // row info slots
-enum { RI_FX = 0, RI_FY, RI_IX, RI_IY, RI_VX, RI_VY, RI_DEPTH, RI_VALID, RI_MASK, RI_VIS, RI_DD, RI_W,
-       RI_RD0, RI_RD1, RI_RD2, RI_RD3, RI_N };
+// per map a bilinear footprint is stored ready to use: 4 pixel indices (y * width + x, clamped into the map; as int bits) and
+// 4 weights (0 for taps that do not contribute) - computed once per row in phase 1 instead of once per lane in every gather
+enum { RI_TF = 0, RI_TI = 8, RI_TV = 16, RI_DEPTH = 24, RI_VALID, RI_MASK, RI_VIS, RI_DD, RI_W,
+       RI_RD0, RI_RD1, RI_RD2, RI_RD3, RI_N = 36 };
+
+__device__ __forceinline__ void store_taps(float* slot, const Taps& t, int w, int h) {
+  const int x0 = min(max(t.x0, 0), w - 1), x1 = min(max(t.x0 + 1, 0), w - 1);
+  const int y0 = min(max(t.y0, 0), h - 1), y1 = min(max(t.y0 + 1, 0), h - 1);
+  *reinterpret_cast<int4*>(slot) = make_int4(y0 * w + x0, y0 * w + x1, y1 * w + x0, y1 * w + x1);
+  *reinterpret_cast<float4*>(slot + 4) = make_float4(t.w[0], t.w[1], t.w[2], t.w[3]);
+}
 
 constexpr int LDF = 196;   // rgb_feat rows: 195 (+1)
 constexpr int LDH = 132;
@@ -172,10 +181,8 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           const bool inb = px <= (float)(sc.W - 1) && px >= 0.f && py <= (float)(sc.H - 1) && py >= 0.f;
           ri[RI_MASK] = (inb && ph2 > 0.f) ? 1.f : 0.f;
           const float gx = 2.f * px / (float)(sc.W - 1) - 1.f, gy = 2.f * py / (float)(sc.H - 1) - 1.f;
-          ri[RI_IX] = ((gx + 1.f) / 2.f) * (float)(sc.W - 1);
-          ri[RI_IY] = ((gy + 1.f) / 2.f) * (float)(sc.H - 1);
-          ri[RI_FX] = ((gx + 1.f) / 2.f) * (float)(sc.w - 1);
-          ri[RI_FY] = ((gy + 1.f) / 2.f) * (float)(sc.h - 1);
+          store_taps(ri + RI_TI, make_taps(((gx + 1.f) / 2.f) * (float)(sc.W - 1), ((gy + 1.f) / 2.f) * (float)(sc.H - 1), sc.W, sc.H, true), sc.W, sc.H);
+          store_taps(ri + RI_TF, make_taps(((gx + 1.f) / 2.f) * (float)(sc.w - 1), ((gy + 1.f) / 2.f) * (float)(sc.h - 1), sc.w, sc.h, true), sc.w, sc.h);
         } else if (job == 1) {
           // NeuRay convention
           const float* kr = cam + 12;
@@ -189,13 +196,15 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           ri[RI_VALID] = (!bad && !outside) ? 1.f : 0.f;
           ri[RI_DEPTH] = dep;
           const float xn = qx / (float)(sc.W - 1) * 2.f - 1.f, yn = qy / (float)(sc.H - 1) * 2.f - 1.f;
+          float vx, vy;
           if (sc.vh == sc.H && sc.vw == sc.W) {  // align_corners=True only when the map has the image size
-            ri[RI_VX] = ((xn + 1.f) / 2.f) * (float)(sc.vw - 1);
-            ri[RI_VY] = ((yn + 1.f) / 2.f) * (float)(sc.vh - 1);
+            vx = ((xn + 1.f) / 2.f) * (float)(sc.vw - 1);
+            vy = ((yn + 1.f) / 2.f) * (float)(sc.vh - 1);
           } else {
-            ri[RI_VX] = ((xn + 1.f) * (float)sc.vw - 1.f) / 2.f;
-            ri[RI_VY] = ((yn + 1.f) * (float)sc.vh - 1.f) / 2.f;
+            vx = ((xn + 1.f) * (float)sc.vw - 1.f) / 2.f;
+            vy = ((yn + 1.f) * (float)sc.vh - 1.f) / 2.f;
           }
+          store_taps(ri + RI_TV, make_taps(vx, vy, sc.vw, sc.vh, false), sc.vw, sc.vh);
         } else {
           // colour-blend ray difference (ibrnet.py:144-167) between the query camera and view v
           const float* cc = cam + 24;
@@ -232,16 +241,14 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       if (r < rows) {
         const float* ri = sRI + r * RI_N;
         const int v = r % V;
-        const Taps t = make_taps(ri[RI_VX], ri[RI_VY], sc.vw, sc.vh, false);
+        const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TV);
+        const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TV + 4);
         const float* base = sc.vis + ((size_t)v * sc.vh * sc.vw) * C_VIS + lane;
-        const int x0 = min(max(t.x0, 0), sc.vw - 1), x1 = min(max(t.x0 + 1, 0), sc.vw - 1);
-        const int y0 = min(max(t.y0, 0), sc.vh - 1), y1 = min(max(t.y0 + 1, 0), sc.vh - 1);
-        q[u][0] = __ldg(base + ((size_t)y0 * sc.vw + x0) * C_VIS);
-        q[u][1] = __ldg(base + ((size_t)y0 * sc.vw + x1) * C_VIS);
-        q[u][2] = __ldg(base + ((size_t)y1 * sc.vw + x0) * C_VIS);
-        q[u][3] = __ldg(base + ((size_t)y1 * sc.vw + x1) * C_VIS);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) wgt[u][k] = t.w[k];
+        q[u][0] = __ldg(base + (size_t)ti.x * C_VIS);
+        q[u][1] = __ldg(base + (size_t)ti.y * C_VIS);
+        q[u][2] = __ldg(base + (size_t)ti.z * C_VIS);
+        q[u][3] = __ldg(base + (size_t)ti.w * C_VIS);
+        wgt[u][0] = tw.x; wgt[u][1] = tw.y; wgt[u][2] = tw.z; wgt[u][3] = tw.w;
         valid[u] = ri[RI_VALID];
       }
     }
@@ -386,15 +393,14 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       if (r < rows) {
         const float* ri = sRI + r * RI_N;
         const int v = r % V;
-        const Taps tf = make_taps(ri[RI_FX], ri[RI_FY], sc.w, sc.h, true);
+        const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TF);
+        const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TF + 4);
         const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
-        const int fx0 = min(max(tf.x0, 0), sc.w - 1), fx1 = min(max(tf.x0 + 1, 0), sc.w - 1);
-        const int fy0 = min(max(tf.y0, 0), sc.h - 1), fy1 = min(max(tf.y0 + 1, 0), sc.h - 1);
-        const float* tp[4] = {fb + ((size_t)fy0 * sc.w + fx0) * C_FEAT, fb + ((size_t)fy0 * sc.w + fx1) * C_FEAT,
-                              fb + ((size_t)fy1 * sc.w + fx0) * C_FEAT, fb + ((size_t)fy1 * sc.w + fx1) * C_FEAT};
+        const float* tp[4] = {fb + (size_t)ti.x * C_FEAT, fb + (size_t)ti.y * C_FEAT, fb + (size_t)ti.z * C_FEAT, fb + (size_t)ti.w * C_FEAT};
+        const float twv[4] = {tw.x, tw.y, tw.z, tw.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          wt[u][t] = tf.w[t];
+          wt[u][t] = twv[t];
 #pragma unroll
           for (int j = 0; j < 3; ++j) q[u][t][j] = __ldg(reinterpret_cast<const float2*>(tp[t] + j * 64));
         }
@@ -444,23 +450,23 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         if (r < rows) {
           const float* ri = sRI + r * RI_N;
           const int v = r % V;
-          const Taps ti = make_taps(ri[RI_IX], ri[RI_IY], sc.W, sc.H, true);
-          if (lane < 4 && ti.w[lane] != 0.f) {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(
-                sc.images + (((size_t)v * sc.H + ti.y0 + (lane >> 1)) * sc.W + ti.x0 + (lane & 1)) * 4));
-            cq[u] = make_float4(q.x * ti.w[lane], q.y * ti.w[lane], q.z * ti.w[lane], 0.f);
+          if (lane < 4) {
+            const float wi = ri[RI_TI + 4 + lane];
+            if (wi != 0.f) {
+              const int pix = __float_as_int(ri[RI_TI + lane]);
+              const float4 q = __ldg(reinterpret_cast<const float4*>(sc.images + ((size_t)v * sc.H * sc.W + pix) * 4));
+              cq[u] = make_float4(q.x * wi, q.y * wi, q.z * wi, 0.f);
+            }
           }
           if (with_blend) {
-            const Taps tf = make_taps(ri[RI_FX], ri[RI_FY], sc.w, sc.h, true);
+            const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TF);
+            const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TF + 4);
             const float* bb = sc.featb + ((size_t)v * sc.h * sc.w) * 32 + lane;
-            const int fx0 = min(max(tf.x0, 0), sc.w - 1), fx1 = min(max(tf.x0 + 1, 0), sc.w - 1);
-            const int fy0 = min(max(tf.y0, 0), sc.h - 1), fy1 = min(max(tf.y0 + 1, 0), sc.h - 1);
-            bq[u][0] = __ldg(bb + ((size_t)fy0 * sc.w + fx0) * 32);
-            bq[u][1] = __ldg(bb + ((size_t)fy0 * sc.w + fx1) * 32);
-            bq[u][2] = __ldg(bb + ((size_t)fy1 * sc.w + fx0) * 32);
-            bq[u][3] = __ldg(bb + ((size_t)fy1 * sc.w + fx1) * 32);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) bw[u][t] = tf.w[t];
+            bq[u][0] = __ldg(bb + (size_t)ti.x * 32);
+            bq[u][1] = __ldg(bb + (size_t)ti.y * 32);
+            bq[u][2] = __ldg(bb + (size_t)ti.z * 32);
+            bq[u][3] = __ldg(bb + (size_t)ti.w * 32);
+            bw[u][0] = tw.x; bw[u][1] = tw.y; bw[u][2] = tw.z; bw[u][3] = tw.w;
           }
         }
       }
@@ -512,10 +518,10 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   AGG_STAMP(7);
   // ---- phase 7: out_fc 393 -> 64 -> 128 (ELU) --------------------------------------------------------------------
   cta_sync();  // sG complete
-  rows16_gemm<64, TP_MAX>([&](int r, int) { return sG + r * LDG; }, w.fc1, 64, 416, sB,
+  rows16_gemm<64, TP_MAX, 416, 8>([&](int r, int) { return sG + r * LDG; }, w.fc1, 64, sB,
                   [&](int r, int c, float v) { sO1[r * 68 + c] = elu(v + __ldg(w.fc1_b + c)); });
   cta_sync();
-  rows16_gemm<128, TP_MAX>([&](int r, int) { return sO1 + r * 68; }, w.fc2, 128, 64, sB, [&](int r, int c, float v) {
+  rows16_gemm<128, TP_MAX, 64, 8>([&](int r, int) { return sO1 + r * 68; }, w.fc2, 128, sB, [&](int r, int c, float v) {
     if (r < np) agg_out[(n0 + r) * W_HID + c] = elu(v + __ldg(w.fc2_b + c));
   });
 

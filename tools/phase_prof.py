@@ -25,6 +25,7 @@ names = ["P0(t): PE, rd_fc, A1 -> TMEM", "A(t-1): scores, softmax, ctx", "wait L
 for i in range(11):
     print(f"{names[i]:36s} {v[i+1]-v[i]:8d} clk")
 print("slot total", v[11] - v[0])
+print("C1 detail: weights", v[12]-v[7], "LN", v[13]-v[12], "barrier", v[14]-v[13], "out", v[8]-v[14])
 
 an = ["proj", "vis gather", "decoder GEMMs+heads", "view weights", "rgb/feat gather", "blend partial", "mean/var", "out_fc"]
 for i in range(8):
