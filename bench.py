@@ -31,7 +31,7 @@ F_KERNEL = {"aggregate": 201e3 + 176e3 * V / 8, "neighbor": 1108e3 + 1081e3 + 26
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes;
 # None until a capture of the current build exists
-TRAFFIC = {"aggregate": 4.06e9, "ray": 4.07e9, "knn": 0.18e9}  # profiles/r1d_ncu_metrics.json, per launch of 18,944 rays
+TRAFFIC = {"aggregate": 4.13e9, "neighbor": 2.64e9, "ray": 4.08e9, "knn": 0.18e9}  # profiles/r1f_ncu_metrics.json, per launch of 18,944 rays
 
 
 def peaks():
@@ -336,7 +336,7 @@ def run_b200(args):
         "config": {"workload": "640x480 query, 128 samples/ray, 8 ref views, full conditional render (configs[1])",
                    "rays_per_step": R_total, "samples_per_ray": S, "views": V, "support_points": int(model.support_neural_points["fine"]["xyz"].shape[0]),
                    "chunk_rays": args.chunk,
-                   "mma_mode": "3xTF32 tcgen05 (neighbour MLP, RayUnet, feat/blend layers) + fp32 FFMA (aggregator, small per-sample GEMMs)",
+                   "mma_mode": "3xTF32 tcgen05 (neighbour MLP with the A operand in tensor memory, RayUnet, feat/blend layers) + fp32 FFMA2 (aggregator, small per-sample GEMMs)",
                    "l2": "working set per step (scene 294 MB + >1 GB of per-chunk intermediates) exceeds the 126 MB L2",
                    "parallelism": f"ray-shard x{world}" + (" + NCCL all-gather of feat[R,192]" if world > 1 else ""),
                    "per_frame_setup_ms": setup_ms},
