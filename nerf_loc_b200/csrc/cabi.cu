@@ -75,6 +75,19 @@ struct Prof {
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+// one low-priority non-blocking stream per host thread and device, created on first use and kept for the process lifetime
+static cudaStream_t side_stream() {
+  static thread_local cudaStream_t s[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+  if (!s[dev]) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = numerically largest = lowest priority
+    if (cudaStreamCreateWithPriority(&s[dev], cudaStreamNonBlocking, lo) != cudaSuccess) { s[dev] = nullptr; cudaGetLastError(); }
+  }
+  return s[dev];
+}
+
 struct Carver {
   char* p;
   size_t left;
@@ -196,7 +209,8 @@ int nlb_confidence_head(const float* packed_weights, int S, const float* aggrega
 size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
   const size_t n = (size_t)(chunk_rays < 1 ? 1 : chunk_rays) * S;
   const size_t slabs = S > 128 ? align256((size_t)RL_MAX_GRID * ray_long_slab_floats(S) * 4) : 0;
-  return align256(n * KNN_K * 4) * 2 + align256(n * W_HID * 4) * 2 + align256(n * V * 32 * 4) + align256(n * V * 16) +
+  // KNN lists are double buffered: the search of chunk i+1 runs on a side stream underneath the ray kernel of chunk i
+  return align256(n * KNN_K * 4) * 4 + align256(n * W_HID * 4) * 2 + align256(n * V * 32 * 4) + align256(n * V * 16) +
          align256(n) + slabs + 2048;
 }
 
@@ -223,8 +237,9 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
   const int V = scene->V;
   const size_t n = (size_t)chunk_rays * S;
   Carver c{(char*)scratch, scratch_bytes};
-  int* idx = c.take<int>(n * KNN_K);
-  float* d2 = c.take<float>(n * KNN_K);
+  int* idx2[2];
+  float* d22[2];
+  for (int b = 0; b < 2; ++b) { idx2[b] = c.take<int>(n * KNN_K); d22[b] = c.take<float>(n * KNN_K); }
   float* agg = c.take<float>(n * W_HID);
   float* fagg = c.take<float>(n * W_HID);
   float* partial = c.take<float>(n * V * 32);
@@ -234,8 +249,36 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
   if (!c.ok) return set_error("nlb_render_rays: scratch too small (see nlb_render_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
+  const int64_t nchunks = (R + chunk_rays - 1) / chunk_rays;
+  // The exact KNN search is a register-light, shared-memory-free tree walk; the ray kernel is one latency-bound CTA per SM that
+  // leaves a third of the register file idle.  With more than one chunk the search of chunk i+1 therefore runs on a
+  // low-priority side stream underneath the ray kernel of chunk i (events order it after neighbor(i), which frees the buffer
+  // pair it writes, and before neighbor(i+1), which reads it).  Profiling mode keeps everything on the caller's stream.
+  const bool overlap = !g_prof_on && nchunks > 1;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_knn[2] = {nullptr, nullptr}, ev_nb = nullptr;
+  if (overlap) {
+    side = side_stream();
+    if (!side) return set_error("nlb_render_rays: could not create the side stream");
+    for (auto& e : ev_knn) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_nb, cudaEventDisableTiming);
+    cudaEventRecord(ev_nb, st);            // everything the caller queued before this call (scene, rays) is visible to the side stream
+    cudaStreamWaitEvent(side, ev_nb, 0);
+  }
+  auto knn_chunk = [&](int64_t i, cudaStream_t s) {
+    const int64_t r0 = i * chunk_rays;
+    const int64_t rc = (R - r0) < chunk_rays ? (R - r0) : chunk_rays;
+    return knn_query_rays(sc.knn, rays_o + r0 * 3, rays_d + r0 * 3, z_vals + r0 * z_stride, z_stride, sc.sup_geo, rc, S,
+                          idx2[i & 1], d22[i & 1], s);
+  };
+  int rc_err = 0;
+  if (overlap) {
+    rc_err = knn_chunk(0, side);
+    cudaEventRecord(ev_knn[0], side);
+  }
   Prof prof(st);
-  for (int64_t r0 = 0; r0 < R; r0 += chunk_rays) {
+  for (int64_t i = 0; i < nchunks && !rc_err; ++i) {
+    const int64_t r0 = i * chunk_rays;
     const int64_t rc = (R - r0) < chunk_rays ? (R - r0) : chunk_rays;
     const int64_t nc = rc * S;
     const float* ro = rays_o + r0 * 3;
@@ -243,27 +286,42 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
     const float* zc = z_vals + r0 * z_stride;
     PointSrc ps{nullptr, nullptr, ro, rd, zc, S, z_stride};
     float* fa = dbg_feature_agg ? dbg_feature_agg + r0 * S * W_HID : fagg;
+    int* idx = idx2[i & 1];
+    float* d2 = d22[i & 1];
     prof.mark();
-    if (knn_query_rays(sc.knn, ro, rd, zc, z_stride, sc.sup_geo, rc, S, idx, d2, st)) return 1;
+    if (!overlap && knn_chunk(i, st)) { rc_err = 1; break; }
     prof.mark();
-    if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, st)) return 1;
+    if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, st)) { rc_err = 1; break; }
     prof.mark();
-    if (launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)) return 1;
+    if (overlap) cudaStreamWaitEvent(st, ev_knn[i & 1], 0);
+    if (launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)) { rc_err = 1; break; }
+    if (overlap) cudaEventRecord(ev_nb, st);
     prof.mark();
     if (S <= 128) {
       if (launch_ray(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                      weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
-                     dbg_sigma ? dbg_sigma + r0 * S : nullptr, st))
-        return 1;
+                     dbg_sigma ? dbg_sigma + r0 * S : nullptr, st)) { rc_err = 1; break; }
     } else if (launch_ray_long(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                                weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
                                dbg_sigma ? dbg_sigma + r0 * S : nullptr, slabs, st)) {
-      return 1;
+      rc_err = 1; break;
+    }
+    if (overlap && i + 1 < nchunks) {
+      // queued after the ray kernel so that its CTAs are placed first; the search fills the registers they leave
+      cudaStreamWaitEvent(side, ev_nb, 0);
+      if (knn_chunk(i + 1, side)) { rc_err = 1; break; }
+      cudaEventRecord(ev_knn[(i + 1) & 1], side);
     }
     prof.mark();
     prof.flush(4);
   }
-  return 0;
+  if (overlap) {
+    // on an error path the side stream may still hold work the caller's stream has not been ordered after
+    if (rc_err) { cudaEventRecord(ev_knn[0], side); cudaStreamWaitEvent(st, ev_knn[0], 0); }
+    for (auto& e : ev_knn) cudaEventDestroy(e);
+    cudaEventDestroy(ev_nb);
+  }
+  return rc_err;
 }
 
 int nlb_hierarchical_depths(const nlb_scene* scene, const float* packed_weights, int S_total, const float* center,

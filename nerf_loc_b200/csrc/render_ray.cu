@@ -207,7 +207,9 @@ __device__ __forceinline__ void load_x(unsigned char* sm, const float* __restric
   }
 }
 
-__global__ void __launch_bounds__(NT + 64, 1)
+// 128 registers (not the 204 a 320-thread CTA could have): a third of the register file stays free for the KNN search of the
+// next chunk, which nlb_render_rays runs underneath this kernel on a side stream
+__global__ void __maxnreg__(128)
 ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals, const int64_t zs, const int S, const int white_bkgd,
            const float* __restrict__ fagg, const float* __restrict__ partial, const float* __restrict__ rgbvis,
            const unsigned char* __restrict__ nvalid, float* __restrict__ rgb_out, float* __restrict__ depth_out,
