@@ -64,28 +64,33 @@ int match_weights_pack(const float* const* p, int n_params, int C, float* packed
 }
 
 // ---- S2D scores -----------------------------------------------------------------------------------------------------
+// A CTA owns S2D_ROWS = 64 cells of the 2D map and walks a slice of the 3D points; two CTAs share an SM (109 KB of shared
+// memory and <= 128 registers each), so the barrier / staging stalls of one overlap the FFMA2 stream of the other (with one
+// 128-cell CTA per SM the kernel sat at 50 % of the fp32 pipe).
 constexpr int LDD = 196;  // 192 + 4
 constexpr int LDH2 = 132;
-constexpr int S2D_SMEM_FLOATS = STAGE_FLOATS + 128 * LDD + 128 * LDH2 + 192 + 64;
+constexpr int S2D_ROWS = 64;
+constexpr int S2D_NS = 3;  // weight staging slots (8 KB each)
+constexpr int S2D_SMEM_FLOATS = S2D_NS * KT * 128 + S2D_ROWS * LDD + S2D_ROWS * LDH2 + 192 + 64;
 
 // second layer + 128->1 head on a hidden tile held in shared memory; returns the logit of row r0+i in lane tc==0
-template <class Out>
-__device__ __forceinline__ void pair_tail(const PairMlp& m, const float* sH, float* sB, Out out) {
-  Frag<8, 8, 128> f;
-  tile_gemm_frag<8, 8, 128>(plainA(sH, LDH2), 128, m.w2t, 128, 128, sB, f);
-  float part[8];
+template <int TM, int NS, class Out>
+__device__ __forceinline__ void pair_tail(const PairMlp& m, const float* sH, const int rows, float* sB, Out out) {
+  Frag<TM, 8, 128> f;
+  tile_gemm_frag<TM, 8, 128, false, NS>(plainA(sH, LDH2), rows, m.w2t, 128, 128, sB, f);
+  float part[TM];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) part[i] = 0.f;
+  for (int i = 0; i < TM; ++i) part[i] = 0.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int c = f.col(j);
     const float b = __ldg(m.b2 + c), w3 = __ldg(m.w3 + c);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) part[i] = fmaf(fmaxf(f.acc[i][j] + b, 0.f), w3, part[i]);
+    for (int i = 0; i < TM; ++i) part[i] = fmaf(fmaxf(f.acc[i][j] + b, 0.f), w3, part[i]);
   }
   const float b3 = __ldg(m.b3);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < TM; ++i) {
     float v = part[i];
     v += __shfl_xor_sync(0xffffffffu, v, 8);
     v += __shfl_xor_sync(0xffffffffu, v, 4);
@@ -95,18 +100,19 @@ __device__ __forceinline__ void pair_tail(const PairMlp& m, const float* sH, flo
   }
 }
 
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 s2d_kernel(const PairMlp m, const float* __restrict__ desc0, const float* __restrict__ desc1, const int64_t N,
            const int64_t M, const int n_per_cta, float* __restrict__ score) {
   extern __shared__ __align__(16) float smem[];
+  constexpr int TM = S2D_ROWS / 16;
   float* sB = smem;
-  float* sD = sB + STAGE_FLOATS;   // [128][LDD] cell descriptors
-  float* sH = sD + 128 * LDD;      // [128][LDH2]
-  float* sAn = sH + 128 * LDH2;    // [192]
+  float* sD = sB + S2D_NS * KT * 128;   // [S2D_ROWS][LDD] cell descriptors
+  float* sH = sD + S2D_ROWS * LDD;      // [S2D_ROWS][LDH2]
+  float* sAn = sH + S2D_ROWS * LDH2;    // [192]
   const int tid = threadIdx.x;
-  const int64_t m0 = (int64_t)blockIdx.x * 128;
-  const int mr = (int)min((int64_t)128, M - m0);
-  for (int i = tid; i < 128 * 48; i += NT) {
+  const int64_t m0 = (int64_t)blockIdx.x * S2D_ROWS;
+  const int mr = (int)min((int64_t)S2D_ROWS, M - m0);
+  for (int i = tid; i < S2D_ROWS * 48; i += NT) {
     const int r = i / 48, c4 = i % 48;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < mr) v = __ldg(reinterpret_cast<const float4*>(desc1 + (m0 + r) * 192 + c4 * 4));
@@ -118,17 +124,17 @@ s2d_kernel(const PairMlp m, const float* __restrict__ desc0, const float* __rest
     __syncthreads();  // previous iteration is done with sAn / sH
     if (tid < 192) sAn[tid] = __ldg(desc0 + n * 192 + tid);
     {
-      Frag<8, 8, 128> f;
-      tile_gemm_frag<8, 8, 128, true>(plainA(sD, LDD), 128, m.w1t, 128, 192, sB, f, sAn);
+      Frag<TM, 8, 128> f;
+      tile_gemm_frag<TM, 8, 128, true, S2D_NS>(plainA(sD, LDD), S2D_ROWS, m.w1t, 128, 192, sB, f, sAn);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int c = f.col(j);
         const float b = __ldg(m.b1 + c);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) sH[(f.r0 + i) * LDH2 + c] = fmaxf(f.acc[i][j] + b, 0.f);
+        for (int i = 0; i < TM; ++i) sH[(f.r0 + i) * LDH2 + c] = fmaxf(f.acc[i][j] + b, 0.f);
       }
     }
-    pair_tail(m, sH, sB, [&](int r, float logit) {
+    pair_tail<TM, S2D_NS>(m, sH, S2D_ROWS, sB, [&](int r, float logit) {
       if (r < mr) score[n * M + m0 + r] = 1.f / (1.f + expf(-logit));
     });
   }
@@ -139,9 +145,9 @@ int launch_s2d(const MatchW& w, const float* desc0, const float* desc1, int64_t 
   const size_t smem = S2D_SMEM_FLOATS * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-  const unsigned gx = (unsigned)((M + 127) / 128);
-  // aim for ~4 waves of 148 CTAs
-  int64_t gy = (592 + gx - 1) / gx;
+  const unsigned gx = (unsigned)((M + S2D_ROWS - 1) / S2D_ROWS);
+  // aim for ~4 waves of 296 resident CTAs
+  int64_t gy = (1184 + gx - 1) / gx;
   if (gy > N) gy = N;
   if (gy < 1) gy = 1;
   const int n_per = (int)((N + gy - 1) / gy);
@@ -301,7 +307,7 @@ fine_match_kernel(const PairMlp m, const float* __restrict__ f0, const float* __
   }
   tile_gemm<8, 8, 128, false>(plainA(sX, LDD), 128, m.w1t, 128, 192, sB,
                               [&](int r, int c, float v) { sH[r * LDH2 + c] = fmaxf(v + __ldg(m.b1 + c), 0.f); });
-  pair_tail(m, sH, sB, [&](int r, float logit) { sL[r] = logit; });
+  pair_tail<8, NSTG>(m, sH, 128, sB, [&](int r, float logit) { sL[r] = logit; });
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
   if (warp < 2 && t0 + warp < Mm) {

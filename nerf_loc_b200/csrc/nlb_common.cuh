@@ -85,7 +85,7 @@ __device__ __forceinline__ ASrc plainA(const float* base, int ld) { return ASrc{
 //   sB: shared staging, 2*KT*COLS floats.
 //   kscale (SCALE only): shared/global array of K factors; staged row k of Wt is multiplied by kscale[k] by the
 //   thread that copied it, i.e. the GEMM computes A * (diag(kscale) Wt) - the S2D "fold a_n into layer 1" form.
-template <int TM, int TN, int COLS, bool SCALE>
+template <int TM, int TN, int COLS, bool SCALE, int NS = NSTG>
 __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const bool active, const float* __restrict__ Wt,
                                           const int ldb, const int K, float* sB, const float* kscale,
                                           float (&acc)[TM][TN]) {
@@ -106,7 +106,7 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
 
   auto stage_load = [&](int kt) {
     if (kt < nkt) {
-      float* dst = sB + (kt % NSTG) * STG;
+      float* dst = sB + (kt % NS) * STG;
       const float* src = Wt + (size_t)kt * KT * ldb;
       for (int c = tid; c < CHUNKS; c += NT) {
         const int k = c / (COLS / 4), n4 = c % (COLS / 4);
@@ -118,12 +118,12 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
 
   cta_sync();  // previous users of sB (and producers of A) are done
 #pragma unroll
-  for (int i = 0; i < NSTG - 1; ++i) stage_load(i);
+  for (int i = 0; i < NS - 1; ++i) stage_load(i);
 
   for (int kt = 0; kt < nkt; ++kt) {
-    cp_async_wait<NSTG - 2>();  // tile kt has landed (this thread's part)
+    cp_async_wait<NS - 2>();  // tile kt has landed (this thread's part)
     if (SCALE) {
-      float* cur = sB + (kt % NSTG) * STG;
+      float* cur = sB + (kt % NS) * STG;
       for (int c = tid; c < CHUNKS; c += NT) {
         const int k = c / (COLS / 4), n4 = c % (COLS / 4);
         const float sc = kscale[kt * KT + k];
@@ -134,13 +134,13 @@ __device__ __forceinline__ void gemm_core(const ASrc& A, const int r0, const boo
       }
     }
     cta_sync();                  // everybody's part of tile kt is visible; tile kt-1's slot is free
-    stage_load(kt + NSTG - 1);   // refill the slot tile kt-1 used
+    stage_load(kt + NS - 1);   // refill the slot tile kt-1 used
     if (active) {
       const int k0 = kt * KT;
       const int tap = k0 / A.cin;
       const int roff = tap == 0 ? A.off0 : (tap == 1 ? A.off1 : A.off2);
       const float* arow = A.base + (r0 + roff) * A.ld + (k0 - tap * A.cin);
-      const float* bt = sB + (kt % NSTG) * STG + tc * 4;
+      const float* bt = sB + (kt % NS) * STG + tc * 4;
 #pragma unroll
       for (int kk = 0; kk < KT; kk += 4) {
         float4 a[TM];
@@ -208,14 +208,14 @@ struct Frag {
   __device__ __forceinline__ int col(int j) const { return (j / 4) * GSTRIDE + (threadIdx.x % TC) * 4 + (j % 4); }
 };
 
-template <int TM, int TN, int COLS, bool SCALE = false>
+template <int TM, int TN, int COLS, bool SCALE = false, int NS = NSTG>
 __device__ __forceinline__ void tile_gemm_frag(const ASrc A, const int rows, const float* __restrict__ Wt, const int ldb,
                                                const int K, float* sB, Frag<TM, TN, COLS>& f,
                                                const float* kscale = nullptr) {
   constexpr int TC = COLS / TN;
   f.r0 = (threadIdx.x / TC) * TM;
   f.active = f.r0 < rows;
-  gemm_core<TM, TN, COLS, SCALE>(A, f.r0, f.active, Wt, ldb, K, sB, kscale, f.acc);
+  gemm_core<TM, TN, COLS, SCALE, NS>(A, f.r0, f.active, Wt, ldb, K, sB, kscale, f.acc);
 }
 
 // Small-M GEMM: out[r][c] = sum_k A_r[k] * Wt[k*ldb + c] for r < R (<= 16), c < COLS.  A tile GEMM would give every thread one
