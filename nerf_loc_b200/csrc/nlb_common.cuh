@@ -50,6 +50,11 @@ __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x
 __device__ __forceinline__ float elu(float x) { return x > 0.f ? x : __expf(x) - 1.f; }
 __device__ __forceinline__ float softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoidf(float x) { return 1.f / (1.f + expf(-x)); }
+// Hardware-exponential variants for the visibility decoder's output activations (64 rows x 8 transcendentals per tile sit on
+// a short serial path): absolute error ~1e-7 on outputs of order 1, two orders below what the 1e-4 parity bar needs.
+__device__ __forceinline__ float softplus_fast(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - __fdividef(2.f, 1.f + __expf(2.f * x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

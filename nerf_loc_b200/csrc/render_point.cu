@@ -329,50 +329,85 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       a0 = fmaf(w4.x, h4.x, a0); a1 = fmaf(w4.y, h4.y, a1); a2 = fmaf(w4.z, h4.z, a2); a3 = fmaf(w4.w, h4.w, a3);
     }
     const float o = ((a0 + a1) + (a2 + a3)) + __ldg(w.dec3_b + j);
-    sO1[i] = j < 2 ? softplus(o) : (j < 4 ? softplus(o) + 0.05f : sigmoidf(o));
+    sO1[i] = j < 2 ? softplus_fast(o) : (j < 4 ? softplus_fast(o) + 0.05f : sigmoid_fast(o));
   }
   cta_sync();
-  if (tid < rows) {
+  const bool fused_w = V == 8;   // rows of a sample are 8 consecutive lanes: the view weights follow in the same threads
+  if (tid < ROWS && (fused_w || tid < rows)) {
     const float m0 = sO1[tid * 6], m1 = sO1[tid * 6 + 1], v0 = sO1[tid * 6 + 2], v1 = sO1[tid * 6 + 3];
     const float aw = sO1[tid * 6 + 4], vs = sO1[tid * 6 + 5];
     float* ri = sRI + tid * RI_N;
+    const bool live = tid < rows;
     const float dep = ri[RI_DEPTH];
     const float near_inv = -1.f / near_, far_inv = -1.f / far_;
     float refd = -1.f / (m0 * (far_inv - near_inv) + near_inv);
     refd = fminf(fmaxf(refd, near_), far_);
-    ri[RI_DD] = fabsf(dep - refd) / (far_ - near_);
+    const float dd = live ? fabsf(dep - refd) / (far_ - near_) : 0.f;
     const float dn = (-1.f / fmaxf(dep, 1e-5f) - near_inv) / (far_inv - near_inv);
-    const float cdf0 = (0.5f + 0.5f * tanhf((dn - m0) * v0)) * vs;
-    const float cdf1 = (0.5f + 0.5f * tanhf((dn - m1) * v1)) * vs;
-    const float vis = (1.f - cdf0) * aw + (1.f - cdf1) * (1.f - aw);
-    ri[RI_VIS] = vis * ri[RI_VALID];
-    if (mvv_out) mvv_out[n0 * V + tid] = ri[RI_VIS];
-  }
-  cta_sync();
-
-  AGG_STAMP(3);
-  // ---- phase 4: per-sample view weights --------------------------------------------------------------------------
-  for (int p = warp; p < np; p += NT / 32) {
-    // one warp per sample, lane = view
-    const bool on = lane < V;
-    float* ri = sRI + (p * V + (on ? lane : 0)) * RI_N;
-    const float vis = on ? ri[RI_VIS] : 0.f, dd = on ? ri[RI_DD] : 0.f;
-    const float den = warp_sum(vis) + 1e-8f;
-    const float wv = vis / den;
-    if (on) ri[RI_W] = wv;
-    const float ddm = warp_sum(dd * wv);
-    const float wsum = warp_sum(wv);
-    const unsigned nval = __popc(__ballot_sync(0xffffffffu, on && ri[RI_MASK] != 0.f));
-    const float d = dd - ddm;
-    const float ddv = warp_sum(wv * (d * d));
-    float* g = sG + p * LDG;
-    if (lane == 0) {
-      g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
-      if (nvalid_out) nvalid_out[n0 + p] = (unsigned char)nval;
+    const float cdf0 = (0.5f + 0.5f * tanh_fast((dn - m0) * v0)) * vs;
+    const float cdf1 = (0.5f + 0.5f * tanh_fast((dn - m1) * v1)) * vs;
+    const float vis = live ? ((1.f - cdf0) * aw + (1.f - cdf1) * (1.f - aw)) * ri[RI_VALID] : 0.f;
+    if (live) {
+      ri[RI_DD] = dd;
+      ri[RI_VIS] = vis;
+      if (mvv_out) mvv_out[n0 * V + tid] = vis;
     }
-    if (lane < 23) g[393 + lane] = 0.f;
+    if (fused_w) {
+      // ---- phase 4 fused (V == 8): per-sample view weights over the 8 lanes of a sample (same summation tree as warp_sum) --
+      auto sum8 = [](float v) {
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        return v;
+      };
+      const int p = tid >> 3, v = tid & 7;
+      const float den = sum8(vis) + 1e-8f;
+      const float wv = vis / den;
+      const float ddm = sum8(dd * wv);
+      const float wsum = sum8(wv);
+      const unsigned bal = __ballot_sync(0xffffffffu, live && ri[RI_MASK] != 0.f);
+      const unsigned nval = __popc((bal >> (8 * (lane >> 3))) & 0xffu);
+      const float d = dd - ddm;
+      const float ddv = sum8(wv * (d * d));
+      if (live) {
+        ri[RI_W] = wv;
+        float* g = sG + p * LDG;
+        if (v == 0) {
+          g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
+          if (nvalid_out) nvalid_out[n0 + p] = (unsigned char)nval;
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (v * 3 + j < 23) g[393 + v * 3 + j] = 0.f;
+      }
+    }
   }
-  cta_sync();  // sH (arena) is dead from here on
+  if (!fused_w) {
+    cta_sync();
+    // ---- phase 4: per-sample view weights ------------------------------------------------------------------------
+    for (int p = warp; p < np; p += NT / 32) {
+      // one warp per sample, lane = view
+      const bool on = lane < V;
+      float* ri = sRI + (p * V + (on ? lane : 0)) * RI_N;
+      const float vis = on ? ri[RI_VIS] : 0.f, dd = on ? ri[RI_DD] : 0.f;
+      const float den = warp_sum(vis) + 1e-8f;
+      const float wv = vis / den;
+      if (on) ri[RI_W] = wv;
+      const float ddm = warp_sum(dd * wv);
+      const float wsum = warp_sum(wv);
+      const unsigned nval = __popc(__ballot_sync(0xffffffffu, on && ri[RI_MASK] != 0.f));
+      const float d = dd - ddm;
+      const float ddv = warp_sum(wv * (d * d));
+      float* g = sG + p * LDG;
+      if (lane == 0) {
+        g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
+        if (nvalid_out) nvalid_out[n0 + p] = (unsigned char)nval;
+      }
+      if (lane < 23) g[393 + lane] = 0.f;
+    }
+  }
+  AGG_STAMP(3);
+  cta_sync();  // sH (arena) is dead from here on; view weights visible
 
   AGG_STAMP(4);
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
