@@ -208,3 +208,38 @@ def test_hierarchical_sampling_vs_oracle():
     for k, v in report.items():
         assert v < TOL, (k, report)
     assert torch.equal(out["mask"].cpu(), ref["mask"])
+
+
+def test_blend_prepare_is_the_linear_projection():
+    """nlb_blend_prepare: the map-feature columns of rgb_blending_mlp.0 (model.py:90-96,532-535) applied per pixel; the
+    render kernels rely on W f(x) = sum_t b_t (W f_t) for the bilinear fetch f(x)."""
+    import ctypes
+    from nerf_loc_b200 import _lib
+    model, sd = cuda_model(16, 5)
+    L = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    feat = torch.randn(1000, 192, generator=g).cuda()
+    out = torch.empty(1000, 32, device="cuda")
+    _lib.check(L.nlb_blend_prepare(_lib.ptr(model.packed_weights()), model.n_samples, _lib.ptr(feat), 1000, _lib.ptr(out),
+                                   _lib.stream()))
+    torch.cuda.synchronize()
+    W = sd["rgb_blending_mlp.0.weight"].double()          # [32, 128 + 195 + 1 + 4]
+    ref = feat.double().cpu() @ W[:, 128 + 3:128 + 195].t()
+    assert relerr(out.cpu().double(), ref) < 1e-6
+
+
+def test_render_edge_cases_empty_and_ragged():
+    """R = 0 returns empty outputs; a ray count that is not a multiple of any tile size (neighbour tiles of 16 samples, chunks)
+    gives the same rays as the full batch."""
+    name = list(RENDER_CASES)[0]
+    S, sd_cpu, sc, scene, ro, rd = render_inputs(name)
+    model, sd = cuda_model(S, RENDER_CASES[name][5])
+    data = setup_frame(model, sc)
+    full = model.render_rays(data, {"rays_o": ro.cuda(), "rays_d": rd.cuda(), "depth_range": data["depth_range"][0]})
+    n = 13
+    part = model.render_rays(data, {"rays_o": ro[:n].cuda(), "rays_d": rd[:n].cuda(), "depth_range": data["depth_range"][0]})
+    for k in ("rgb", "depth", "weights", "feat", "depth_uncertainty"):
+        assert torch.equal(part[k], full[k][:n]), k
+    assert torch.equal(part["mask"], full["mask"][:n])
+    empty = model.render_rays(data, {"rays_o": ro[:0].cuda(), "rays_d": rd[:0].cuda(), "depth_range": data["depth_range"][0]})
+    assert empty["rgb"].shape[0] == 0 and empty["weights"].shape == (0, S)
