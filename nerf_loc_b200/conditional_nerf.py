@@ -452,7 +452,9 @@ class ConditionalNeRF(nn.Module):
         feat = torch.empty(R, 192, device=dev) if self.args.render.render_feature else None
         dbg_fa = torch.empty(R * S, 128, device=dev) if _debug else None
         dbg_sig = torch.empty(R * S, device=dev) if _debug else None
-        chunk = min(self.chunk_rays, R)
+        # equal chunks (a multiple of the SM count) instead of full chunks plus a small remainder
+        n_chunks = max(1, -(-R // self.chunk_rays))
+        chunk = min(self.chunk_rays, max(1, -(-(-(-R // n_chunks)) // 148) * 148))
         nb = L.nlb_render_scratch_bytes(chunk, S, maps.V)
         key = ("scratch", nb)
         if key not in self._frame:
