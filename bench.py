@@ -6,7 +6,8 @@
 
 A step = one pass of `ConditionalNeRF.render_rays` over every pixel ray of the synthetic 640x480 query frame
 (configs[1]).  With N GPUs the rays of the SAME frame are split into N contiguous slices (strong scaling) and the
-rendered per-ray features are all-gathered once per step over NCCL, as the matcher would need them.
+rendered per-ray features are gathered on every rank once per step, as the matcher would need them - by the ray kernel's own
+epilogue (peer stores over NVLink into symmetric memory, nerf_loc_b200/distributed.py::FeatExchange) plus one barrier.
 Prints ONE JSON line (rank 0).
 """
 import argparse
@@ -253,13 +254,31 @@ def run_b200(args):
     ro_h, rd_h = ro[lo:hi].contiguous().pin_memory(), rd[lo:hi].contiguous().pin_memory()
     ro_d, rd_d = ro_h.to(dev), rd_h.to(dev)
     Rl = hi - lo
+    from nerf_loc_b200.distributed import FeatExchange
+    # the one exchange step, fused into the render: every rank's ray kernel stores its feature rows into all
+    # ranks' gathered [R,192] matrix (symmetric memory, peer stores over NVLink); a device-side barrier closes the step
+    exch, exch_note = None, ""
+    if world > 1:
+        try:
+            exch = FeatExchange(R_total, dev)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:  # symmetric memory not available on this box: one NCCL all-gather per step instead
+            exch, ok, exch_note = None, torch.zeros(1, device=dev), f"{type(e).__name__}"
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
+        if float(ok.item()) == 0.0:
+            exch = None
     from nerf_loc_b200.distributed import all_gather_rows
 
     def step_device():
         rays = {"rays_o": ro_d, "rays_d": rd_d, "depth_range": data["depth_range"][0]}
-        out = model.render_rays(data, rays)
-        if world > 1:
-            out["feat_all"] = all_gather_rows(out["feat"], R_total)  # the one exchange step
+        if exch is None:
+            out = model.render_rays(data, rays)
+            if world > 1:
+                out["feat_all"] = all_gather_rows(out["feat"], R_total)
+            return out
+        out = model.render_rays(data, rays, _feat_peers=(exch.ptrs, lo))
+        exch.barrier()
+        out["feat_all"] = exch.gathered()
         return out
 
     host_out = {}
@@ -267,9 +286,13 @@ def run_b200(args):
     def step_e2e():
         rays = {"rays_o": ro_h.to(dev, non_blocking=True), "rays_d": rd_h.to(dev, non_blocking=True),
                 "depth_range": data["depth_range"][0]}
-        out = model.render_rays(data, rays)
-        if world > 1:
-            all_gather_rows(out["feat"], R_total)
+        if exch is None:
+            out = model.render_rays(data, rays)
+            if world > 1:
+                all_gather_rows(out["feat"], R_total)
+        else:
+            out = model.render_rays(data, rays, _feat_peers=(exch.ptrs, lo))
+            exch.barrier()
         nbytes = 0
         for k, v in out.items():
             if k not in host_out:
@@ -338,7 +361,7 @@ def run_b200(args):
                    "chunk_rays": args.chunk,
                    "mma_mode": "3xTF32 tcgen05 (neighbour MLP with the A operand in tensor memory, RayUnet, feat/blend layers) + fp32 FFMA2 (aggregator, small per-sample GEMMs)",
                    "l2": "working set per step (scene 294 MB + >1 GB of per-chunk intermediates) exceeds the 126 MB L2",
-                   "parallelism": f"ray-shard x{world}" + (" + NCCL all-gather of feat[R,192]" if world > 1 else ""),
+                   "parallelism": f"ray-shard x{world}" + ("" if world == 1 else (" + all-gather of feat[R,192] fused into the ray kernel epilogue (peer stores over NVLink, symmetric memory)" if exch is not None else " + NCCL all-gather of feat[R,192] (symmetric memory unavailable: " + exch_note + ")")),
                    "per_frame_setup_ms": setup_ms},
         "e2e": {"value": R_total / (e2e_ms / e2e_steps * 1e-3), "unit": "rays/s",
                 "h2d_bytes_per_step": int(ro_h.numel() * 4 * 2), "d2h_bytes_per_step": int(d2h)},

@@ -112,6 +112,17 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
                     int64_t chunk_rays,
                     float* rgb, float* depth, float* weights, uint8_t* mask, float* depth_uncertainty, float* feat,
                     float* dbg_feature_agg, float* dbg_sigma, void* scratch, size_t scratch_bytes, void* stream);
+/* Ray-sharded rendering across the GPUs of one NVSwitch box: same as nlb_render_rays for this rank's
+ * R rays, and the rendered 192-d feature of ray i is additionally stored as row (feat_row0 + i) of every buffer in
+ * feat_peers[0..n_peers) (device pointers, n_peers <= 8): the rank's own gathered matrix and the peers', mapped into this
+ * process (CUDA IPC / symmetric memory; the stores cross NVLink).  The all-gather of the rendered 3D features that the
+ * matcher needs is thereby part of the ray kernel's epilogue; the caller only synchronises the ranks afterwards.  `feat`
+ * (the local [R,192] output) may be NULL. */
+int nlb_render_rays_gather(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
+                           const float* rays_d, const float* z_vals, int64_t z_stride, int64_t R, int white_bkgd,
+                           int64_t chunk_rays, float* rgb, float* depth, float* weights, uint8_t* mask,
+                           float* depth_uncertainty, float* feat, void* scratch, size_t scratch_bytes,
+                           float* const* feat_peers /*HOST array*/, int n_peers, int64_t feat_row0, void* stream);
 /* ---- hierarchical sampling, render.N_importance > 0 (model.py:486-496; multiview_aggregator.py:95-154; utils.py:73-112) ---
  * center [3] (HOST) and dirs [R,3] (device): the query camera centre and the UN-normalised NeuRay ray directions
  * (depth_fusion.py:9-30) of the pixels; z_coarse [64] and z_regular [n_samples] from sample_depths; u [R,n_importance] the

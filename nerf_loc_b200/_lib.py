@@ -47,6 +47,9 @@ SIGNATURES = {
     "nlb_render_rays": (c_int, [ctypes.POINTER(NlbScene), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                 c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "nlb_render_rays_gather": (c_int, [ctypes.POINTER(NlbScene), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
+                                       c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p, c_size_t, c_void_p, c_int, c_int64, c_void_p]),
     "nlb_render_launch_count": (c_int64, [c_int64, c_int64]),
     "nlb_hierarchical_depths": (c_int, [ctypes.POINTER(NlbScene), c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
                                         c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -434,7 +434,9 @@ class ConditionalNeRF(nn.Module):
         return z, depth_coarse, inds
 
     @torch.no_grad()
-    def render_rays(self, data, rays, _debug=False, _u=None):
+    def render_rays(self, data, rays, _debug=False, _u=None, _feat_peers=None):
+        """model.py:472-600.  `_feat_peers = (device pointers, row0)` (ray sharding, see distributed.FeatExchange): the rendered
+        feature rows are also stored into every listed [R_total,192] buffer at rows row0.. by the ray kernel itself."""
         L = _lib.load()
         near, far = rays['depth_range']
         S = self.n_samples
@@ -460,11 +462,22 @@ class ConditionalNeRF(nn.Module):
         if key not in self._frame:
             self._frame[key] = torch.empty(nb, dtype=torch.uint8, device=dev)
         white = 1 if data.get('white_bkgd', self.args.render.white_bkgd) else 0
-        _lib.check(L.nlb_render_rays(ctypes.byref(sc), _lib.ptr(self.packed_weights()), S, _lib.ptr(ro), _lib.ptr(rd),
-                                     _lib.ptr(z), S if z.dim() == 2 else 0, R, white, chunk, _lib.ptr(out['rgb']), _lib.ptr(out['depth']),
-                                     _lib.ptr(out['weights']), _lib.ptr(out['mask']), _lib.ptr(out['depth_uncertainty']),
-                                     _lib.ptr(feat), _lib.ptr(dbg_fa), _lib.ptr(dbg_sig), _lib.ptr(self._frame[key]), nb,
-                                     _lib.stream()))
+        if _feat_peers is not None:
+            if _debug:
+                raise ValueError("render_rays: _debug and _feat_peers are mutually exclusive")
+            ptrs, row0 = _feat_peers
+            arr = (ctypes.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+            _lib.check(L.nlb_render_rays_gather(ctypes.byref(sc), _lib.ptr(self.packed_weights()), S, _lib.ptr(ro), _lib.ptr(rd),
+                                                _lib.ptr(z), S if z.dim() == 2 else 0, R, white, chunk, _lib.ptr(out['rgb']),
+                                                _lib.ptr(out['depth']), _lib.ptr(out['weights']), _lib.ptr(out['mask']),
+                                                _lib.ptr(out['depth_uncertainty']), _lib.ptr(feat), _lib.ptr(self._frame[key]), nb,
+                                                arr, len(ptrs), int(row0), _lib.stream()))
+        else:
+            _lib.check(L.nlb_render_rays(ctypes.byref(sc), _lib.ptr(self.packed_weights()), S, _lib.ptr(ro), _lib.ptr(rd),
+                                         _lib.ptr(z), S if z.dim() == 2 else 0, R, white, chunk, _lib.ptr(out['rgb']), _lib.ptr(out['depth']),
+                                         _lib.ptr(out['weights']), _lib.ptr(out['mask']), _lib.ptr(out['depth_uncertainty']),
+                                         _lib.ptr(feat), _lib.ptr(dbg_fa), _lib.ptr(dbg_sig), _lib.ptr(self._frame[key]), nb,
+                                         _lib.stream()))
         out['mask'] = out['mask'].bool()
         if feat is not None:
             out['feat'] = feat

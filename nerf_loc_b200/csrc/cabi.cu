@@ -75,6 +75,11 @@ struct Prof {
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+static FeatPeers peers_at(FeatPeers p, int64_t row0) {
+  p.row0 = row0;
+  return p;
+}
+
 // one low-priority non-blocking stream per host thread and device, created on first use and kept for the process lifetime
 static cudaStream_t side_stream() {
   static thread_local cudaStream_t s[16] = {};
@@ -220,10 +225,11 @@ int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays) {
   return 4 * ((R + chunk_rays - 1) / chunk_rays);
 }
 
-int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
-                    const float* rays_d, const float* z_vals, int64_t z_stride, int64_t R, int white_bkgd, int64_t chunk_rays,
-                    float* rgb, float* depth, float* weights, uint8_t* mask, float* depth_uncertainty, float* feat,
-                    float* dbg_feature_agg, float* dbg_sigma, void* scratch, size_t scratch_bytes, void* stream) {
+static int render_rays_impl(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
+                            const float* rays_d, const float* z_vals, int64_t z_stride, int64_t R, int white_bkgd, int64_t chunk_rays,
+                            float* rgb, float* depth, float* weights, uint8_t* mask, float* depth_uncertainty, float* feat,
+                            float* dbg_feature_agg, float* dbg_sigma, void* scratch, size_t scratch_bytes, void* stream,
+                            float* const* feat_peers, int n_peers, int64_t feat_row0) {
   if (check_scene(scene)) return 1;
   if (R <= 0) return 0;
   if (!packed_weights || !rays_o || !rays_d || !z_vals || !rgb || !depth || !weights || !mask || !depth_uncertainty)
@@ -231,6 +237,13 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
   if (!scene->featmaps_blend) return set_error("nlb_render_rays: scene.featmaps_blend is NULL (call nlb_blend_prepare once per frame)");
   if (S % 8 != 0 || S < 8 || S > 256) return set_error("nlb_render_rays: S must be a multiple of 8 in [8, 256]");
   if (z_stride != 0 && z_stride != S) return set_error("nlb_render_rays: z_stride must be 0 (shared depths) or S (per-ray depths)");
+  if (n_peers < 0 || n_peers > 8 || (n_peers > 0 && !feat_peers)) return set_error("nlb_render_rays_gather: 0..8 peer buffers");
+  FeatPeers peers{};
+  peers.n = n_peers;
+  for (int p = 0; p < n_peers; ++p) {
+    if (!feat_peers[p]) return set_error("nlb_render_rays_gather: NULL peer buffer");
+    peers.p[p] = feat_peers[p];
+  }
   if (chunk_rays < 1) chunk_rays = R;
   if (chunk_rays > R) chunk_rays = R;
   cudaStream_t st = (cudaStream_t)stream;
@@ -300,10 +313,10 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
     if (S <= 128) {
       if (launch_ray(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                      weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
-                     dbg_sigma ? dbg_sigma + r0 * S : nullptr, st)) { rc_err = 1; break; }
+                     dbg_sigma ? dbg_sigma + r0 * S : nullptr, peers_at(peers, feat_row0 + r0), st)) { rc_err = 1; break; }
     } else if (launch_ray_long(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                                weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
-                               dbg_sigma ? dbg_sigma + r0 * S : nullptr, slabs, st)) {
+                               dbg_sigma ? dbg_sigma + r0 * S : nullptr, slabs, peers_at(peers, feat_row0 + r0), st)) {
       rc_err = 1; break;
     }
     if (overlap && i + 1 < nchunks) {
@@ -322,6 +335,24 @@ int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, 
     cudaEventDestroy(ev_nb);
   }
   return rc_err;
+}
+
+int nlb_render_rays(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
+                    const float* rays_d, const float* z_vals, int64_t z_stride, int64_t R, int white_bkgd, int64_t chunk_rays,
+                    float* rgb, float* depth, float* weights, uint8_t* mask, float* depth_uncertainty, float* feat,
+                    float* dbg_feature_agg, float* dbg_sigma, void* scratch, size_t scratch_bytes, void* stream) {
+  return render_rays_impl(scene, packed_weights, S, rays_o, rays_d, z_vals, z_stride, R, white_bkgd, chunk_rays, rgb, depth, weights,
+                          mask, depth_uncertainty, feat, dbg_feature_agg, dbg_sigma, scratch, scratch_bytes, stream, nullptr, 0, 0);
+}
+
+int nlb_render_rays_gather(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
+                           const float* rays_d, const float* z_vals, int64_t z_stride, int64_t R, int white_bkgd,
+                           int64_t chunk_rays, float* rgb, float* depth, float* weights, uint8_t* mask, float* depth_uncertainty,
+                           float* feat, void* scratch, size_t scratch_bytes, float* const* feat_peers, int n_peers,
+                           int64_t feat_row0, void* stream) {
+  return render_rays_impl(scene, packed_weights, S, rays_o, rays_d, z_vals, z_stride, R, white_bkgd, chunk_rays, rgb, depth, weights,
+                          mask, depth_uncertainty, feat, nullptr, nullptr, scratch, scratch_bytes, stream, feat_peers, n_peers,
+                          feat_row0);
 }
 
 int nlb_hierarchical_depths(const nlb_scene* scene, const float* packed_weights, int S_total, const float* center,

@@ -15,6 +15,15 @@ struct PointSrc {
   int64_t zs;
 };
 
+// Peer copies of the rendered-feature matrix (ray sharding across the GPUs of one NVSwitch box): the ray kernels store
+// feat row (row0 + ray) into every listed buffer - the local one and the peers' mapped over NVLink - so the all-gather
+// of the rendered features that precedes matching is part of the render epilogue instead of a separate collective.
+struct FeatPeers {
+  float* p[8];
+  int n;
+  int64_t row0;
+};
+
 int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int with_blend, float* agg,
                      float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, cudaStream_t st);
 int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
@@ -26,7 +35,7 @@ int launch_sup_geo(const float* xyz, const float* dir, const float* conf, int64_
 int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
                const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
-               cudaStream_t st);
+               const FeatPeers& peers, cudaStream_t st);
 
 // hierarchical sampling (hier_sample.cu)
 int launch_hier_sample(const SceneDev& sc, const RenderW& w, const float* center_host, const float* dirs, int64_t R,
@@ -38,6 +47,6 @@ size_t ray_long_slab_floats(int S);
 int launch_ray_long(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
                     const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                     float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
-                    float* slabs, cudaStream_t st);
+                    float* slabs, const FeatPeers& peers, cudaStream_t st);
 
 }  // namespace nlb

@@ -214,7 +214,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
            const float* __restrict__ fagg, const float* __restrict__ partial, const float* __restrict__ rgbvis,
            const unsigned char* __restrict__ nvalid, float* __restrict__ rgb_out, float* __restrict__ depth_out,
            float* __restrict__ weights_out, unsigned char* __restrict__ mask_out, float* __restrict__ unc_out,
-           float* __restrict__ feat_out, float* __restrict__ sigma_dbg) {
+           float* __restrict__ feat_out, float* __restrict__ sigma_dbg, const FeatPeers peers) {
   extern __shared__ __align__(1024) unsigned char sm[];
   float* misc = reinterpret_cast<float*>(sm + RY_MISC);
   float* sRGB = misc;               // [S][4]
@@ -460,7 +460,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
     // ---- rendered feature (model.py:594-598) ---------------------------------------------------------------------------------
     tc::mbar_wait(&sy.d_aux, 0);                                           // feat_mlp layer 1 done (x tile is free now)
     tc::fence_after_sync();
-    if (feat_out) {
+    if (feat_out || peers.n > 0) {
       float* sPart = reinterpret_cast<float*>(sm);  // [128][132] fp32 over the dead x tile
       const float wrow = c.row < S ? sWt[c.row] : 0.f;
 #pragma unroll
@@ -489,7 +489,9 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
       if (tid < C_FEAT) {
         float a = __ldg(w.ft2_b + tid) * wsum;
         for (int k = 0; k < 128; ++k) a = fmaf(__ldg(w.ft2 + k * C_FEAT + tid), sHs[k], a);
-        feat_out[ray * C_FEAT + tid] = a;
+        if (feat_out) feat_out[ray * C_FEAT + tid] = a;
+        // fused all-gather: the same 768-byte row goes to every rank's gathered matrix (peer stores over NVLink)
+        for (int p = 0; p < peers.n; ++p) peers.p[p][(peers.row0 + ray) * C_FEAT + tid] = a;
       }
     }
   }
@@ -504,7 +506,7 @@ int read_prof_ray(long long* out, int n) {
 int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
                const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
-               cudaStream_t st) {
+               const FeatPeers& peers, cudaStream_t st) {
   if (R <= 0) return 0;
   if (S % 8 != 0 || S < 8 || S > 128) return set_error("ray stage: samples per ray must be a multiple of 8 in [8, 128]");
   if (w.S != S) return set_error("ray stage: weights were packed for a different number of samples per ray");
@@ -512,7 +514,7 @@ int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_
   cudaError_t e = cudaFuncSetAttribute(ray_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RY_SMEM_BYTES);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   ray_kernel<<<(unsigned)R, NT + 64, RY_SMEM_BYTES, st>>>(sc, w, z_vals, zs, S, white_bkgd, fagg, partial, rgbvis, nvalid, rgb,
-                                                        depth, weights, mask, depth_unc, feat, sigma_dbg);
+                                                        depth, weights, mask, depth_unc, feat, sigma_dbg, peers);
   return check_launch("ray_kernel");
 }
 

@@ -96,6 +96,7 @@ ray_long_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_
                 const float* __restrict__ rgbvis, const unsigned char* __restrict__ nvalid, float* __restrict__ rgb_out,
                 float* __restrict__ depth_out, float* __restrict__ weights_out, unsigned char* __restrict__ mask_out,
                 float* __restrict__ unc_out, float* __restrict__ feat_out, float* __restrict__ sigma_dbg, float* slabs,
+                const FeatPeers peers,
                 const size_t slab_floats) {
   extern __shared__ __align__(16) float smem[];
   float* sB = smem;                        // weight staging ring
@@ -242,7 +243,7 @@ ray_long_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_
     }
 
     // ---- rendered feature (model.py:594-598): feat = W2 (sum_s w_s h_s) + b2 sum_s w_s -----------------------------------------
-    if (feat_out) {
+    if (feat_out || peers.n > 0) {
       tile_gemm<4, 8, 128, false>(plainA(X, RL_LDX), S, w.ft1, 128, 128, sB,
                                   [&](int rr, int c, float v) { raw[rr * 128 + c] = leaky(v + __ldg(w.ft1_b + c)) * sWt[rr]; });
       cta_sync();
@@ -256,7 +257,8 @@ ray_long_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_
       if (tid < C_FEAT) {
         float a = __ldg(w.ft2_b + tid) * wsum;
         for (int k = 0; k < 128; ++k) a = fmaf(__ldg(w.ft2 + k * C_FEAT + tid), sHs[k], a);
-        feat_out[ray * C_FEAT + tid] = a;
+        if (feat_out) feat_out[ray * C_FEAT + tid] = a;
+        for (int p = 0; p < peers.n; ++p) peers.p[p][(peers.row0 + ray) * C_FEAT + tid] = a;   // fused all-gather (peer stores)
       }
     }
   }
@@ -265,7 +267,7 @@ ray_long_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_
 int launch_ray_long(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
                     const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                     float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
-                    float* slabs, cudaStream_t st) {
+                    float* slabs, const FeatPeers& peers, cudaStream_t st) {
   if (R <= 0) return 0;
   if (S % 8 != 0 || S <= 128 || S > RL_MAX_S) return set_error("long-ray stage: samples per ray must be a multiple of 8 in (128, 256]");
   if (w.S != S) return set_error("ray stage: weights were packed for a different number of samples per ray");
@@ -276,7 +278,7 @@ int launch_ray_long(const SceneDev& sc, const RenderW& w, const float* z_vals, i
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   ray_long_kernel<<<(unsigned)ray_long_grid(R), NT, smem, st>>>(sc, w, z_vals, zs, S, white_bkgd, R, fagg, partial, rgbvis, nvalid,
                                                                 rgb, depth, weights, mask, depth_unc, feat, sigma_dbg, slabs,
-                                                                ray_long_slab_floats(S));
+                                                                peers, ray_long_slab_floats(S));
   return check_launch("ray_long_kernel");
 }
 

@@ -4,6 +4,11 @@ Rays are independent (only the RayUnet couples samples WITHIN a ray), so rank g 
 [g*per, (g+1)*per) of the row-major ray list; scene tensors and weights are replicated.  The one exchange step is an
 all-gather of the per-ray outputs the matcher / caller needs (`feat [R,192]`, optionally rgb / depth / mask).  One process
 per GPU, `torch.distributed` (NCCL on GPUs; gloo works for the host-side logic and the CPU tests).
+
+On GPUs the exchange of `feat` is FUSED into the render: `FeatExchange` allocates the gathered [R,192] matrix in symmetric
+memory (every rank's copy is mapped into every other rank), and the ray kernel's epilogue stores each rendered feature row
+straight into all copies with peer stores over NVLink (`nlb_render_rays_gather`).  What is left of the collective is one
+device-side barrier.  `all_gather_rows` (one NCCL / gloo all-gather) remains for the other outputs and for the CPU tests.
 """
 import torch
 import torch.distributed as dist
@@ -33,9 +38,31 @@ def all_gather_rows(x, R, group=None):
     return out[:R]
 
 
-def render_rays_sharded(model, data, rays, gather=("feat",), group=None):
+class FeatExchange:
+    """Gathered rendered-feature matrix [R,192] in symmetric memory + the peer pointers the ray kernels store into."""
+
+    def __init__(self, R, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.R = R
+        self.buf = symm_mem.empty(max(R, 1), 192, dtype=torch.float32, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self.ptrs) > 8:
+            raise RuntimeError("FeatExchange: at most 8 ranks (one NVSwitch box)")
+
+    def barrier(self):
+        """All ranks' peer stores queued before this point (on the current stream) are visible after it."""
+        self.handle.barrier()
+
+    def gathered(self):
+        return self.buf[:self.R]
+
+
+def render_rays_sharded(model, data, rays, gather=("feat",), group=None, exchange=None):
     """`ConditionalNeRF.render_rays` over this rank's slice of `rays`, then one all-gather per requested output.
-    Returns (local_outputs, gathered_outputs)."""
+    With `exchange` (a FeatExchange over all R rays) the gather of `feat` is done by the ray kernel itself (peer stores) and
+    only a barrier follows.  Returns (local_outputs, gathered_outputs)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     R = rays["rays_o"].shape[0]
@@ -44,9 +71,16 @@ def render_rays_sharded(model, data, rays, gather=("feat",), group=None):
     local["rays_o"], local["rays_d"] = rays["rays_o"][lo:hi], rays["rays_d"][lo:hi]
     if "pixel_coordinates" in rays:
         local["pixel_coordinates"] = rays["pixel_coordinates"][lo:hi]
-    out = model.render_rays(data, local)
+    if exchange is not None:
+        out = model.render_rays(data, local, _feat_peers=(exchange.ptrs, lo))
+        exchange.barrier()
+    else:
+        out = model.render_rays(data, local)
     gathered = {}
     for k in gather:
+        if k == "feat" and exchange is not None:
+            gathered[k] = exchange.gathered()
+            continue
         v = out[k]
         g = all_gather_rows(v.to(torch.uint8) if v.dtype == torch.bool else v, R, group)
         gathered[k] = g.bool() if v.dtype == torch.bool else g
