@@ -395,8 +395,8 @@ __global__ void __launch_bounds__(128) knn_query_rays_kernel(const void* __restr
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const bool ok = best.id[k] != 0x7fffffff;
-      idx32[i * K + k] = ok ? best.id[k] : 0;
-      dist2[i * K + k] = ok ? best.d[k] : 0.f;
+      __stcs(idx32 + i * K + k, ok ? best.id[k] : 0);
+      __stcs(dist2 + i * K + k, ok ? best.d[k] : 0.f);
     }
   }
 }

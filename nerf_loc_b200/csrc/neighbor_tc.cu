@@ -446,7 +446,7 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           const float f = sO[p * NB_LDH + c];
           float a = 0.f;
           for (int k = 0; k < K; ++k) a += f * sSc[p * 8 + k];
-          fagg_out[(n0p + p) * W_HID + c] = a;
+          __stcs(fagg_out + (n0p + p) * W_HID + c, a);   // read once by the ray kernel, much later
           if (feature_out) feature_out[(n0p + p) * W_HID + c] = f;
         }
       }

@@ -518,7 +518,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           const int p = r / V, v = r - p * V;
           if (lane == 0) {
             frow[0] = c.x; frow[1] = c.y; frow[2] = c.z;
-            if (rgbvis_out) *reinterpret_cast<float4*>(rgbvis_out + ((n0 + p) * V + v) * 4) = make_float4(c.x, c.y, c.z, ri[RI_VIS]);
+            if (rgbvis_out) __stcs(reinterpret_cast<float4*>(rgbvis_out + ((n0 + p) * V + v) * 4), make_float4(c.x, c.y, c.z, ri[RI_VIS]));
           }
           if (with_blend) {
             float a = 0.f;
@@ -527,7 +527,9 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
             a = fmaf(c.x, wb[0], a); a = fmaf(c.y, wb[1], a); a = fmaf(c.z, wb[2], a);
             a = fmaf(ri[RI_VIS], wb[3], a);
             a = fmaf(ri[RI_RD0], wb[4], a); a = fmaf(ri[RI_RD1], wb[5], a); a = fmaf(ri[RI_RD2], wb[6], a); a = fmaf(ri[RI_RD3], wb[7], a);
-            partial_out[((n0 + p) * V + v) * 32 + lane] = a + bias;
+            // per-chunk intermediates are written once and read once by the next kernel: streaming stores keep them from
+            // evicting the reference feature maps (118 MB, gathered by every sample) out of the 126 MB L2
+            __stcs(partial_out + ((n0 + p) * V + v) * 32 + lane, a + bias);
           }
         }
       }
@@ -557,7 +559,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
                   [&](int r, int c, float v) { sO1[r * 68 + c] = elu(v + __ldg(w.fc1_b + c)); });
   cta_sync();
   rows16_gemm<128, TP_MAX, 64, 8>([&](int r, int) { return sO1 + r * 68; }, w.fc2, 128, sB, [&](int r, int c, float v) {
-    if (r < np) agg_out[(n0 + r) * W_HID + c] = elu(v + __ldg(w.fc2_b + c));
+    if (r < np) __stcs(agg_out + (n0 + r) * W_HID + c, elu(v + __ldg(w.fc2_b + c)));
   });
 
   AGG_STAMP(8);

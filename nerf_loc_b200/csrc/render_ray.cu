@@ -197,7 +197,7 @@ __device__ __forceinline__ void load_x(unsigned char* sm, const float* __restric
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int i = i0 + u * NT;
-      v[u] = i < S * 32 ? __ldg(reinterpret_cast<const float4*>(fagg + (s0 + (i >> 5)) * W_HID + (i & 31) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[u] = i < S * 32 ? __ldcs(reinterpret_cast<const float4*>(fagg + (s0 + (i >> 5)) * W_HID + (i & 31) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
@@ -306,7 +306,7 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
       float h1[32];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 a = __ldg(pp + q);
+        const float4 a = __ldcs(pp + q);   // streamed once
         const float4 b = *reinterpret_cast<const float4*>(sBl + s * 36 + q * 4);
         h1[q * 4 + 0] = leaky(a.x + b.x); h1[q * 4 + 1] = leaky(a.y + b.y);
         h1[q * 4 + 2] = leaky(a.z + b.z); h1[q * 4 + 3] = leaky(a.w + b.w);
