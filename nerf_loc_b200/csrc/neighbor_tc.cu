@@ -363,6 +363,8 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
       if (prev) {
         // ---- B (tile t-1): o_h = Wv_h ctx_h ; fc + residual ------------------------------------------------------------------
         cta_sync();  // ctx complete
+        // (these two stay on the FFMA2 small-M GEMM: the warp-level mma.sync path shares the tensor pipe with the tcgen05
+        // layer that runs underneath this chunk and measured 14.1 k vs 11.4 k clk here; it wins for the q / q~ pair below)
         rows16_gemm<128, 16, 128, 32>([&](int r, int c) { return sQT + (r * 4 + (c >> 5)) * NB_LDH; }, w.wv, 128, sB,
                          [&](int r, int c, float v) { sO[r * NB_LDH + c] = v; });
         cta_sync();
@@ -456,40 +458,12 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         // ---- C2 (tile t): q = Wq agg ; q~_h = Wk_h^T q_h ------------------------------------------------------------------------
         cp_async_wait<0>();
         cta_sync();  // every thread's part of the agg tile has landed
-        rows16_gemm<128, 16, 128, 32>([&](int r, int) { return sAgg + r * NB_LDH; }, w.wq, 128, sB,
-                         [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v; });
+        rows16_mma<128, 128, 1>([&](int r, int, int) { return sAgg + r * NB_LDH; }, w.wq, 128,
+                                [&](int r, int c, float v, int) { sQ[r * NB_LDH + c] = v; });
         cta_sync();
-        {
-          // q~[p][h][c] = sum_j q[p][32h+j] Wk[32h+j][c]: thread = (column c, head pair); all 64 weight loads of a thread are
-          // independent, no K split and no reduction
-          const int c = tid & 127, hp = tid >> 7;
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int hd = hp * 2 + hh;
-            float acc[16][2];
-#pragma unroll
-            for (int r = 0; r < 16; ++r) { acc[r][0] = 0.f; acc[r][1] = 0.f; }
-            const float* wp = w.wk + (size_t)(32 * hd) * 128 + c;
-#pragma unroll
-            for (int k = 0; k < 32; k += 8) {
-              float b[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) b[j] = __ldg(wp + (size_t)(k + j) * 128);
-#pragma unroll
-              for (int r = 0; r < 16; ++r) {
-                const float* ap = sQ + r * NB_LDH + 32 * hd + k;
-                const float4 a0 = *reinterpret_cast<const float4*>(ap);
-                const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
-                fma2_v(acc[r][0], acc[r][1], a0.x, a0.y, b[0], b[1]);
-                fma2_v(acc[r][0], acc[r][1], a0.z, a0.w, b[2], b[3]);
-                fma2_v(acc[r][0], acc[r][1], a1.x, a1.y, b[4], b[5]);
-                fma2_v(acc[r][0], acc[r][1], a1.z, a1.w, b[6], b[7]);
-              }
-            }
-#pragma unroll
-            for (int r = 0; r < 16; ++r) sQT[(r * 4 + hd) * NB_LDH + c] = acc[r][0] + acc[r][1];
-          }
-        }
+        // q~[p][h][c] = sum_j q[p][32h+j] Wk[32h+j][c]: four K = 32 products sharing the 128 output columns
+        rows16_mma<128, 32, 4>([&](int r, int, int h) { return sQ + r * NB_LDH + 32 * h; }, w.wk, 128,
+                               [&](int r, int c, float v, int h) { sQT[(r * 4 + h) * NB_LDH + c] = v; });
       }
       if (stamp) g_prof[9] = clock64();
 

@@ -284,6 +284,74 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
   }
 }
 
+// ---- 16-row GEMM on the warp-level tensor-core path (mma.sync.m16n8k8 tf32, 3xTF32 split) -----------------------------------
+// out[16][NCOLS] = A[16][K] * W[K][NCOLS].  M = 16 is exactly one MMA tile, so the per-sample projections of the neighbour
+// kernel (16 samples per tile) need no K split, no shared-memory reduction and no barrier: warp w owns columns
+// [w * NCOLS/8, (w+1) * NCOLS/8), reads its B fragments (W row-major [k][n], leading dimension ldb) straight from L2 in ONE
+// batch, its A fragments from shared memory (row stride % 32 == 4: conflict free), and keeps the fp32 accumulators in
+// registers.  3xTF32: hi = value with the low 13 mantissa bits cleared, lo = value - hi; lo*hi + hi*lo + hi*hi.
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                 "r"(__float_as_uint(b[0])), "r"(__float_as_uint(b[1])));
+}
+__device__ __forceinline__ void split_hi_lo(const float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+// HEADS > 1: HEADS independent products that share the output columns, head h using K rows of W starting at row h*K
+// (the folded key projection: q~_h = Wk_h^T q_h).  arow(r, n, h) -> shared-memory pointer to row r of A as seen by output
+// column n (multiple of 8) of head h; epi(r, n, value, h).  All B fragments of all heads are requested before the first MMA.
+template <int NCOLS, int K, int HEADS, class ARow, class Epi>
+__device__ __forceinline__ void rows16_mma(ARow arow, const float* __restrict__ W, const int ldb, Epi epi) {
+  constexpr int NTW = NCOLS / 64;          // 8-column tiles per warp (8 warps)
+  constexpr int KS = K / 8;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int n0 = warp * (NCOLS / 8);
+  float b[HEADS][KS][NTW][2];
+#pragma unroll
+  for (int h = 0; h < HEADS; ++h)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        b[h][ks][nt][0] = __ldg(W + (size_t)(h * K + ks * 8 + t) * ldb + n0 + nt * 8 + g);
+        b[h][ks][nt][1] = __ldg(W + (size_t)(h * K + ks * 8 + t + 4) * ldb + n0 + nt * 8 + g);
+      }
+#pragma unroll
+  for (int h = 0; h < HEADS; ++h) {
+    float c[NTW][4];
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
+    const float* a_r0 = arow(g, n0, h);       // rows g and g + 8 of the 16-row tile
+    const float* a_r8 = arow(g + 8, n0, h);
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      float ah[4], al[4];
+      split_hi_lo(a_r0[ks * 8 + t], ah[0], al[0]);
+      split_hi_lo(a_r8[ks * 8 + t], ah[1], al[1]);
+      split_hi_lo(a_r0[ks * 8 + t + 4], ah[2], al[2]);
+      split_hi_lo(a_r8[ks * 8 + t + 4], ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        float bh[2], bl[2];
+        split_hi_lo(b[h][ks][nt][0], bh[0], bl[0]);
+        split_hi_lo(b[h][ks][nt][1], bh[1], bl[1]);
+        mma_tf32_16x8x8(c[nt], al, bh);
+        mma_tf32_16x8x8(c[nt], ah, bl);
+        mma_tf32_16x8x8(c[nt], ah, bh);
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < NTW; ++nt) {
+      const int n = n0 + nt * 8 + 2 * t;
+      epi(g, n, c[nt][0], h); epi(g, n + 1, c[nt][1], h); epi(g + 8, n, c[nt][2], h); epi(g + 8, n + 1, c[nt][3], h);
+    }
+  }
+}
+
 // Register-tile GEMM against a weight tile that is ALREADY resident in shared memory (no staging, no barriers):
 // acc[i][j] += sum_k A[r0+i][k] * Bs[k*ldb + col(j)], columns col(j) = (j/4)*gstride + c0 + (j%4).
 template <int TM, int TN, int UNROLL = 2>
