@@ -152,6 +152,9 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
     for (int i = tid; i < 64 + 16 + 432 + 27; i += NT)
       sW[i] = i < 64 ? __ldg(w.rd1 + i) : (i < 80 ? __ldg(w.rd1_b + i - 64) : (i < 512 ? __ldg(w.rd2 + i - 80) : __ldg(w.rd2_b + i - 512)));
     cta_sync();
+    // LayerNorm affine parameters of this lane's four channels (loop invariant: loaded once per CTA)
+    const float4 ln_g4 = __ldg(reinterpret_cast<const float4*>(w.ln_g + lane * 4));
+    const float4 ln_b4 = __ldg(reinterpret_cast<const float4*>(w.ln_b + lane * 4));
     int64_t n0p = 0;   // previous tile
     int npp = 0;
     // this thread's (sample, neighbour) record of a tile: neighbour id + geometry, sample position and viewing direction.
@@ -434,8 +437,7 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           const float d0 = y.x - mean, d1 = y.y - mean, d2 = y.z - mean, d3 = y.w - mean;
           const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.f / 128.f);
           const float rstd = 1.f / sqrtf(var + 1e-6f);
-          const float4 g = __ldg(reinterpret_cast<const float4*>(w.ln_g + lane * 4));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(w.ln_b + lane * 4));
+          const float4 g = ln_g4, b = ln_b4;
           float4 f;
           f.x = d0 * rstd * g.x + b.x; f.y = d1 * rstd * g.y + b.y; f.z = d2 * rstd * g.z + b.z; f.w = d3 * rstd * g.w + b.w;
           *reinterpret_cast<float4*>(sO + p * NB_LDH + lane * 4) = f;
