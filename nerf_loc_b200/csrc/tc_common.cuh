@@ -36,17 +36,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// The suspend-time hint lets the hardware park the waiting thread until the phase completes (or ~10 ms pass) instead of
+// returning to a software spin loop every few cycles.  That matters here: the service warps (MMA issuer, weight producer)
+// have the highest warp ids, the warp arbiter favours high ids, and a spinning service warp would take issue slots from the
+// two compute warps that share its scheduler for as long as it waits - i.e. during every epilogue.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t a = smem_u32(bar);
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
-      "}\n" ::"r"(a), "r"(parity) : "memory");
+      "}\n" ::"r"(a), "r"(parity), "r"(0x989680u) : "memory");
 }
 // arrives on the mbarrier once every tcgen05 operation issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
