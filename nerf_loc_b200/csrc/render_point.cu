@@ -411,57 +411,14 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
 
   AGG_STAMP(4);
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
-  // features: a warp handles two rows per iteration and requests all 2 x 4 taps x 3 chunks (24 independent 8-byte loads
-  // per lane) before it consumes any; addresses are clamped into the map and taps outside carry weight 0.
-  for (int rb = warp; rb < ROWS; rb += 2 * (NT / 32)) {
-    float2 q[2][4][3];
-    float wt[2][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int r = rb + u * (NT / 32);
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        wt[u][t] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 3; ++j) q[u][t][j] = make_float2(0.f, 0.f);
-      }
-      if (r < rows) {
-        const float* ri = sRI + r * RI_N;
-        const int v = r % V;
-        const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TF);
-        const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TF + 4);
-        const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
-        const float* tp[4] = {fb + (size_t)ti.x * C_FEAT, fb + (size_t)ti.y * C_FEAT, fb + (size_t)ti.z * C_FEAT, fb + (size_t)ti.w * C_FEAT};
-        const float twv[4] = {tw.x, tw.y, tw.z, tw.w};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          wt[u][t] = twv[t];
-#pragma unroll
-          for (int j = 0; j < 3; ++j) q[u][t][j] = __ldg(reinterpret_cast<const float2*>(tp[t] + j * 64));
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      float* frow = sF + (rb + u * (NT / 32)) * LDF;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          acc.x = fmaf(q[u][t][j].x, wt[u][t], acc.x);
-          acc.y = fmaf(q[u][t][j].y, wt[u][t], acc.y);
-        }
-        frow[3 + j * 64 + lane * 2] = acc.x;
-        frow[3 + j * 64 + lane * 2 + 1] = acc.y;
-      }
-    }
-  }
-  // rgb (lanes 0..3 fetch one tap each) and, for rendering, the per-view half of the colour-blend first layer
-  // (model.py:532-535).  That layer is linear, and so is the bilinear fetch: W f(x) = sum_t b_t (W f_t), so the 192 map
-  // channels are pre-projected once per frame (sc.featb, [V][h][w][32]) and a row gathers 32 more channels instead of
-  // running a [224 x 32] GEMM; the remaining inputs (rgb, visibility, ray difference) are 8 FMAs per output.
-  // Four rows per iteration, all loads requested before any is consumed.
+  // A warp handles two rows per iteration and requests everything they need before it consumes any of it: 2 x 4 taps x 3
+  // chunks of the feature map (24 independent 8-byte loads per lane), the rgb taps (lanes 0..3, one tap each) and, for
+  // rendering, 4 taps of the pre-projected colour-blend channels; addresses are clamped into the maps and taps outside carry
+  // weight 0.
+  // Colour blend, per-view half of the first layer (model.py:532-535): that layer is linear, and so is the bilinear fetch:
+  // W f(x) = sum_t b_t (W f_t), so the 192 map channels are pre-projected once per frame (sc.featb, [V][h][w][32]) and a row
+  // gathers 32 more channels instead of running a [224 x 32] GEMM; the remaining inputs (rgb, visibility, ray difference)
+  // are 8 FMAs per output.
   {
     float wb[8], bias = 0.f;
 #pragma unroll
@@ -473,48 +430,72 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       for (int i = 0; i < 5; ++i) wb[3 + i] = __ldg(w.bl1v + (195 + i) * 32 + lane);
       bias = __ldg(w.bl1_b + lane);
     }
-    for (int rb = warp; rb < ROWS; rb += 4 * (NT / 32)) {
-      float4 cq[4];
-      float bq[4][4], bw[4][4];
+    for (int rb = warp; rb < ROWS; rb += 2 * (NT / 32)) {
+      float2 q[2][4][3];
+      float wt[2][4], bq[2][4];
+      float4 cq[2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int r = rb + u * (NT / 32);
         cq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) { bq[u][t] = 0.f; bw[u][t] = 0.f; }
+        for (int t = 0; t < 4; ++t) {
+          wt[u][t] = 0.f; bq[u][t] = 0.f;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) q[u][t][j] = make_float2(0.f, 0.f);
+        }
         if (r < rows) {
           const float* ri = sRI + r * RI_N;
           const int v = r % V;
+          const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TF);
+          const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TF + 4);
+          const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
+          const float* tp[4] = {fb + (size_t)ti.x * C_FEAT, fb + (size_t)ti.y * C_FEAT, fb + (size_t)ti.z * C_FEAT, fb + (size_t)ti.w * C_FEAT};
+          const float twv[4] = {tw.x, tw.y, tw.z, tw.w};
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            wt[u][t] = twv[t];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) q[u][t][j] = __ldg(reinterpret_cast<const float2*>(tp[t] + j * 64));
+          }
           if (lane < 4) {
             const float wi = ri[RI_TI + 4 + lane];
             if (wi != 0.f) {
               const int pix = __float_as_int(ri[RI_TI + lane]);
-              const float4 q = __ldg(reinterpret_cast<const float4*>(sc.images + ((size_t)v * sc.H * sc.W + pix) * 4));
-              cq[u] = make_float4(q.x * wi, q.y * wi, q.z * wi, 0.f);
+              const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc.images + ((size_t)v * sc.H * sc.W + pix) * 4));
+              cq[u] = make_float4(c4.x * wi, c4.y * wi, c4.z * wi, 0.f);
             }
           }
           if (with_blend) {
-            const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TF);
-            const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TF + 4);
             const float* bb = sc.featb + ((size_t)v * sc.h * sc.w) * 32 + lane;
             bq[u][0] = __ldg(bb + (size_t)ti.x * 32);
             bq[u][1] = __ldg(bb + (size_t)ti.y * 32);
             bq[u][2] = __ldg(bb + (size_t)ti.z * 32);
             bq[u][3] = __ldg(bb + (size_t)ti.w * 32);
-            bw[u][0] = tw.x; bw[u][1] = tw.y; bw[u][2] = tw.z; bw[u][3] = tw.w;
           }
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const int r = rb + u * (NT / 32);
+        float* frow = sF + r * LDF;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            acc.x = fmaf(q[u][t][j].x, wt[u][t], acc.x);
+            acc.y = fmaf(q[u][t][j].y, wt[u][t], acc.y);
+          }
+          frow[3 + j * 64 + lane * 2] = acc.x;
+          frow[3 + j * 64 + lane * 2 + 1] = acc.y;
+        }
         if (r < rows) {   // warp-uniform
           float4 c = cq[u];
           c.x += __shfl_xor_sync(0xffffffffu, c.x, 1); c.y += __shfl_xor_sync(0xffffffffu, c.y, 1); c.z += __shfl_xor_sync(0xffffffffu, c.z, 1);
           c.x += __shfl_xor_sync(0xffffffffu, c.x, 2); c.y += __shfl_xor_sync(0xffffffffu, c.y, 2); c.z += __shfl_xor_sync(0xffffffffu, c.z, 2);
           c.x = __shfl_sync(0xffffffffu, c.x, 0); c.y = __shfl_sync(0xffffffffu, c.y, 0); c.z = __shfl_sync(0xffffffffu, c.z, 0);
           const float* ri = sRI + r * RI_N;
-          float* frow = sF + r * LDF;
           const int p = r / V, v = r - p * V;
           if (lane == 0) {
             frow[0] = c.x; frow[1] = c.y; frow[2] = c.z;
@@ -523,7 +504,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           if (with_blend) {
             float a = 0.f;
 #pragma unroll
-            for (int t = 0; t < 4; ++t) a = fmaf(bq[u][t], bw[u][t], a);
+            for (int t = 0; t < 4; ++t) a = fmaf(bq[u][t], wt[u][t], a);
             a = fmaf(c.x, wb[0], a); a = fmaf(c.y, wb[1], a); a = fmaf(c.z, wb[2], a);
             a = fmaf(ri[RI_VIS], wb[3], a);
             a = fmaf(ri[RI_RD0], wb[4], a); a = fmaf(ri[RI_RD1], wb[5], a); a = fmaf(ri[RI_RD2], wb[6], a); a = fmaf(ri[RI_RD3], wb[7], a);
