@@ -408,7 +408,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=0, help="debug: render only the first N rays of the frame")
-    ap.add_argument("--chunk", type=int, default=18944, help="rays per kernel wave (148 SMs x 128)")
+    ap.add_argument("--chunk", type=int, default=37888, help="rays per kernel wave (148 SMs x 256)")
     ap.add_argument("--cpu-match-n3", type=int, default=256, help="3D points in the CPU matcher sample (0 = skip)")
     ap.add_argument("--cpu-rays", type=int, default=256, help="rays in the CPU-baseline sample (0 = skip)")
     args = ap.parse_args()

@@ -183,7 +183,7 @@ class ConditionalNeRF(nn.Module):
         self._packed = None
         self._packed_key = None
         self._frame = {}
-        self.chunk_rays = 18944  # rays per kernel wave inside nlb_render_rays (148 SMs x 128)
+        self.chunk_rays = 37888  # rays per kernel wave inside nlb_render_rays (148 SMs x 256; 2.3 KB of scratch per sample)
 
     # ---- per-frame cache protocol -------------------------------------------------------------------------------------
     @property

@@ -137,7 +137,6 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   float* sRI = sO1 + TP_MAX * 68;
   float* sPt = sRI + ROWS * RI_N;
   float* sX = arena;                // [ROWS][LDX]
-  float* sH = arena + ROWS * LDX;   // [ROWS][LDH]
   float* sF = arena;                // [ROWS][LDF] (after the decoder is done)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,12 +148,17 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   const float near_ = sc.near_, far_ = sc.far_;
 
   AGG_STAMP(0);
-  // decoder weights (32 KB) go into the staging ring, which is idle until phase 7: dec1 as [32][128], dec2 as [32][128]
-  // with the four heads side by side.  Requested now, consumed in phase 3.
-  for (int i = tid; i < 1024; i += NT) cp_async16(sB + i * 4, w.dec1 + i * 4);
+  // decoder weights (32 KB) go into the staging ring, which is idle until phase 7: dec1 as [32][128] (the four heads side by
+  // side), dec2 as 4 x [32][32].  Both are read as mma.sync B fragments (thread (g, t) reads rows t / t + 4 resp. 2t / 2t + 1,
+  // column g), so 8-column groups are XOR-swizzled with the row to keep those reads bank-conflict free without padding:
+  // dec1 (k, n) -> k * 128 + (n ^ 8 (k & 3)), dec2 (k, n) -> k * 32 + (n ^ 8 ((k >> 1) & 3)).  Requested now, consumed in phase 3.
   for (int i = tid; i < 1024; i += NT) {
-    const int hd = i >> 8, k = (i >> 3) & 31, j4 = i & 7;   // source chunk (head, k, j4) of the 4 x [32][32] blocks
-    cp_async16(sB + 4096 + k * 128 + hd * 32 + j4 * 4, w.dec2 + hd * 1024 + k * 32 + j4 * 4);
+    const int k = i >> 5, n = (i & 31) * 4;
+    cp_async16(sB + k * 128 + (n ^ ((k & 3) << 3)), w.dec1 + i * 4);
+  }
+  for (int i = tid; i < 1024; i += NT) {
+    const int k = (i >> 3) & 31, n = (i & 7) * 4;
+    cp_async16(sB + 4096 + (i >> 3) * 32 + (n ^ (((k >> 1) & 3) << 3)), w.dec2 + i * 4);
   }
   cp_async_commit();
 
@@ -271,66 +275,100 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   cp_async_wait<0>();
   cta_sync();  // decoder weights landed, sX complete
   AGG_STAMP(9);
+  // Both decoder layers and the head outputs run on the warp-level tensor-core path (mma.sync m16n8k8 tf32 with the 3xTF32
+  // hi / lo split, fp32 accumulation) and never leave registers: warp (mt, hp) owns the 16-row tile mt and the head pair hp
+  // (heads 2hp, 2hp + 1 = 64 of the 128 hidden columns).  Layer 2 is block diagonal (head h maps its own 32 columns to
+  // themselves), so the layer-1 accumulator fragment IS the layer-2 A operand: an accumulator holds columns 2t, 2t + 1 of an
+  // 8-column tile where the A fragment wants k = t, t + 4, and since a product does not care in which order k is summed the
+  // B fragment is simply read in the matching order (rows 2t, 2t + 1).  The six head outputs (visibility_decoder.py:99-148)
+  // are 32-long dot products with the layer-2 rows: in-thread over the 8 columns a thread holds, then over the four t lanes.
   {
-    // layer 1 of the four heads at once: [ROWS x 32] -> [ROWS x 128], (ROWS/16) x 8 register tile
-    constexpr int TM1 = ROWS / 16;
-    const int tc = tid & 15, r0 = (tid >> 4) * TM1;
-    float acc[TM1][8];
+    const int g = lane >> 2, t = lane & 3;
+    const int mt = warp & 3, hp = warp >> 2;
+    const float* xa = sX + (mt * 16 + g) * LDX;   // rows g and g + 8 of the tile
+    const float* xb = xa + 8 * LDX;
+    float c1[8][4];
 #pragma unroll
-    for (int i = 0; i < TM1; ++i)
+    for (int nt = 0; nt < 8; ++nt) { c1[nt][0] = 0.f; c1[nt][1] = 0.f; c1[nt][2] = 0.f; c1[nt][3] = 0.f; }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-    gemm_resident<TM1, 8, 4>(sX + r0 * LDX, LDX, sB, 128, tc * 4, 64, 32, acc);
-    float bias[8];
+    for (int ks = 0; ks < 4; ++ks) {
+      float ah[4], al[4];
+      split_hi_lo(xa[ks * 8 + t], ah[0], al[0]);
+      split_hi_lo(xb[ks * 8 + t], ah[1], al[1]);
+      split_hi_lo(xa[ks * 8 + t + 4], ah[2], al[2]);
+      split_hi_lo(xb[ks * 8 + t + 4], ah[3], al[3]);
+      const float* b0p = sB + (ks * 8 + t) * 128;   // rows k = 8 ks + t and k + 4: both have k & 3 == t
 #pragma unroll
-    for (int j = 0; j < 8; ++j) bias[j] = __ldg(w.dec1_b + (j >> 2) * 64 + tc * 4 + (j & 3));
-#pragma unroll
-    for (int i = 0; i < TM1; ++i)
-#pragma unroll
-      for (int g = 0; g < 2; ++g)
-        *reinterpret_cast<float4*>(sH + (r0 + i) * LDH + g * 64 + tc * 4) =
-            make_float4(elu(acc[i][g * 4] + bias[g * 4]), elu(acc[i][g * 4 + 1] + bias[g * 4 + 1]),
-                        elu(acc[i][g * 4 + 2] + bias[g * 4 + 2]), elu(acc[i][g * 4 + 3] + bias[g * 4 + 3]));
-  }
-  cta_sync();
-  AGG_STAMP(10);
-  {
-    // layer 2, block diagonal: head h maps columns [32h, 32h+32) to themselves; (ROWS/8) x 4 register tile inside one head
-    constexpr int TM2 = ROWS / 8;
-    const int cg = tid & 31, r0 = (tid >> 5) * TM2, hd = cg >> 3;
-    float acc[TM2][4];
-#pragma unroll
-    for (int i = 0; i < TM2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    gemm_resident<TM2, 4, 4>(sH + r0 * LDH + 32 * hd, LDH, sB + 4096, 128, cg * 4, 0, 32, acc);
-    cta_sync();  // every thread has read its inputs: write in place
-    const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.dec2_b + cg * 4));
-#pragma unroll
-    for (int i = 0; i < TM2; ++i)
-      *reinterpret_cast<float4*>(sH + (r0 + i) * LDH + cg * 4) =
-          make_float4(elu(acc[i][0] + b4.x), elu(acc[i][1] + b4.y), elu(acc[i][2] + b4.z), elu(acc[i][3] + b4.w));
-  }
-  cta_sync();
-  AGG_STAMP(11);
-  // head outputs: (row, j) dot products of length 32 spread over all threads, each followed by its own output activation
-  // (softplus for the two means, softplus + 0.05 for the two scales, sigmoid for the mixture / visibility weights);
-  // then one thread per row for the short scalar tail
-  for (int i = tid; i < rows * 6; i += NT) {
-    const int r = i / 6, j = i - r * 6;
-    const int hd = j < 2 ? 0 : (j < 4 ? 1 : (j == 4 ? 2 : 3));
-    const float* hrow = sH + r * LDH + 32 * hd;
-    const float* wj = w.dec3 + j * 32;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-    for (int k = 0; k < 32; k += 4) {
-      const float4 h4 = *reinterpret_cast<const float4*>(hrow + k);
-      const float4 w4 = __ldg(reinterpret_cast<const float4*>(wj + k));
-      a0 = fmaf(w4.x, h4.x, a0); a1 = fmaf(w4.y, h4.y, a1); a2 = fmaf(w4.z, h4.z, a2); a3 = fmaf(w4.w, h4.w, a3);
+      for (int nt = 0; nt < 8; ++nt) {
+        const int n = (hp * 64 + nt * 8 + g) ^ (t << 3);
+        float bh[2], bl[2];
+        split_hi_lo(b0p[n], bh[0], bl[0]);
+        split_hi_lo(b0p[4 * 128 + n], bh[1], bl[1]);
+        mma_tf32_16x8x8(c1[nt], al, bh);
+        mma_tf32_16x8x8(c1[nt], ah, bl);
+        mma_tf32_16x8x8(c1[nt], ah, bh);
+      }
     }
-    const float o = ((a0 + a1) + (a2 + a3)) + __ldg(w.dec3_b + j);
-    sO1[i] = j < 2 ? softplus_fast(o) : (j < 4 ? softplus_fast(o) + 0.05f : sigmoid_fast(o));
+#pragma unroll
+    for (int hl = 0; hl < 2; ++hl) {
+      const int hh = hp * 2 + hl;
+      float c2[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { c2[nt][0] = 0.f; c2[nt][1] = 0.f; c2[nt][2] = 0.f; c2[nt][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float2 b1 = __ldg(reinterpret_cast<const float2*>(w.dec1_b + hh * 32 + ks * 8 + 2 * t));
+        const float* c = c1[hl * 4 + ks];
+        float ah[4], al[4];
+        split_hi_lo(elu(c[0] + b1.x), ah[0], al[0]);   // (row g,     k = 2t)
+        split_hi_lo(elu(c[2] + b1.x), ah[1], al[1]);   // (row g + 8, k = 2t)
+        split_hi_lo(elu(c[1] + b1.y), ah[2], al[2]);   // (row g,     k = 2t + 1)
+        split_hi_lo(elu(c[3] + b1.y), ah[3], al[3]);   // (row g + 8, k = 2t + 1)
+        const float* b0p = sB + 4096 + hh * 1024 + (ks * 8 + 2 * t) * 32;   // rows k = 8 ks + 2t, k + 1: (k >> 1) & 3 == t
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int n = (nt * 8 + g) ^ (t << 3);
+          float bh[2], bl[2];
+          split_hi_lo(b0p[n], bh[0], bl[0]);
+          split_hi_lo(b0p[32 + n], bh[1], bl[1]);
+          mma_tf32_16x8x8(c2[nt], al, bh);
+          mma_tf32_16x8x8(c2[nt], ah, bl);
+          mma_tf32_16x8x8(c2[nt], ah, bh);
+        }
+      }
+      // layer-2 bias + ELU in place: c2[nt] = rows g | g + 8, columns 8 nt + 2t, + 1 of head hh
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 b2 = __ldg(reinterpret_cast<const float2*>(w.dec2_b + hh * 32 + nt * 8 + 2 * t));
+        c2[nt][0] = elu(c2[nt][0] + b2.x); c2[nt][1] = elu(c2[nt][1] + b2.y);
+        c2[nt][2] = elu(c2[nt][2] + b2.x); c2[nt][3] = elu(c2[nt][3] + b2.y);
+      }
+      // head outputs: mean head -> j = 0, 1 (softplus), scale head -> j = 2, 3 (softplus + 0.05), mixture weight -> j = 4
+      // and visibility scale -> j = 5 (sigmoid)
+      const int nj = hp == 0 ? 2 : 1, jb = hp == 0 ? hl * 2 : 4 + hl;
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        if (jj < nj) {   // warp-uniform
+          const int j = jb + jj;
+          float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt) {
+            const float2 w3 = __ldg(reinterpret_cast<const float2*>(w.dec3 + j * 32 + nt * 8 + 2 * t));
+            p0 = fmaf(c2[nt][0], w3.x, p0); p0 = fmaf(c2[nt][1], w3.y, p0);
+            p1 = fmaf(c2[nt][2], w3.x, p1); p1 = fmaf(c2[nt][3], w3.y, p1);
+          }
+          p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+          p0 += __shfl_xor_sync(0xffffffffu, p0, 2); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+          if (t < 2) {   // lane t = 0 finishes row g, lane t = 1 row g + 8
+            const float o = (t == 0 ? p0 : p1) + __ldg(w.dec3_b + j);
+            sO1[(mt * 16 + g + 8 * t) * 6 + j] = j < 2 ? softplus_fast(o) : (j < 4 ? softplus_fast(o) + 0.05f : sigmoid_fast(o));
+          }
+        }
+      }
+    }
   }
+  AGG_STAMP(10);
+  AGG_STAMP(11);
   cta_sync();
   const bool fused_w = V == 8;   // rows of a sample are 8 consecutive lanes: the view weights follow in the same threads
   if (tid < ROWS && (fused_w || tid < rows)) {
@@ -407,7 +445,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     }
   }
   AGG_STAMP(3);
-  cta_sync();  // sH (arena) is dead from here on; view weights visible
+  cta_sync();  // sX (arena) is dead from here on; view weights visible
 
   AGG_STAMP(4);
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
