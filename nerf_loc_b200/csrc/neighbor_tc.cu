@@ -428,6 +428,12 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
           ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
           const float wk = v / fmaxf(ssum, 1e-8f);
           sSc[tid] = wk;
+          // the K rows of `feature` are identical, so feature_agg = feature * sum_k w_k: the sum is taken once per sample here
+          float wt = wk;
+          wt += __shfl_xor_sync(0xffffffffu, wt, 1);
+          wt += __shfl_xor_sync(0xffffffffu, wt, 2);
+          wt += __shfl_xor_sync(0xffffffffu, wt, 4);
+          if (k == 0) sSc[128 + (tid >> 3)] = wt;
           if (weights_out && (tid >> 3) < npp && k < K) weights_out[(n0p + (tid >> 3)) * K + k] = wk;
         }
         if (stamp) g_prof[12] = clock64();
@@ -448,9 +454,7 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         for (int i = tid; i < npp * W_HID; i += NT) {
           const int p = i >> 7, c = i & 127;
           const float f = sO[p * NB_LDH + c];
-          float a = 0.f;
-          for (int k = 0; k < K; ++k) a += f * sSc[p * 8 + k];
-          __stcs(fagg_out + (n0p + p) * W_HID + c, a);   // read once by the ray kernel, much later
+          __stcs(fagg_out + (n0p + p) * W_HID + c, f * sSc[128 + p]);   // read once by the ray kernel, much later
           if (feature_out) feature_out[(n0p + p) * W_HID + c] = f;
         }
       }

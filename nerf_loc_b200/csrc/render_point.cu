@@ -106,19 +106,32 @@ __device__ __forceinline__ void mean_var_rows(const float* __restrict__ f0, cons
   float wv[VM];
 #pragma unroll
   for (int v = 0; v < VM; ++v) wv[v] = v < V ? ri0[v * RI_N + RI_W] : 0.f;
-#pragma unroll 2
-  for (int c = lane; c < C_RGBF; c += 32) {
-    float f[VM];
+  // all loads of a lane's (up to) seven channels are requested before the first is consumed (V <= 8; two at a time above)
+  constexpr int NC = (C_RGBF + 31) / 32;
+  constexpr int JB = VM <= 8 ? NC : 2;
 #pragma unroll
-    for (int v = 0; v < VM; ++v) f[v] = v < V ? f0[v * LDF + c] : 0.f;
-    float m = 0.f;
+  for (int j0 = 0; j0 < NC; j0 += JB) {
+    float f[JB][VM];
 #pragma unroll
-    for (int v = 0; v < VM; ++v) m += f[v] * wv[v];
-    float var = 0.f;
+    for (int j = 0; j < JB; ++j) {
+      const int c = min(lane + 32 * (j0 + j), C_RGBF - 1);
 #pragma unroll
-    for (int v = 0; v < VM; ++v) { const float d = f[v] - m; var += wv[v] * (d * d); }
-    g[c] = m;
-    g[C_RGBF + c] = var;
+      for (int v = 0; v < VM; ++v) f[j][v] = v < V ? f0[v * LDF + c] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < JB; ++j) {
+      const int c = lane + 32 * (j0 + j);
+      float m = 0.f;
+#pragma unroll
+      for (int v = 0; v < VM; ++v) m += f[j][v] * wv[v];
+      float var = 0.f;
+#pragma unroll
+      for (int v = 0; v < VM; ++v) { const float d = f[j][v] - m; var += wv[v] * (d * d); }
+      if (j0 + j < NC && c < C_RGBF) {
+        g[c] = m;
+        g[C_RGBF + c] = var;
+      }
+    }
   }
 }
 
@@ -232,12 +245,13 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
 
   AGG_STAMP(1);
   // ---- phase 2: 32-channel visibility features (border padding), one warp per row ------------------------------
-  // All four taps of four rows are requested before any is consumed (addresses clamped into the map, taps outside
-  // carry weight 0), so a warp keeps 16 independent loads in flight instead of one.
-  for (int rb = warp; rb < ROWS; rb += 4 * (NT / 32)) {
-    float q[4][4], wgt[4][4], valid[4];
+  // All four taps of all ROWS / 8 rows of a warp are requested before any is consumed (addresses clamped into the map, taps
+  // outside carry weight 0): one L2 round trip for the whole phase.
+  constexpr int VU = ROWS / (NT / 32);
+  for (int rb = warp; rb < ROWS; rb += VU * (NT / 32)) {
+    float q[VU][4], wgt[VU][4], valid[VU];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < VU; ++u) {
       const int r = rb + u * (NT / 32);
       valid[u] = 0.f;
 #pragma unroll
@@ -257,7 +271,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < VU; ++u) {
       const int r = rb + u * (NT / 32);
       if (r < ROWS) {
         float a = q[u][0] * wgt[u][0];
@@ -378,10 +392,11 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     const bool live = tid < rows;
     const float dep = ri[RI_DEPTH];
     const float near_inv = -1.f / near_, far_inv = -1.f / far_;
-    float refd = -1.f / (m0 * (far_inv - near_inv) + near_inv);
+    // (divisions of this serial per-row tail use the hardware reciprocal: 2 ulp, operands far from the denormal range)
+    float refd = __fdividef(-1.f, m0 * (far_inv - near_inv) + near_inv);
     refd = fminf(fmaxf(refd, near_), far_);
-    const float dd = live ? fabsf(dep - refd) / (far_ - near_) : 0.f;
-    const float dn = (-1.f / fmaxf(dep, 1e-5f) - near_inv) / (far_inv - near_inv);
+    const float dd = live ? __fdividef(fabsf(dep - refd), far_ - near_) : 0.f;
+    const float dn = __fdividef(__fdividef(-1.f, fmaxf(dep, 1e-5f)) - near_inv, far_inv - near_inv);
     const float cdf0 = (0.5f + 0.5f * tanh_fast((dn - m0) * v0)) * vs;
     const float cdf1 = (0.5f + 0.5f * tanh_fast((dn - m1) * v1)) * vs;
     const float vis = live ? ((1.f - cdf0) * aw + (1.f - cdf1) * (1.f - aw)) * ri[RI_VALID] : 0.f;
@@ -400,7 +415,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       };
       const int p = tid >> 3, v = tid & 7;
       const float den = sum8(vis) + 1e-8f;
-      const float wv = vis / den;
+      const float wv = __fdividef(vis, den);
       const float ddm = sum8(dd * wv);
       const float wsum = sum8(wv);
       const unsigned bal = __ballot_sync(0xffffffffu, live && ri[RI_MASK] != 0.f);
@@ -525,8 +540,10 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
             acc.x = fmaf(q[u][t][j].x, wt[u][t], acc.x);
             acc.y = fmaf(q[u][t][j].y, wt[u][t], acc.y);
           }
-          frow[3 + j * 64 + lane * 2] = acc.x;
-          frow[3 + j * 64 + lane * 2 + 1] = acc.y;
+          // lanes 0-15 store their even channel first, lanes 16-31 their odd one: each store covers 32 distinct banks
+          const int up = lane >> 4;
+          frow[3 + j * 64 + lane * 2 + up] = up ? acc.y : acc.x;
+          frow[3 + j * 64 + lane * 2 + (up ^ 1)] = up ? acc.x : acc.y;
         }
         if (r < rows) {   // warp-uniform
           float4 c = cq[u];
