@@ -321,34 +321,73 @@ __device__ __forceinline__ void rows16_mma(ARow arow, const float* __restrict__ 
         b[h][ks][nt][0] = __ldg(W + (size_t)(h * K + ks * 8 + t) * ldb + n0 + nt * 8 + g);
         b[h][ks][nt][1] = __ldg(W + (size_t)(h * K + ks * 8 + t + 4) * ldb + n0 + nt * 8 + g);
       }
+  // MMAs into the same accumulator are dependent (and these asm statements keep their order), so two independent groups u are
+  // run side by side and the three 3xTF32 passes are issued pass-major over (u, n-tile): 2 * NTW independent MMAs sit between
+  // two dependent ones.  HEADS == 1: u = parity of the k-step (two partial accumulators, added at the end); HEADS > 1: u = head
+  // of a pair.
+  static_assert(HEADS == 1 ? KS % 2 == 0 : HEADS % 2 == 0, "rows16_mma: k-steps / heads are processed in pairs");
+  constexpr int NOUT = HEADS == 1 ? 1 : HEADS / 2;    // outer iterations (head pairs)
+  constexpr int KSTEP = HEADS == 1 ? 2 : 1;
 #pragma unroll
-  for (int h = 0; h < HEADS; ++h) {
-    float c[NTW][4];
+  for (int op = 0; op < NOUT; ++op) {
+    float c[2][NTW][4];
 #pragma unroll
-    for (int nt = 0; nt < NTW; ++nt) { c[nt][0] = 0.f; c[nt][1] = 0.f; c[nt][2] = 0.f; c[nt][3] = 0.f; }
-    const float* a_r0 = arow(g, n0, h);       // rows g and g + 8 of the 16-row tile
-    const float* a_r8 = arow(g + 8, n0, h);
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-    for (int ks = 0; ks < KS; ++ks) {
-      float ah[4], al[4];
-      split_hi_lo(a_r0[ks * 8 + t], ah[0], al[0]);
-      split_hi_lo(a_r8[ks * 8 + t], ah[1], al[1]);
-      split_hi_lo(a_r0[ks * 8 + t + 4], ah[2], al[2]);
-      split_hi_lo(a_r8[ks * 8 + t + 4], ah[3], al[3]);
+      for (int nt = 0; nt < NTW; ++nt) { c[u][nt][0] = 0.f; c[u][nt][1] = 0.f; c[u][nt][2] = 0.f; c[u][nt][3] = 0.f; }
+    const float* a_r0[2];
+    const float* a_r8[2];
 #pragma unroll
-      for (int nt = 0; nt < NTW; ++nt) {
-        float bh[2], bl[2];
-        split_hi_lo(b[h][ks][nt][0], bh[0], bl[0]);
-        split_hi_lo(b[h][ks][nt][1], bh[1], bl[1]);
-        mma_tf32_16x8x8(c[nt], al, bh);
-        mma_tf32_16x8x8(c[nt], ah, bl);
-        mma_tf32_16x8x8(c[nt], ah, bh);
-      }
+    for (int u = 0; u < 2; ++u) {
+      const int h = HEADS == 1 ? 0 : 2 * op + u;
+      a_r0[u] = arow(g, n0, h);         // rows g and g + 8 of the 16-row tile
+      a_r8[u] = arow(g + 8, n0, h);
     }
 #pragma unroll
-    for (int nt = 0; nt < NTW; ++nt) {
-      const int n = n0 + nt * 8 + 2 * t;
-      epi(g, n, c[nt][0], h); epi(g, n + 1, c[nt][1], h); epi(g + 8, n, c[nt][2], h); epi(g + 8, n + 1, c[nt][3], h);
+    for (int ks0 = 0; ks0 < KS; ks0 += KSTEP) {
+      float ah[2][4], al[2][4], bh[2][NTW][2], bl[2][NTW][2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int h = HEADS == 1 ? 0 : 2 * op + u;
+        const int ks = HEADS == 1 ? ks0 + u : ks0;
+        split_hi_lo(a_r0[u][ks * 8 + t], ah[u][0], al[u][0]);
+        split_hi_lo(a_r8[u][ks * 8 + t], ah[u][1], al[u][1]);
+        split_hi_lo(a_r0[u][ks * 8 + t + 4], ah[u][2], al[u][2]);
+        split_hi_lo(a_r8[u][ks * 8 + t + 4], ah[u][3], al[u][3]);
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) {
+          split_hi_lo(b[h][ks][nt][0], bh[u][nt][0], bl[u][nt][0]);
+          split_hi_lo(b[h][ks][nt][1], bh[u][nt][1], bl[u][nt][1]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) mma_tf32_16x8x8(c[u][nt], al[u], bh[u][nt]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) mma_tf32_16x8x8(c[u][nt], ah[u], bl[u][nt]);
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) mma_tf32_16x8x8(c[u][nt], ah[u], bh[u][nt]);
+    }
+    if (HEADS == 1) {
+#pragma unroll
+      for (int nt = 0; nt < NTW; ++nt) {
+        const int n = n0 + nt * 8 + 2 * t;
+        epi(g, n, c[0][nt][0] + c[1][nt][0], 0); epi(g, n + 1, c[0][nt][1] + c[1][nt][1], 0);
+        epi(g + 8, n, c[0][nt][2] + c[1][nt][2], 0); epi(g + 8, n + 1, c[0][nt][3] + c[1][nt][3], 0);
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int nt = 0; nt < NTW; ++nt) {
+          const int n = n0 + nt * 8 + 2 * t, h = 2 * op + u;
+          epi(g, n, c[u][nt][0], h); epi(g, n + 1, c[u][nt][1], h); epi(g + 8, n, c[u][nt][2], h); epi(g + 8, n + 1, c[u][nt][3], h);
+        }
     }
   }
 }

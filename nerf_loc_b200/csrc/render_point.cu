@@ -312,16 +312,20 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       split_hi_lo(xa[ks * 8 + t + 4], ah[2], al[2]);
       split_hi_lo(xb[ks * 8 + t + 4], ah[3], al[3]);
       const float* b0p = sB + (ks * 8 + t) * 128;   // rows k = 8 ks + t and k + 4: both have k & 3 == t
+      // MMAs into one accumulator are dependent: the three 3xTF32 passes are issued pass-major over the eight n-tiles
+      float bh[8][2], bl[8][2];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         const int n = (hp * 64 + nt * 8 + g) ^ (t << 3);
-        float bh[2], bl[2];
-        split_hi_lo(b0p[n], bh[0], bl[0]);
-        split_hi_lo(b0p[4 * 128 + n], bh[1], bl[1]);
-        mma_tf32_16x8x8(c1[nt], al, bh);
-        mma_tf32_16x8x8(c1[nt], ah, bl);
-        mma_tf32_16x8x8(c1[nt], ah, bh);
+        split_hi_lo(b0p[n], bh[nt][0], bl[nt][0]);
+        split_hi_lo(b0p[4 * 128 + n], bh[nt][1], bl[nt][1]);
       }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(c1[nt], al, bh[nt]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(c1[nt], ah, bl[nt]);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(c1[nt], ah, bh[nt]);
     }
 #pragma unroll
     for (int hl = 0; hl < 2; ++hl) {
@@ -339,16 +343,19 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         split_hi_lo(elu(c[1] + b1.y), ah[2], al[2]);   // (row g,     k = 2t + 1)
         split_hi_lo(elu(c[3] + b1.y), ah[3], al[3]);   // (row g + 8, k = 2t + 1)
         const float* b0p = sB + 4096 + hh * 1024 + (ks * 8 + 2 * t) * 32;   // rows k = 8 ks + 2t, k + 1: (k >> 1) & 3 == t
+        float bh[4][2], bl[4][2];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt) {
           const int n = (nt * 8 + g) ^ (t << 3);
-          float bh[2], bl[2];
-          split_hi_lo(b0p[n], bh[0], bl[0]);
-          split_hi_lo(b0p[32 + n], bh[1], bl[1]);
-          mma_tf32_16x8x8(c2[nt], al, bh);
-          mma_tf32_16x8x8(c2[nt], ah, bl);
-          mma_tf32_16x8x8(c2[nt], ah, bh);
+          split_hi_lo(b0p[n], bh[nt][0], bl[nt][0]);
+          split_hi_lo(b0p[32 + n], bh[nt][1], bl[nt][1]);
         }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_16x8x8(c2[nt], al, bh[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_16x8x8(c2[nt], ah, bl[nt]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) mma_tf32_16x8x8(c2[nt], ah, bh[nt]);
       }
       // layer-2 bias + ELU in place: c2[nt] = rows g | g + 8, columns 8 nt + 2t, + 1 of head hh
 #pragma unroll

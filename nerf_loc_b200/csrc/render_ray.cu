@@ -300,32 +300,50 @@ ray_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals,
       for (int j = 0; j < 16; ++j) sBl[c.row * 36 + c.half * 16 + j] = v[j];
     }
     cta_sync();
-    for (int i = tid; i < S * V; i += NT) {
-      const int s = i / V;
-      const float4* pp = reinterpret_cast<const float4*>(partial + (s0 * V + i) * 32);
-      float h1[32];
+    // two (sample, view) items per thread at a time: both rows of `partial` (streamed from HBM, written by aggregate_kernel a
+    // chunk ago) are requested together - half as many exposed round trips - and the layer-2 weights are read once per pair
+    for (int i0 = tid; i0 < S * V; i0 += 2 * NT) {
+      const int i1 = i0 + NT;
+      const bool two = i1 < S * V;
+      const int ib[2] = {i0, two ? i1 : i0};
+      float4 pa[2][8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 a = __ldcs(pp + q);   // streamed once
-        const float4 b = *reinterpret_cast<const float4*>(sBl + s * 36 + q * 4);
-        h1[q * 4 + 0] = leaky(a.x + b.x); h1[q * 4 + 1] = leaky(a.y + b.y);
-        h1[q * 4 + 2] = leaky(a.z + b.z); h1[q * 4 + 3] = leaky(a.w + b.w);
+      for (int u = 0; u < 2; ++u) {
+        const float4* pp = reinterpret_cast<const float4*>(partial + (s0 * V + ib[u]) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pa[u][q] = __ldcs(pp + q);   // streamed once
       }
-      float logit = sW2[544];
-#pragma unroll 4
+      float h1[2][32];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int s = ib[u] / V;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 a = pa[u][q];
+          const float4 b = *reinterpret_cast<const float4*>(sBl + s * 36 + q * 4);
+          h1[u][q * 4 + 0] = leaky(a.x + b.x); h1[u][q * 4 + 1] = leaky(a.y + b.y);
+          h1[u][q * 4 + 2] = leaky(a.z + b.z); h1[u][q * 4 + 3] = leaky(a.w + b.w);
+        }
+      }
+      float logit0 = sW2[544], logit1 = logit0;
+#pragma unroll 2
       for (int o = 0; o < 16; ++o) {
         // even-k / odd-k partial sums: one FFMA2 per two k, weights read as float4 (broadcast)
-        float a = sW2[512 + o], a1 = 0.f;
+        float a = sW2[512 + o], a1 = 0.f, c = a, c1 = 0.f;
 #pragma unroll
         for (int k = 0; k < 32; k += 4) {
           const float4 w4 = *reinterpret_cast<const float4*>(sW2 + o * 32 + k);
-          fma2_v(a, a1, w4.x, w4.y, h1[k], h1[k + 1]);
-          fma2_v(a, a1, w4.z, w4.w, h1[k + 2], h1[k + 3]);
+          fma2_v(a, a1, w4.x, w4.y, h1[0][k], h1[0][k + 1]);
+          fma2_v(c, c1, w4.x, w4.y, h1[1][k], h1[1][k + 1]);
+          fma2_v(a, a1, w4.z, w4.w, h1[0][k + 2], h1[0][k + 3]);
+          fma2_v(c, c1, w4.z, w4.w, h1[1][k + 2], h1[1][k + 3]);
         }
-        logit = fmaf(sW2[528 + o], leaky(a + a1), logit);
+        const float w3 = sW2[528 + o];
+        logit0 = fmaf(w3, leaky(a + a1), logit0);
+        logit1 = fmaf(w3, leaky(c + c1), logit1);
       }
-      const float vis = __ldg(rgbvis + (s0 * V + i) * 4 + 3);
-      sLogit[i] = vis == 0.f ? -1e9f : logit;
+      sLogit[i0] = __ldg(rgbvis + (s0 * V + i0) * 4 + 3) == 0.f ? -1e9f : logit0;
+      if (two) sLogit[i1] = __ldg(rgbvis + (s0 * V + i1) * 4 + 3) == 0.f ? -1e9f : logit1;
     }
     cta_sync();
     if (tid < S) {
