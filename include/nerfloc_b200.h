@@ -186,7 +186,8 @@ int nlb_pnp_ransac(const float* p2d, const float* p3d, int64_t M, const float* c
                    size_t scratch_bytes, void* stream);
 
 /* ---- self-test of the tcgen05 building blocks: C[128,128] = A[128,K] * W[128,K]^T, K multiple of 8 <= 64;
- * mode 0 = single-pass tf32, 1 = 3xTF32 (fp32-equivalent) -------------------------------------------------------------- */
+ * mode 0 = single-pass tf32, 1 = 3xTF32 (fp32-equivalent), 2 = 3xTF32 with the A operand in tensor memory;
+ * mode 3 = the warp-level path (mma.sync.m16n8k8 tf32, 3xTF32): C[16,128] = A[16,K] * W[K,128], W k-major, K = 32 or 64 ---- */
 /* clock64() phase stamps of block 0 of the last neighbor_kernel launch (debug aid) */
 int nlb_debug_read_prof(long long* out /*[n]*/, int n /*<= 64: 0..31 neighbour/aggregate, 32..63 ray kernel*/);
 int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C, void* stream);

@@ -98,7 +98,22 @@ tc_test_kernel(const float* __restrict__ A, const float* __restrict__ W, const i
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
+// mode 3: the warp-level path (rows16_mma: 3xTF32 on mma.sync.m16n8k8): C[16][128] = A[0:16][K] * Wt[K][128] (Wt is k-major here)
+template <int K>
+__global__ void __launch_bounds__(256) mma_sync_test_kernel(const float* __restrict__ A, const float* __restrict__ Wt, float* __restrict__ C) {
+  __shared__ float sA[16][K + 4];
+  for (int i = threadIdx.x; i < 16 * K; i += 256) sA[i / K][i % K] = A[i];
+  __syncthreads();
+  rows16_mma<128, K, 1>([&](int r, int, int) { return &sA[r][0]; }, Wt, 128, [&](int r, int c, float v, int) { C[r * 128 + c] = v; });
+}
+
 int launch_tc_test(const float* A, const float* W, int K, int mode, float* C, cudaStream_t st) {
+  if (mode == 3) {
+    if (K == 32) mma_sync_test_kernel<32><<<1, 256, 0, st>>>(A, W, C);
+    else if (K == 64) mma_sync_test_kernel<64><<<1, 256, 0, st>>>(A, W, C);
+    else return set_error("tc_test: mode 3 takes K = 32 or 64");
+    return check_launch("mma_sync_test_kernel");
+  }
   if (K % 8 != 0 || K < 8 || K > 64) return set_error("tc_test: K must be a multiple of 8 in [8, 64]");
   const size_t smem = (size_t)4 * 128 * K * 4;
   cudaError_t e = cudaFuncSetAttribute(tc_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
