@@ -283,33 +283,68 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
       cta_sync();  // sIdx / sD of this tile visible
       if (stamp) g_prof[1] = clock64();
 
+      // per-frame support part of layer 1 for this thread's row (gathered by neighbour id, 64 columns): the first 32 columns
+      // are requested here, a whole attention chunk ahead of their use in E1
+      float4 spre[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) spre[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (cur && sIdx[row] >= 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) spre[j] = __ldg(reinterpret_cast<const float4*>(sc.sup_pre + (size_t)sIdx[row] * W_HID + half * 64 + j * 4));
+      }
+
       if (prev) {
         // ---- A (tile t-1): attention scores + softmax over the K neighbours ------------------------------------------------
-        for (int it2 = 0; it2 < 2; ++it2) {
-          const int i = tid + it2 * NT;  // (p, h, k), k fastest
-          const int p = i >> 5, hd = (i >> 3) & 3, k = i & 7;
-          const float* qv = sQT + (p * 4 + hd) * NB_LDH;
-          const float* kv = sA + (p * 8 + k) * NB_LDH;
-          float a = 0.f, a1 = 0.f;
-#pragma unroll 8
-          for (int c = 0; c < 128; c += 4) {
-            const float4 q4 = *reinterpret_cast<const float4*>(qv + c);
-            const float4 k4 = *reinterpret_cast<const float4*>(kv + c);
-            fma2_v(a, a1, q4.x, q4.y, k4.x, k4.y);
-            fma2_v(a, a1, q4.z, q4.w, k4.z, k4.w);
+        // thread = (sample p, column slice sl of 8): partial dot products of the 4 q~ rows with the 8 neighbour rows over its 8
+        // columns (every q~ / pf element is read from shared memory once), then a transposing butterfly over the 16 lanes of
+        // the sample (16 + 8 + 4 + 2 shuffles) that leaves lane sl with the two scores (head sl >> 2, k = 2 (sl & 3), + 1)
+        {
+          const int p = tid >> 4, sl = tid & 15;
+          float4 q[4][2];
+#pragma unroll
+          for (int hd = 0; hd < 4; ++hd) {
+            q[hd][0] = *reinterpret_cast<const float4*>(sQT + (p * 4 + hd) * NB_LDH + sl * 8);
+            q[hd][1] = *reinterpret_cast<const float4*>(sQT + (p * 4 + hd) * NB_LDH + sl * 8 + 4);
           }
-          a = (a + a1) * 0.17677669529663687f;  // 1/sqrt(d_k = 32)
-          if (k >= K) a = -FLT_MAX;
-          float m = a;
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 k0 = *reinterpret_cast<const float4*>(sA + (p * 8 + k) * NB_LDH + sl * 8);
+            const float4 k1 = *reinterpret_cast<const float4*>(sA + (p * 8 + k) * NB_LDH + sl * 8 + 4);
+#pragma unroll
+            for (int hd = 0; hd < 4; ++hd) {
+              float a = 0.f, a1 = 0.f;
+              fma2_v(a, a1, q[hd][0].x, q[hd][0].y, k0.x, k0.y);
+              fma2_v(a, a1, q[hd][0].z, q[hd][0].w, k0.z, k0.w);
+              fma2_v(a, a1, q[hd][1].x, q[hd][1].y, k1.x, k1.y);
+              fma2_v(a, a1, q[hd][1].z, q[hd][1].w, k1.z, k1.w);
+              v[hd * 8 + k] = a + a1;
+            }
+          }
+#pragma unroll
+          for (int w2 = 16; w2 >= 2; w2 >>= 1) {
+            // of its 2 * w2 values a lane keeps [0, w2) if bit (w2 / 2) of its slice index is clear, [w2, 2 * w2) otherwise, and
+            // adds what the partner lane (which keeps the other half) sends for the same positions
+            const bool up = (sl & (w2 >> 1)) != 0;
+#pragma unroll
+            for (int j = 0; j < w2; ++j) {
+              const float send = up ? v[j] : v[j + w2];
+              const float keep = up ? v[j + w2] : v[j];
+              v[j] = keep + __shfl_xor_sync(0xffffffffu, send, w2 >> 1);
+            }
+          }
+          const int k0i = 2 * (sl & 3);
+          float a0 = v[0] * 0.17677669529663687f, a1 = v[1] * 0.17677669529663687f;  // 1/sqrt(d_k = 32)
+          if (k0i >= K) a0 = -FLT_MAX;
+          if (k0i + 1 >= K) a1 = -FLT_MAX;
+          float m = fmaxf(a0, a1);
           m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
           m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
-          m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
-          const float e = k < K ? expf(a - m) : 0.f;
-          float ssum = e;
+          const float e0 = k0i < K ? expf(a0 - m) : 0.f, e1 = k0i + 1 < K ? expf(a1 - m) : 0.f;
+          float ssum = e0 + e1;
           ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
           ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
-          ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
-          sSc[i] = e / ssum;
+          *reinterpret_cast<float2*>(sSc + 2 * tid) = make_float2(e0 / ssum, e1 / ssum);   // index p * 32 + head * 8 + k
         }
         cta_sync();
         // ---- per-head context = sum_k a_k * point_feature_k (overwrites q~) -----------------------------------------------------
@@ -347,11 +382,22 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         for (int cc = 0; cc < 64; cc += 32) {
           float v[32], lo[32];
           tc::tmem_ld32(trow + NB_TM_D + (uint32_t)(c0 + cc), v);
+          float4 snx[8];
+          if (cc == 0) {   // second half of the row: requested before the first half is consumed
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              snx[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (id >= 0) snx[j] = __ldg(reinterpret_cast<const float4*>(sc.sup_pre + (size_t)id * W_HID + c0 + 32 + j * 4));
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (id >= 0) s4 = __ldg(reinterpret_cast<const float4*>(sc.sup_pre + (size_t)id * W_HID + c0 + cc + j));
+            const float4 s4 = spre[j >> 2];
             v[j] += s4.x; v[j + 1] += s4.y; v[j + 2] += s4.z; v[j + 3] += s4.w;
+          }
+          if (cc == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) spre[j] = snx[j];
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) tc::split_tf32(leaky(v[j]), v[j], lo[j]);
@@ -368,11 +414,17 @@ neighbor_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int
         cta_sync();  // ctx complete
         // (these two stay on the FFMA2 small-M GEMM: the warp-level mma.sync path shares the tensor pipe with the tcgen05
         // layer that runs underneath this chunk and measured 14.1 k vs 11.4 k clk here; it wins for the q / q~ pair below)
-        rows16_gemm<128, 16, 128, 32>([&](int r, int c) { return sQT + (r * 4 + (c >> 5)) * NB_LDH; }, w.wv, 128, sB,
-                         [&](int r, int c, float v) { sO[r * NB_LDH + c] = v; });
+        // a thread's K slice of either weight matrix is one batch of 32 float2 registers: the slice of the output projection is
+        // requested as soon as the FMA loop of the value projection has consumed its own, so that its L2 round trip runs
+        // underneath the K-split reduction and the epilogue
+        float2 wreg[32];
+        rows16_load<128, 128>(w.wv, 128, wreg);
+        rows16_compute<128, 16, 128>(wreg, [&](int r, int c) { return sQT + (r * 4 + (c >> 5)) * NB_LDH; }, sB,
+                                     [&] { rows16_load<128, 128>(w.wfc, 128, wreg); },
+                                     [&](int r, int c, float v) { sO[r * NB_LDH + c] = v; });
         cta_sync();
-        rows16_gemm<128, 16, 128, 32>([&](int r, int) { return sO + r * NB_LDH; }, w.wfc, 128, sB,
-                         [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v + sAgg[r * NB_LDH + c]; });
+        rows16_compute<128, 16, 128>(wreg, [&](int r, int) { return sO + r * NB_LDH; }, sB, [] {},
+                                     [&](int r, int c, float v) { sQ[r * NB_LDH + c] = v + sAgg[r * NB_LDH + c]; });
       }
       cta_sync();  // sAgg of tile t-1 is dead
       if (cur) {

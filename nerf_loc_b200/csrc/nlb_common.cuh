@@ -230,8 +230,10 @@ __device__ __forceinline__ void tile_gemm_frag(const ASrc A, const int rows, con
 // barrier per K-tile) and the 256 threads split K in 2*NT/COLS slices that are reduced through `red`
 // (>= (2*NT/COLS)*R*COLS floats of shared scratch).  Many K slices keep the number of dependent L2 round trips per thread
 // small - the loop is latency bound.  arow(r, c) -> shared-memory pointer to row r as seen by column c (c even).
-template <int COLS, int R, int K, int KB, class ARow, class Epi>
-__device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__ Wt, const int ldb, float* red, Epi epi) {
+struct NoMid { __device__ __forceinline__ void operator()() const {} };
+// `mid()` runs right after the FMA loop, when the weight registers are dead (see rows16_load / rows16_compute below).
+template <int COLS, int R, int K, int KB, class ARow, class Epi, class Mid = NoMid>
+__device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__ Wt, const int ldb, float* red, Epi epi, Mid mid = Mid()) {
   constexpr int KSPLIT = 2 * NT / COLS;
   constexpr int KPER = K / KSPLIT;                 // k per thread, multiple of 4
   constexpr int NBATCH = (KPER + KB - 1) / KB;     // weight batches: batch n+1 is requested before the FMAs of batch n
@@ -273,6 +275,52 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
       for (int j = 0; j < KB; ++j) b[j] = bn[j];
     }
   }
+  mid();
+  cta_sync();  // `red` may alias a buffer an earlier phase still reads
+#pragma unroll
+  for (int r = 0; r < R; ++r) *reinterpret_cast<float2*>(red + (ks * R + r) * COLS + c) = make_float2(acc[r][0], acc[r][1]);
+  cta_sync();
+  for (int i = tid; i < R * COLS; i += NT) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < KSPLIT; ++q) v += red[q * R * COLS + i];
+    epi(i / COLS, i % COLS, v);
+  }
+}
+
+// Split form of rows16_gemm for the case where a thread's whole K slice is ONE batch of weights (K / KSPLIT float2 registers):
+// rows16_load requests the slice, rows16_compute runs the FMA loop, calls `mid()` (the weights are dead by then: the caller
+// uses it to request the NEXT product's slice, whose L2 round trip then overlaps the reduction and the epilogue) and reduces.
+template <int COLS, int K>
+__device__ __forceinline__ void rows16_load(const float* __restrict__ Wt, const int ldb, float2 (&b)[K / (2 * NT / COLS)]) {
+  constexpr int KPER = K / (2 * NT / COLS);
+  const int tid = threadIdx.x;
+  const float* wp = Wt + (size_t)((tid / (COLS / 2)) * KPER) * ldb + (tid % (COLS / 2)) * 2;
+#pragma unroll
+  for (int j = 0; j < KPER; ++j) b[j] = __ldg(reinterpret_cast<const float2*>(wp + (size_t)j * ldb));
+}
+template <int COLS, int R, int K, class ARow, class Mid, class Epi>
+__device__ __forceinline__ void rows16_compute(float2 (&b)[K / (2 * NT / COLS)], ARow arow, float* red, Mid mid, Epi epi) {
+  constexpr int KSPLIT = 2 * NT / COLS;
+  constexpr int KPER = K / KSPLIT;
+  static_assert(K % KSPLIT == 0 && KPER % 4 == 0, "rows16_compute: bad K split");
+  const int tid = threadIdx.x;
+  const int c = (tid % (COLS / 2)) * 2, ks = tid / (COLS / 2);
+  float acc[R][2];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    acc[r][0] = 0.f; acc[r][1] = 0.f;
+    const float* ap = arow(r, c) + ks * KPER;
+#pragma unroll
+    for (int g = 0; g < KPER / 4; ++g) {
+      const float4 a = *reinterpret_cast<const float4*>(ap + 4 * g);
+      fma2_s(acc[r][0], acc[r][1], a.x, b[4 * g].x, b[4 * g].y);
+      fma2_s(acc[r][0], acc[r][1], a.y, b[4 * g + 1].x, b[4 * g + 1].y);
+      fma2_s(acc[r][0], acc[r][1], a.z, b[4 * g + 2].x, b[4 * g + 2].y);
+      fma2_s(acc[r][0], acc[r][1], a.w, b[4 * g + 3].x, b[4 * g + 3].y);
+    }
+  }
+  mid();
   cta_sync();  // `red` may alias a buffer an earlier phase still reads
 #pragma unroll
   for (int r = 0; r < R; ++r) *reinterpret_cast<float2*>(red + (ks * R + r) * COLS + c) = make_float2(acc[r][0], acc[r][1]);
