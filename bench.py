@@ -32,7 +32,10 @@ F_KERNEL = {"aggregate": 201e3 + 176e3 * V / 8, "neighbor": 1108e3 + 1081e3 + 26
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture (profiles/), bytes;
 # None until a capture of the current build exists
-TRAFFIC = {"aggregate": 4.13e9, "neighbor": 2.64e9, "ray": 4.08e9, "knn": 0.18e9}  # profiles/r1f_ncu_metrics.json, per launch of 18,944 rays
+# profiles/r1i_ncu_metrics.json: one launch each on 37,888 rays; kept per ray and scaled to the rays one launch of the timed run covers
+TRAFFIC_RAYS = 37888
+TRAFFIC = {"aggregate": 0.041086e9 + 8.021647e9, "neighbor": 2.832573e9 + 2.443556e9, "ray": 10.319115e9 + 0.053280e9,
+           "knn": 0.004504e9 + 0.320801e9}
 
 
 def peaks():
@@ -359,7 +362,7 @@ def run_b200(args):
         "config": {"workload": "640x480 query, 128 samples/ray, 8 ref views, full conditional render (configs[1])",
                    "rays_per_step": R_total, "samples_per_ray": S, "views": V, "support_points": int(model.support_neural_points["fine"]["xyz"].shape[0]),
                    "chunk_rays": args.chunk,
-                   "mma_mode": "3xTF32 tcgen05 (neighbour MLP with the A operand in tensor memory, RayUnet, feat/blend layers) + fp32 FFMA2 (aggregator, small per-sample GEMMs)",
+                   "mma_mode": "3xTF32 tcgen05 (neighbour MLP with the A operand in tensor memory, RayUnet, feat/blend layers) + 3xTF32 mma.sync (visibility decoder, q / q~ projections) + fp32 FFMA2 (rest of the aggregator, small per-sample GEMMs)",
                    "l2": "working set per step (scene 294 MB + >1 GB of per-chunk intermediates) exceeds the 126 MB L2",
                    "parallelism": f"ray-shard x{world}" + ("" if world == 1 else (" + all-gather of feat[R,192] fused into the ray kernel epilogue (peer stores over NVLink, symmetric memory)" if exch is not None else " + NCCL all-gather of feat[R,192] (symmetric memory unavailable: " + exch_note + ")")),
                    "per_frame_setup_ms": setup_ms},
@@ -369,7 +372,8 @@ def run_b200(args):
         "clocks": sampler.summary(),
         "kernels_ms_per_step": {n: kern[n]["ms"] for n in names},
         "roofline": {"bound": "tensor", "kernel": dom + "_kernel", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s",
-                     "frac": ach / tf_peak, "traffic": TRAFFIC.get(dom), "peak_source": which + " bf16 sustained",
+                     "frac": ach / tf_peak,
+                     "traffic": TRAFFIC[dom] / TRAFFIC_RAYS * Rl / max(1, kern[dom]["launches"]), "peak_source": which + " bf16 sustained",
                      "whole_step_achieved": F_SAMPLE * R_total * S / (ms_step * 1e-3) / 1e12,
                      "per_kernel": {n: {"achieved": (F_KERNEL[n] * samples_rank / (kern[n]["ms"] * 1e-3) / 1e12) if kern[n]["ms"] > 0 else 0.0,
                                         "frac": (F_KERNEL[n] * samples_rank / (kern[n]["ms"] * 1e-3) / 1e12 / tf_peak) if kern[n]["ms"] > 0 else 0.0}
