@@ -7,12 +7,12 @@ from oracle import matcher_oracle as MO
 from oracle import nerfloc_oracle as O
 from oracle.make_golden import matcher_inputs
 from nerf_loc_b200 import params, synthetic as syn
-from tests.common import RENDER_CASES, golden, relerr, render_inputs
+from tests.common import ORACLE_CASES, golden, relerr, render_inputs
 
 TOL = 2e-5  # fp32 re-association noise between two CPU evaluations of the same algorithm
 
 
-@pytest.mark.parametrize("name", list(RENDER_CASES))
+@pytest.mark.parametrize("name", list(ORACLE_CASES))
 def test_render_oracle_vs_golden(name):
     S, sd, sc, scene, ro, rd = render_inputs(name)
     g = golden(name)
