@@ -75,7 +75,7 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int w, int h, bool
 // per map a bilinear footprint is stored ready to use: 4 pixel indices (y * width + x, clamped into the map; as int bits) and
 // 4 weights (0 for taps that do not contribute) - computed once per row in phase 1 instead of once per lane in every gather
 enum { RI_TF = 0, RI_TI = 8, RI_TV = 16, RI_DEPTH = 24, RI_VALID, RI_MASK, RI_VIS, RI_DD, RI_W,
-       RI_RD0, RI_RD1, RI_RD2, RI_RD3, RI_N = 36 };
+       RI_RD0, RI_RD1, RI_RD2, RI_RD3, RI_V, RI_P, RI_N = 36 };   // RI_V / RI_P: view and sample index of the row (int bits)
 
 __device__ __forceinline__ void store_taps(float* slot, const Taps& t, int w, int h) {
   const int x0 = min(max(t.x0, 0), w - 1), x1 = min(max(t.x0 + 1, 0), w - 1);
@@ -186,6 +186,9 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       const float* cam = sc.cams + v * 32;
       for (int job = part; job < 3; job += PARTS) {
         if (job == 0) {
+          // the (sample, view) split of the row index is taken once here: a runtime division per row in each of the later
+          // per-row loops was 11 % of the kernel's instructions
+          ri[RI_V] = __int_as_float(v); ri[RI_P] = __int_as_float(p);
           if (v == 0) { sPt[p * 4] = x; sPt[p * 4 + 1] = y; sPt[p * 4 + 2] = z; }
           // IBRNet convention
           const float ph0 = fmaf(cam[2], z, fmaf(cam[1], y, cam[0] * x)) + cam[3];
@@ -258,7 +261,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       for (int t = 0; t < 4; ++t) { q[u][t] = 0.f; wgt[u][t] = 0.f; }
       if (r < rows) {
         const float* ri = sRI + r * RI_N;
-        const int v = r % V;
+        const int v = __float_as_int(ri[RI_V]);
         const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TV);
         const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TV + 4);
         const float* base = sc.vis + ((size_t)v * sc.vh * sc.vw) * C_VIS + lane;
@@ -506,7 +509,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         }
         if (r < rows) {
           const float* ri = sRI + r * RI_N;
-          const int v = r % V;
+          const int v = __float_as_int(ri[RI_V]);
           const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TF);
           const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TF + 4);
           const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
@@ -558,7 +561,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           c.x += __shfl_xor_sync(0xffffffffu, c.x, 2); c.y += __shfl_xor_sync(0xffffffffu, c.y, 2); c.z += __shfl_xor_sync(0xffffffffu, c.z, 2);
           c.x = __shfl_sync(0xffffffffu, c.x, 0); c.y = __shfl_sync(0xffffffffu, c.y, 0); c.z = __shfl_sync(0xffffffffu, c.z, 0);
           const float* ri = sRI + r * RI_N;
-          const int p = r / V, v = r - p * V;
+          const int p = __float_as_int(ri[RI_P]), v = __float_as_int(ri[RI_V]);
           if (lane == 0) {
             frow[0] = c.x; frow[1] = c.y; frow[2] = c.z;
             if (rgbvis_out) __stcs(reinterpret_cast<float4*>(rgbvis_out + ((n0 + p) * V + v) * 4), make_float4(c.x, c.y, c.z, ri[RI_VIS]));

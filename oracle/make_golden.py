@@ -24,9 +24,9 @@ RENDER_CASES = {
     "render_s16": (16, 64, 96, 3, 24, 1234, 1234),
     "render_s64": (64, 64, 96, 4, 12, 4321, 77),
     "render_s192": (192, 64, 96, 3, 6, 555, 99),   # long rays (BASELINE configs[3]: 192 samples per ray)
-    # the metric's own configuration (8 reference views, 128 samples per ray) on a small image: pins the ORACLE there; the CUDA
-    # path at this shape is held to the oracle by test_gpu_render / bench.py's parity_on_sample (tests/common.py ORACLE_CASES)
+    # the metric's own configuration (8 reference views, 128 samples per ray) on a small image
     "render_v8_s128": (128, 64, 96, 8, 4, 2024, 8),
+    "render_v16_s32": (32, 64, 96, 16, 6, 777, 21),   # the upper end of the supported view count
 }
 
 

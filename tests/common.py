@@ -13,12 +13,13 @@ RENDER_CASES = {
     "render_s16": (16, 64, 96, 3, 24, 1234, 1234),
     "render_s64": (64, 64, 96, 4, 12, 4321, 77),
     "render_s192": (192, 64, 96, 3, 6, 555, 99),   # long rays (BASELINE configs[3]: 192 samples per ray)
+    "render_v8_s128": (128, 64, 96, 8, 4, 2024, 8),   # the metric's configuration: 8 views, 128 samples per ray
+    "render_v16_s32": (32, 64, 96, 16, 6, 777, 21),   # the upper end of the supported view count
 }
 
 
-# cases that pin the oracle only (CPU suite); the -m gpu tests iterate over RENDER_CASES
+# every case pins the oracle (CPU suite) AND the CUDA path (-m gpu tests iterate over RENDER_CASES)
 ORACLE_CASES = dict(RENDER_CASES)
-ORACLE_CASES["render_v8_s128"] = (128, 64, 96, 8, 4, 2024, 8)   # the metric's configuration: 8 views, 128 samples per ray
 
 
 def relerr(a, b):

@@ -122,6 +122,34 @@ def test_render_rays_vs_golden(name):
     assert torch.equal(out["mask"].cpu(), g["mask"])
 
 
+def test_render_v8_s128_multi_chunk_vs_oracle():
+    """The metric's shape (8 views: the fused view-weight path of the aggregator; 128 samples: a full 128-row tensor-core tile
+    per ray) over several chunks of the internal chunk loop, with a ragged last chunk, against the oracle."""
+    name = "render_v8_s128"
+    S, H, W, V, _, wseed, sseed = RENDER_CASES[name]
+    sc = syn.make_scene(H, W, V, seed=sseed)
+    ro, rd = syn.pixel_rays(sc["K"], sc["pose"], syn.random_pixels(H, W, 21))
+    model, sd = cuda_model(S, wseed)
+    data = setup_frame(model, sc)
+    model.chunk_rays = 8
+    rays = {"rays_o": ro.cuda(), "rays_d": rd.cuda(), "depth_range": data["depth_range"][0]}
+    out = model.render_rays(data, rays, _debug=True)
+    sup = oracle_support(sd, sc)
+    with torch.no_grad():
+        ref = O.render_rays(sd, oracle_scene(sc), sup["fine"], sc["feat_fine_src"].permute(0, 3, 1, 2), ro, rd, sc["pose"], S,
+                            return_debug=True)
+    report = {k: relerr(out[k].cpu(), ref[k]) for k in ("feature_agg", "sigma", "rgb", "depth", "weights",
+                                                         "depth_uncertainty", "feat")}
+    print(report)
+    for k, v in report.items():
+        assert v < TOL, (k, report)
+    assert torch.equal(out["mask"].cpu(), ref["mask"])
+    model.chunk_rays = 21
+    one = model.render_rays(data, rays)
+    for k in ("rgb", "depth", "weights", "depth_uncertainty", "feat", "mask"):
+        assert torch.equal(one[k], out[k]), k
+
+
 def test_render_chunking_is_invisible():
     name = "render_s16"
     S, sd_cpu, sc, scene, ro, rd = render_inputs(name)
