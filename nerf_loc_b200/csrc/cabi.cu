@@ -1,5 +1,6 @@
 // extern "C" surface of libnerfloc_b200.so (declared in include/nerfloc_b200.h).
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "../../include/nerfloc_b200.h"
 #include "match_kernels.h"
@@ -110,7 +111,7 @@ struct Carver {
 }  // namespace nlb
 
 namespace nlb { int launch_tc_test(const float* A, const float* W, int K, int mode, float* C, cudaStream_t st); }
-namespace nlb { int read_prof(long long* out, int n); int read_prof_ray(long long* out, int n); }
+namespace nlb { int read_prof(long long* out, int n); int read_prof_ray(long long* out, int n); int read_prof_ray2(long long* out, int n); }
 using namespace nlb;
 
 extern "C" {
@@ -263,6 +264,7 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
   const int64_t nchunks = (R + chunk_rays - 1) / chunk_rays;
+  static const bool ray_v1 = getenv("NLB_RAY_V1") != nullptr;   // A/B switch: the one-ray-per-CTA 3xTF32 kernel of render_ray.cu
   // The exact KNN search is a register-light, shared-memory-free tree walk; the ray kernel is one latency-bound CTA per SM that
   // leaves a third of the register file idle.  With more than one chunk the search of chunk i+1 therefore runs on a
   // low-priority side stream underneath the ray kernel of chunk i (events order it after neighbor(i), which frees the buffer
@@ -310,7 +312,11 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
     if (launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)) { rc_err = 1; break; }
     if (overlap) cudaEventRecord(ev_nb, st);
     prof.mark();
-    if (S <= 128) {
+    if (S <= 128 && !ray_v1) {
+      if (launch_ray2(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
+                      weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
+                      dbg_sigma ? dbg_sigma + r0 * S : nullptr, peers_at(peers, feat_row0 + r0), st)) { rc_err = 1; break; }
+    } else if (S <= 128) {
       if (launch_ray(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                      weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
                      dbg_sigma ? dbg_sigma + r0 * S : nullptr, peers_at(peers, feat_row0 + r0), st)) { rc_err = 1; break; }
@@ -437,6 +443,10 @@ int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C,
   return launch_tc_test(A, W, K, mode, C, (cudaStream_t)stream);
 }
 
-int nlb_debug_read_prof(long long* out, int n) { return n > 32 ? read_prof_ray(out + 32, n - 32) || read_prof(out, 32) : read_prof(out, n); }
+int nlb_debug_read_prof(long long* out, int n) {
+  if (n <= 32) return read_prof(out, n);
+  const int e = getenv("NLB_RAY_V1") ? read_prof_ray(out + 32, n - 32) : read_prof_ray2(out + 32, n - 32);
+  return e || read_prof(out, 32);
+}
 
 }  // extern "C"

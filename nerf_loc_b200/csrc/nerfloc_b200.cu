@@ -5,6 +5,7 @@
 #include "neighbor_tc.cu"
 #include "render_point.cu"
 #include "render_ray.cu"
+#include "render_ray2.cu"
 #include "render_ray_long.cu"
 #include "hier_sample.cu"
 #include "match.cu"

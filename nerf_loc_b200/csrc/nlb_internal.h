@@ -62,6 +62,10 @@ struct RenderW {
   const float* tcu[7][3];       // tensor-core operands of the RayUnet layers (see pack.cu)
   const float* tcu_x2[3];       // conv_out, x2 part (K = 32)
   const float *tc_bl1a, *tc_ft1;
+  // bf16x3 copies for the pair kernel (render_ray2.cu): per layer and TAP (0, 1, 2) the [Cout x Cin] operand as K-tiles of
+  // [hi | lo] weight tiles (tc_bf16.cuh); conv_out keeps its 160 input channels in one block (K-tiles 0-3: x, 4: x2)
+  const float* tb_u[7][3];
+  const float *tb_bl1a, *tb_ft1;
   const float *sig_w, *sig_b;   // [128], [1]
   const float *ft1, *ft1_b;     // [128][128], [128]
   const float *ft2, *ft2_b;     // [128][192], [192]

@@ -77,6 +77,11 @@ static RenderW layout(const float* base, int S, size_t* total) {
     }
   w.tc_bl1a = a.take(2 * 32 * 128);
   w.tc_ft1 = a.take(2 * 128 * 128);
+  // bf16 hi | lo: 2 planes x 2 bytes = one float per weight
+  for (int l = 0; l < 7; ++l)
+    for (int t = 0; t < 3; ++t) w.tb_u[l][t] = a.take((size_t)UN_COUT[l] * UN_CIN[l]);
+  w.tb_bl1a = a.take(32 * 128);
+  w.tb_ft1 = a.take(128 * 128);
   w.sig_w = a.take(128); w.sig_b = a.take(1);
   w.ft1 = a.take(128 * 128); w.ft1_b = a.take(128);
   w.ft2 = a.take(128 * 192); w.ft2_b = a.take(192);
@@ -148,6 +153,27 @@ __global__ void pack_tcb_kernel(float* dst, const float* __restrict__ src, int N
   dst[base + (size_t)N * ktile + off] = lo;
 }
 
+// bf16x3 B operand (tc_bf16.cuh): W [N][K] -> per K-tile of `ktile` columns: hi tile then lo tile, each in the weight-tile
+// layout (8-row x 16-byte core matrices, adjacent in K contiguous, 8-row groups ktile*16 bytes apart); hi = bf16(x), lo = bf16(x - hi)
+__global__ void pack_tcb16_kernel(uint16_t* dst, const float* __restrict__ src, int N, int K, int src_ld, int src_off, int src_ks,
+                                  int ktile) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const int n = i / K, k = i % K;
+  const float x = src[(size_t)n * src_ld + src_off + (size_t)k * src_ks];
+  const uint32_t xb = __float_as_uint(x);
+  // round to nearest even by hand (identical to __float2bfloat16_rn for finite values)
+  const uint32_t hb = (xb + 0x7FFFu + ((xb >> 16) & 1u)) >> 16;
+  const float r = x - __uint_as_float(hb << 16);
+  const uint32_t rb = __float_as_uint(r);
+  const uint32_t lb = (rb + 0x7FFFu + ((rb >> 16) & 1u)) >> 16;
+  const int kt = k / ktile, kl = k % ktile;
+  const size_t base = (size_t)kt * (2 * N * ktile);
+  const size_t off = (size_t)(n / 8) * (ktile * 8) + (size_t)(kl / 8) * 64 + (n % 8) * 8 + (kl % 8);
+  dst[base + off] = (uint16_t)hb;
+  dst[base + (size_t)N * ktile + off] = (uint16_t)lb;
+}
+
 namespace {
 struct Packer {
   const float* const* p;
@@ -165,6 +191,11 @@ struct Packer {
     const int n = N * Kp;
     pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv, src_ks,
                                                      2048 / N, perm);
+  }
+  void tcb16(const float* dst, int src, int N, int K, int src_ld, int src_off, int src_ks, int ktile) {
+    const int n = N * K;
+    pack_tcb16_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<uint16_t*>(const_cast<float*>(dst)), p[src], N, K, src_ld,
+                                                       src_off, src_ks, ktile);
   }
   void conv(const float* dst, int src, int Cin, int Cout, int ntaps, int t0, int t1, int t2, bool tr) {
     const int n = ntaps * Cin * Cout;
@@ -252,6 +283,19 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
   }
   k.tcb(w.tc_bl1a, BL0_W, 32, 128, 328, 0, 128);
   k.tcb(w.tc_ft1, FT0_W, 128, 128, 128, 0, 128);
+  if (S > 0) {
+    // K-tile extents as render_ray2.cu's GEMM list uses them (a tile is at most 16 KB and never straddles two source tiles)
+    static const int KT16[7] = {64, 32, 32, 32, 64, 64, 32};
+    for (int l = 0; l < 7; ++l) {
+      const int b = UNET + 4 * l, ci = UN_CIN[l], co = UN_COUT[l];
+      for (int t = 0; t < 3; ++t) {
+        if (UN_TR[l]) k.tcb16(w.tb_u[l][t], b, co, ci, 3, t, co * 3, KT16[l]);    // ConvTranspose1d weight [ci][co][3]
+        else k.tcb16(w.tb_u[l][t], b, co, ci, ci * 3, t, 3, KT16[l]);             // Conv1d weight [co][ci][3]
+      }
+    }
+  }
+  k.tcb16(w.tb_bl1a, BL0_W, 32, 128, 328, 0, 1, 128);
+  k.tcb16(w.tb_ft1, FT0_W, 128, 128, 128, 0, 1, 32);
   k.c(w.sig_w, SIG_W, 128);  k.c(w.sig_b, SIG_B, 1);
   k.t(w.ft1, FT0_W, 128, 128, 128, 0, 128);  k.c(w.ft1_b, FT0_B, 128);
   k.t(w.ft2, FT2_W, 128, 192, 128, 0, 128);  k.c(w.ft2_b, FT2_B, 192);

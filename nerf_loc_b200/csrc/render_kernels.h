@@ -37,6 +37,12 @@ int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_
                float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
                const FeatPeers& peers, cudaStream_t st);
 
+// pair kernel (render_ray2.cu): two rays per CTA, bf16x3 tcgen05; same contract as launch_ray
+int launch_ray2(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
+                const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
+                float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
+                const FeatPeers& peers, cudaStream_t st);
+
 // hierarchical sampling (hier_sample.cu)
 int launch_hier_sample(const SceneDev& sc, const RenderW& w, const float* center_host, const float* dirs, int64_t R,
                        const float* z_coarse, const float* z_reg, int S, const float* u, int NI, float* z_out,

@@ -33,9 +33,12 @@ for i in range(8):
 print("agg total", v[24] - v[16])
 print("decoder detail: wait weights/sX", v[25]-v[18], "dec1", v[26]-v[25], "dec2", v[27]-v[26], "heads+vis", v[19]-v[27])
 
-rn = ["load x", "blend weights + wait blend GEMM", "blend MLP + softmax", "wait conv1", "epi conv1", "wait conv2", "epi conv2", "wait conv3", "epi conv3",
-      "wait tconv3", "epi tconv3", "wait tconv2", "epi tconv2", "wait tconv1", "epi tconv1 + reload x", "wait conv_out", "epi conv_out", "composite", "feat"]
+rn = ["load x (both rays)", "blend weights + wait blend GEMM", "blend MLP + softmax (both rays)", "wait conv1", "epi conv1", "wait conv2",
+      "epi conv2", "wait conv3", "epi conv3", "wait tconv3", "epi tconv3", "wait tconv2", "epi tconv2", "wait tconv1",
+      "epi tconv1 + reload x", "wait conv_out", "epi conv_out", "composite", "feat"]
 rv = v[32:]
-for i in range(18):
+if os.environ.get("NLB_RAY_V1"):
+    rn = rn[:18]
+for i in range(len(rn)):
     print(f"ray {rn[i]:34s} {rv[i+1]-rv[i]:8d} clk")
-print("ray total", rv[18] - rv[0])
+print("ray total (per pair of rays unless NLB_RAY_V1)", rv[len(rn)] - rv[0])
