@@ -262,14 +262,15 @@ def run_b200(args):
     # ranks' gathered [R,192] matrix (symmetric memory, peer stores over NVLink); a device-side barrier closes the step
     exch, exch_note = None, ""
     if world > 1:
+        # agree on the path BEFORE the collective allocation: a rank that failed alone inside the rendezvous would hang the rest
         try:
-            exch = FeatExchange(R_total, dev)
+            import torch.distributed._symmetric_memory  # noqa: F401
             ok = torch.ones(1, device=dev)
-        except Exception as e:  # symmetric memory not available on this box: one NCCL all-gather per step instead
-            exch, ok, exch_note = None, torch.zeros(1, device=dev), f"{type(e).__name__}"
+        except Exception as e:  # symmetric memory not available in this build: one NCCL all-gather per step instead
+            ok, exch_note = torch.zeros(1, device=dev), f"{type(e).__name__}"
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
-        if float(ok.item()) == 0.0:
-            exch = None
+        if float(ok.item()) != 0.0:
+            exch = FeatExchange(R_total, dev)
     from nerf_loc_b200.distributed import all_gather_rows
 
     def step_device():
@@ -279,7 +280,7 @@ def run_b200(args):
             if world > 1:
                 out["feat_all"] = all_gather_rows(out["feat"], R_total)
             return out
-        out = model.render_rays(data, rays, _feat_peers=(exch.ptrs, lo))
+        out = model.render_rays(data, rays, _feat_peers=(exch.begin_frame(), lo))
         exch.barrier()
         out["feat_all"] = exch.gathered()
         return out
@@ -294,7 +295,7 @@ def run_b200(args):
             if world > 1:
                 all_gather_rows(out["feat"], R_total)
         else:
-            out = model.render_rays(data, rays, _feat_peers=(exch.ptrs, lo))
+            out = model.render_rays(data, rays, _feat_peers=(exch.begin_frame(), lo))
             exch.barrier()
         nbytes = 0
         for k, v in out.items():

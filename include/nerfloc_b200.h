@@ -190,6 +190,10 @@ int nlb_pnp_ransac(const float* p2d, const float* p3d, int64_t M, const float* c
  * mode 3 = the warp-level path (mma.sync.m16n8k8 tf32, 3xTF32): C[16,128] = A[16,K] * W[K,128], W k-major, K = 32 or 64 ---- */
 /* clock64() phase stamps of block 0 of the last neighbor_kernel launch (debug aid) */
 int nlb_debug_read_prof(long long* out /*[n]*/, int n /*<= 64: 0..31 neighbour/aggregate, 32..63 ray kernel*/);
+/* Test hook: the ray-sample K = 8 search the render path runs per chunk (sample n = r * S + s at o_r + d_r * z_s; results as
+ * int32 indices / squared distances [R * S, 8]); same definition as nlb_knn_query (ops/knn/src/knn_cpu.cpp:13-64). */
+int nlb_debug_knn_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, int64_t z_stride,
+                       const float* sup_geo /*[M,8]*/, int64_t R, int S, int32_t* idx, float* dist2, void* stream);
 int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C, void* stream);
 
 #ifdef __cplusplus

@@ -54,6 +54,8 @@ SIGNATURES = {
     "nlb_hierarchical_depths": (c_int, [ctypes.POINTER(NlbScene), c_void_p, c_int, c_void_p, c_void_p, c_int64, c_void_p,
                                         c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nlb_debug_read_prof": (c_int, [c_void_p, c_int]),
+    "nlb_debug_knn_rays": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p, c_void_p,
+                                   c_void_p]),
     "nlb_debug_tc_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "nlb_profile_enable": (None, [c_int]),
     "nlb_profile_read": (c_int, [c_void_p, c_void_p, c_int]),

@@ -182,6 +182,7 @@ class ConditionalNeRF(nn.Module):
         self._support_points = None
         self._packed = None
         self._packed_key = None
+        self._packed_src = None
         self._frame = {}
         self.chunk_rays = 37888  # rays per kernel wave inside nlb_render_rays (148 SMs x 256; 2.3 KB of scratch per sample)
 
@@ -196,12 +197,19 @@ class ConditionalNeRF(nn.Module):
         self._frame = {}
 
     # ---- weights ----------------------------------------------------------------------------------------------------------
+    def _apply(self, fn, *args, **kwargs):
+        # .cuda() / .to() replace the parameter tensors: drop the cached references to the old ones
+        self._packed_src = None
+        return super()._apply(fn, *args, **kwargs)
+
     def packed_weights(self):
         """Flat device buffer in the kernels' layout; re-packed when any parameter changed."""
         L = _lib.load()
-        sd = self.state_dict()
-        names = list(params.conditional_nerf_shapes(self.n_samples).keys())
-        tensors = [sd[n] for n in names]
+        if self._packed_src is None:
+            # parameter tensors in the packer's order, looked up once per model (state_dict() + ~100 keys per call otherwise)
+            sd = self.state_dict()
+            self._packed_src = [sd[n] for n in params.conditional_nerf_shapes(self.n_samples).keys()]
+        tensors = self._packed_src
         key = tuple((t.data_ptr(), t._version) for t in tensors)
         if self._packed is None or key != self._packed_key:
             dev = tensors[0].device
@@ -342,7 +350,14 @@ class ConditionalNeRF(nn.Module):
             self.build_support_neural_points(data)
         level = _level
         if level is None:
-            level = 'fine' if support_neural_points is self.support_neural_points['fine'] else 'coarse'
+            if support_neural_points is self.support_neural_points['fine']:
+                level = 'fine'
+            elif support_neural_points is None or support_neural_points is self.support_neural_points['coarse']:
+                level = 'coarse'
+            else:
+                raise ValueError("query: support_neural_points must be self.support_neural_points['coarse'] or ['fine'] of the "
+                                 "current frame (the kernels read the per-frame precomputes of that level); pass _level to "
+                                 "name the level explicitly")
         sc, maps, sup = self._level_scene(data, level)
         pts = _lib.f32(xyz)
         N, dev = pts.shape[0], pts.device

@@ -76,6 +76,12 @@ struct Prof {
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
+// A/B switch: the folded-attention neighbour kernel of neighbor_tc.cu instead of neighbor2.cu
+static bool nb_v1() {
+  static const bool v = getenv("NLB_NB_V1") != nullptr;
+  return v;
+}
+
 static FeatPeers peers_at(FeatPeers p, int64_t row0) {
   p.row0 = row0;
   return p;
@@ -111,7 +117,7 @@ struct Carver {
 }  // namespace nlb
 
 namespace nlb { int launch_tc_test(const float* A, const float* W, int K, int mode, float* C, cudaStream_t st); }
-namespace nlb { int read_prof(long long* out, int n); int read_prof_ray(long long* out, int n); int read_prof_ray2(long long* out, int n); }
+namespace nlb { int read_prof(long long* out, int n); int read_prof_ray(long long* out, int n); int read_prof_ray2(long long* out, int n); int read_prof_nb2(long long* out, int n); }
 using namespace nlb;
 
 extern "C" {
@@ -159,7 +165,8 @@ int nlb_blend_prepare(const float* packed_weights, int S, const float* featmaps,
 
 size_t nlb_query_scratch_bytes(int64_t N, int K) {
   if (N < 1) N = 1;
-  return align256((size_t)N * K * 4) + align256((size_t)N * K * 4) + align256((size_t)N * W_HID * 4) + 1024;
+  return align256((size_t)N * K * 4) + align256((size_t)N * K * 4) + align256((size_t)N * W_HID * 4) +
+         align256(neighbor2_scratch_floats(N) * 4) + 1024;
 }
 
 int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S, const float* xyz,
@@ -175,13 +182,15 @@ int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S,
   int* idx = knn_idx ? knn_idx : c.take<int>((size_t)N * K);
   float* d2 = knn_d2 ? knn_d2 : c.take<float>((size_t)N * K);
   float* agg = aggregated ? aggregated : c.take<float>((size_t)N * W_HID);
+  float* nb2 = c.take<float>(neighbor2_scratch_floats(N));
   if (!c.ok) return set_error("nlb_query_points: scratch too small (see nlb_query_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
   PointSrc ps{xyz, direction, nullptr, nullptr, nullptr, 1, 0};
   if (knn_query(sc.knn, xyz, N, K, nullptr, idx, d2, st)) return 1;
   if (launch_aggregate(sc, w, ps, N, 0, agg, nullptr, nullptr, nullptr, mv_feature, mv_visibility, st)) return 1;
-  return launch_neighbor(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, st);
+  if (nb_v1()) return launch_neighbor(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, st);
+  return launch_neighbor2(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, nb2, st);
 }
 
 int nlb_aggregate_points(const nlb_scene* scene, const float* packed_weights, int S, const float* xyz, int64_t N,
@@ -217,7 +226,7 @@ size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
   const size_t slabs = S > 128 ? align256((size_t)RL_MAX_GRID * ray_long_slab_floats(S) * 4) : 0;
   // KNN lists are double buffered: the search of chunk i+1 runs on a side stream underneath the ray kernel of chunk i
   return align256(n * KNN_K * 4) * 4 + align256(n * W_HID * 4) * 2 + align256(n * V * 32 * 4) + align256(n * V * 16) +
-         align256(n) + slabs + 2048;
+         align256(n) + align256(neighbor2_scratch_floats((int64_t)n) * 4) + slabs + 2048;
 }
 
 int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays) {
@@ -259,6 +268,7 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
   float* partial = c.take<float>(n * V * 32);
   float* rgbvis = c.take<float>(n * V * 4);
   unsigned char* nvalid = c.take<unsigned char>(n);
+  float* nb2 = c.take<float>(neighbor2_scratch_floats((int64_t)n));
   float* slabs = S > 128 ? c.take<float>((size_t)RL_MAX_GRID * ray_long_slab_floats(S)) : nullptr;
   if (!c.ok) return set_error("nlb_render_rays: scratch too small (see nlb_render_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
@@ -309,7 +319,8 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
     if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, st)) { rc_err = 1; break; }
     prof.mark();
     if (overlap) cudaStreamWaitEvent(st, ev_knn[i & 1], 0);
-    if (launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)) { rc_err = 1; break; }
+    if (nb_v1() ? launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)
+                : launch_neighbor2(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, nb2, st)) { rc_err = 1; break; }
     if (overlap) cudaEventRecord(ev_nb, st);
     prof.mark();
     if (S <= 128 && !ray_v1) {
@@ -438,6 +449,12 @@ int nlb_fine_match(const float* packed, int C, const float* f0, const float* f1,
   return launch_fine_match(match_weights_view(packed, C), f0, f1, Mm, mkps2d_c, expec_f, mkps2d_f, (cudaStream_t)stream);
 }
 
+int nlb_debug_knn_rays(const void* index, const float* rays_o, const float* rays_d, const float* z_vals, int64_t z_stride,
+                       const float* sup_geo, int64_t R, int S, int32_t* idx, float* dist2, void* stream) {
+  if (!index || !rays_o || !rays_d || !z_vals || !sup_geo || !idx || !dist2) return set_error("nlb_debug_knn_rays: NULL pointer");
+  return knn_query_rays(index, rays_o, rays_d, z_vals, z_stride, sup_geo, R, S, idx, dist2, (cudaStream_t)stream);
+}
+
 int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C, void* stream) {
   if (!A || !W || !C) return set_error("nlb_debug_tc_gemm: NULL pointer");
   return launch_tc_test(A, W, K, mode, C, (cudaStream_t)stream);
@@ -446,7 +463,8 @@ int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C,
 int nlb_debug_read_prof(long long* out, int n) {
   if (n <= 32) return read_prof(out, n);
   const int e = getenv("NLB_RAY_V1") ? read_prof_ray(out + 32, n - 32) : read_prof_ray2(out + 32, n - 32);
-  return e || read_prof(out, 32);
+  if (e || read_prof(out, 32)) return 1;
+  return nb_v1() ? 0 : read_prof_nb2(out, 16);   // slots 0-15: neighbour stamps, 16-31: aggregate stamps
 }
 
 }  // extern "C"

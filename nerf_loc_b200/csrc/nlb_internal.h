@@ -66,6 +66,9 @@ struct RenderW {
   // [hi | lo] weight tiles (tc_bf16.cuh); conv_out keeps its 160 input channels in one block (K-tiles 0-3: x, 4: x2)
   const float* tb_u[7][3];
   const float *tb_bl1a, *tb_ft1;
+  // bf16x3 copies for the neighbour kernels (neighbor2.cu): [N = 128][K] operands as K-tiles of 32 ([hi | lo], 16 KB each);
+  // tb_w1b in the K order neighbor2_kernel writes its layer-1 operand (pack.cu::tcb_src_index)
+  const float *tb_w1b, *tb_w2, *tb_w3, *tb_wq, *tb_wk, *tb_wv, *tb_wfc;
   const float *sig_w, *sig_b;   // [128], [1]
   const float *ft1, *ft1_b;     // [128][128], [128]
   const float *ft2, *ft2_b;     // [128][192], [192]

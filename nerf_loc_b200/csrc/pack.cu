@@ -82,6 +82,9 @@ static RenderW layout(const float* base, int S, size_t* total) {
     for (int t = 0; t < 3; ++t) w.tb_u[l][t] = a.take((size_t)UN_COUT[l] * UN_CIN[l]);
   w.tb_bl1a = a.take(32 * 128);
   w.tb_ft1 = a.take(128 * 128);
+  w.tb_w1b = a.take(128 * 96);
+  w.tb_w2 = a.take(128 * 128); w.tb_w3 = a.take(128 * 128);
+  w.tb_wq = a.take(128 * 128); w.tb_wk = a.take(128 * 128); w.tb_wv = a.take(128 * 128); w.tb_wfc = a.take(128 * 128);
   w.sig_w = a.take(128); w.sig_b = a.take(1);
   w.ft1 = a.take(128 * 128); w.ft1_b = a.take(128);
   w.ft2 = a.take(128 * 192); w.ft2_b = a.take(192);
@@ -156,11 +159,12 @@ __global__ void pack_tcb_kernel(float* dst, const float* __restrict__ src, int N
 // bf16x3 B operand (tc_bf16.cuh): W [N][K] -> per K-tile of `ktile` columns: hi tile then lo tile, each in the weight-tile
 // layout (8-row x 16-byte core matrices, adjacent in K contiguous, 8-row groups ktile*16 bytes apart); hi = bf16(x), lo = bf16(x - hi)
 __global__ void pack_tcb16_kernel(uint16_t* dst, const float* __restrict__ src, int N, int K, int src_ld, int src_off, int src_ks,
-                                  int ktile) {
+                                  int ktile, int Kv, int perm) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
   const int n = i / K, k = i % K;
-  const float x = src[(size_t)n * src_ld + src_off + (size_t)k * src_ks];
+  const int ksrc = tcb_src_index(k, perm);
+  const float x = (ksrc >= 0 && ksrc < Kv) ? src[(size_t)n * src_ld + src_off + (size_t)ksrc * src_ks] : 0.f;
   const uint32_t xb = __float_as_uint(x);
   // round to nearest even by hand (identical to __float2bfloat16_rn for finite values)
   const uint32_t hb = (xb + 0x7FFFu + ((xb >> 16) & 1u)) >> 16;
@@ -192,10 +196,10 @@ struct Packer {
     pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv, src_ks,
                                                      2048 / N, perm);
   }
-  void tcb16(const float* dst, int src, int N, int K, int src_ld, int src_off, int src_ks, int ktile) {
+  void tcb16(const float* dst, int src, int N, int K, int src_ld, int src_off, int src_ks, int ktile, int Kv = -1, int perm = 0) {
     const int n = N * K;
     pack_tcb16_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<uint16_t*>(const_cast<float*>(dst)), p[src], N, K, src_ld,
-                                                       src_off, src_ks, ktile);
+                                                       src_off, src_ks, ktile, Kv < 0 ? K : Kv, perm);
   }
   void conv(const float* dst, int src, int Cin, int Cout, int ntaps, int t0, int t1, int t2, bool tr) {
     const int n = ntaps * Cin * Cout;
@@ -294,6 +298,13 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
       }
     }
   }
+  k.tcb16(w.tb_w1b, BM0_W, 128, 96, 285, 195, 1, 32, 90, 1);
+  k.tcb16(w.tb_w2, BM2_W, 128, 128, 128, 0, 1, 32);
+  k.tcb16(w.tb_w3, BM4_W, 128, 128, 128, 0, 1, 32);
+  k.tcb16(w.tb_wq, AT_Q, 128, 128, 128, 0, 1, 32);
+  k.tcb16(w.tb_wk, AT_K, 128, 128, 128, 0, 1, 32);
+  k.tcb16(w.tb_wv, AT_V, 128, 128, 128, 0, 1, 32);
+  k.tcb16(w.tb_wfc, AT_FC, 128, 128, 128, 0, 1, 32);
   k.tcb16(w.tb_bl1a, BL0_W, 32, 128, 328, 0, 1, 128);
   k.tcb16(w.tb_ft1, FT0_W, 128, 128, 128, 0, 1, 32);
   k.c(w.sig_w, SIG_W, 128);  k.c(w.sig_b, SIG_B, 1);

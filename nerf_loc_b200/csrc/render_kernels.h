@@ -28,6 +28,12 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
                      float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, cudaStream_t st);
 int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
                     const float* d2, const float* agg, float* fagg, float* feature, float* weights, cudaStream_t st);
+// second generation (neighbor2.cu): q projection, 32-sample super-tiles with the attention projections on tcgen05, fc + LayerNorm
+// tail; `scratch` holds neighbor2_scratch_floats(N) floats
+size_t neighbor2_scratch_floats(int64_t N);
+int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
+                     const float* d2, const float* agg, float* fagg, float* feature, float* weights, float* scratch,
+                     cudaStream_t st);
 int launch_blend_project(const float* feat, int64_t P, const float* bl1v, float* out, cudaStream_t st);
 int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,
                   float* out, int ldo, cudaStream_t st);

@@ -39,24 +39,41 @@ def all_gather_rows(x, R, group=None):
 
 
 class FeatExchange:
-    """Gathered rendered-feature matrix [R,192] in symmetric memory + the peer pointers the ray kernels store into."""
+    """Gathered rendered-feature matrix [R,192] in symmetric memory + the peer pointers the ray kernels store into.
+
+    Two copies, used alternately (`begin_frame`): the peers' ray kernels of frame n+1 store into the copy frame n did NOT use, so
+    a rank that is still reading frame n's gathered matrix (its matcher) is never overwritten by a faster peer.  Frame n+2
+    reuses frame n's copy, and a peer can only get there through the barrier of frame n+1, which this rank joins on the same
+    stream AFTER its frame-n consumers.  Contract: per frame `begin_frame()` -> render with the returned pointers -> `barrier()`
+    -> read `gathered()` on the stream the barrier ran on; the view is valid until the second `begin_frame()` after it."""
 
     def __init__(self, R, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         self.R = R
-        self.buf = symm_mem.empty(max(R, 1), 192, dtype=torch.float32, device=device)
+        self.rows = max(R, 1)
+        self.buf = symm_mem.empty(2 * self.rows, 192, dtype=torch.float32, device=device)
         self.handle = symm_mem.rendezvous(self.buf, self.group)
-        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
-        if len(self.ptrs) > 8:
+        self.base = [int(p) for p in self.handle.buffer_ptrs]
+        if len(self.base) > 8:
             raise RuntimeError("FeatExchange: at most 8 ranks (one NVSwitch box)")
+        self.parity = 1
+        self.ptrs = None
+
+    def begin_frame(self):
+        """Flips to the other copy; returns the peer pointers the ray kernels of this frame store into."""
+        self.parity ^= 1
+        off = self.parity * self.rows * 192 * 4
+        self.ptrs = [p + off for p in self.base]
+        return self.ptrs
 
     def barrier(self):
         """All ranks' peer stores queued before this point (on the current stream) are visible after it."""
         self.handle.barrier()
 
     def gathered(self):
-        return self.buf[:self.R]
+        lo = self.parity * self.rows
+        return self.buf[lo:lo + self.R]
 
 
 def render_rays_sharded(model, data, rays, gather=("feat",), group=None, exchange=None):
@@ -72,7 +89,7 @@ def render_rays_sharded(model, data, rays, gather=("feat",), group=None, exchang
     if "pixel_coordinates" in rays:
         local["pixel_coordinates"] = rays["pixel_coordinates"][lo:hi]
     if exchange is not None:
-        out = model.render_rays(data, local, _feat_peers=(exchange.ptrs, lo))
+        out = model.render_rays(data, local, _feat_peers=(exchange.begin_frame(), lo))
         exchange.barrier()
     else:
         out = model.render_rays(data, local)

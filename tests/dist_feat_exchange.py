@@ -28,10 +28,24 @@ def main():
     ex = FeatExchange(R, dev)
     ex.buf.fill_(float("nan"))
     ex.barrier()
+    # several frames with a slow consumer on the odd ranks: a faster peer's next frame must not overwrite the gathered matrix this
+    # rank is still reading (FeatExchange alternates between two copies)
+    frames_ok = True
+    subs = [{"rays_o": rays["rays_o"].roll(f, 0), "rays_d": rays["rays_d"].roll(f, 0), "depth_range": rays["depth_range"]} for f in range(4)]
+    got = []
+    for sub in subs:                           # fused frames back to back: no host sync, no other collective in between
+        _, g_fused = render_rays_sharded(model, data, sub, gather=("feat",), exchange=ex)
+        if rank % 2 == 1:
+            torch.cuda._sleep(200_000_000)     # ~0.1 s on the stream before this rank's consumer reads
+        got.append(g_fused["feat"].clone())
+    for sub, g in zip(subs, got):
+        _, g_ref = render_rays_sharded(model, data, sub, gather=("feat",))
+        frames_ok = frames_ok and torch.equal(g, g_ref["feat"])
+    torch.cuda.synchronize()
     out_a, g_a = render_rays_sharded(model, data, rays, gather=("feat",))                  # NCCL all-gather
     out_b, g_b = render_rays_sharded(model, data, rays, gather=("feat",), exchange=ex)     # fused peer stores
     torch.cuda.synchronize()
-    ok = torch.equal(g_a["feat"], g_b["feat"])
+    ok = frames_ok and torch.equal(g_a["feat"], g_b["feat"])
     for k in ("rgb", "depth", "weights", "feat", "depth_uncertainty", "mask"):
         ok = ok and torch.equal(out_a[k], out_b[k])
     lo, hi, _ = shard_bounds(R, world, rank)

@@ -52,6 +52,40 @@ def test_knn_points_signature_and_surface_cloud():
     assert torch.equal(out.knn[0].cpu(), xyz[i_ref])
 
 
+@pytest.mark.parametrize("S,per_ray", [(128, False), (64, True), (24, False)])
+def test_knn_ray_samples_bit_exact(S, per_ray):
+    """The render path's own search (8 lanes per query, warm start along the ray; csrc/knn.cu) against the C oracle: indices and
+    squared distances bit for bit, on a surface cloud (multi-view back-projection) with shared and per-ray depths."""
+    import ctypes
+    from nerf_loc_b200 import _lib
+    from nerf_loc_b200.conditional_nerf import ConditionalNeRF
+    from nerf_loc_b200.config import default_args
+    sc = syn.make_scene(64, 96, 4, seed=11)
+    m = ConditionalNeRF(default_args(16))
+    _, xyz, _, _ = m.backproject_support_frame(sc["topk_images"], sc["feat_fine_src"], sc["topk_depths"],
+                                               sc["topk_Ks"], sc["topk_poses"], stride=4)
+    R = 301
+    ro, rd = syn.pixel_rays(sc["K"], sc["pose"], syn.random_pixels(64, 96, R))
+    g = torch.Generator().manual_seed(S)
+    z = torch.linspace(0.2, 6.0, S)
+    if per_ray:
+        z = (z[None] + 0.03 * torch.rand(R, S, generator=g)).sort(dim=1).values.contiguous()
+    q = (ro[:, None, :] + rd[:, None, :] * (z[..., None] if per_ray else z[None, :, None])).reshape(-1, 3)
+    d_ref, i_ref = KO.knn_c(q, xyz, 8)
+    L = _lib.load()
+    index = KnnIndex(xyz.cuda())
+    geo = torch.zeros(xyz.shape[0], 8)
+    geo[:, :3] = xyz
+    geo, rod, rdd, zd = geo.cuda(), ro.cuda().contiguous(), rd.cuda().contiguous(), z.cuda().contiguous()
+    idx = torch.empty(R * S, 8, dtype=torch.int32, device="cuda")
+    d2 = torch.empty(R * S, 8, device="cuda")
+    _lib.check(L.nlb_debug_knn_rays(_lib.ptr(index.buf), _lib.ptr(rod), _lib.ptr(rdd), _lib.ptr(zd), S if per_ray else 0,
+                                    _lib.ptr(geo), R, S, _lib.ptr(idx), _lib.ptr(d2), _lib.stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(idx.long().cpu(), i_ref)
+    assert torch.equal(d2.cpu(), d_ref)
+
+
 @pytest.mark.parametrize("name", list(RENDER_CASES))
 def test_aggregator_and_support_points(name):
     S, sd_cpu, sc, scene, ro, rd = render_inputs(name)
