@@ -232,7 +232,7 @@ size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
 int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays) {
   if (R <= 0) return 0;
   if (chunk_rays < 1) chunk_rays = R;
-  return 4 * ((R + chunk_rays - 1) / chunk_rays);
+  return (nb_v1() ? 4 : 6) * ((R + chunk_rays - 1) / chunk_rays);   // KNN, aggregate, [q projection,] neighbour, [attention tail,] ray
 }
 
 static int render_rays_impl(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
