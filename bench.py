@@ -264,7 +264,7 @@ def run_b200(args):
     if world > 1:
         # agree on the path BEFORE the collective allocation: a rank that failed alone inside the rendezvous would hang the rest
         try:
-            import torch.distributed._symmetric_memory  # noqa: F401
+            __import__("torch.distributed._symmetric_memory")
             ok = torch.ones(1, device=dev)
         except Exception as e:  # symmetric memory not available in this build: one NCCL all-gather per step instead
             ok, exch_note = torch.zeros(1, device=dev), f"{type(e).__name__}"

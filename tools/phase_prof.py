@@ -20,12 +20,19 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 64)()
 _lib.load().nlb_debug_read_prof(buf, 64)
 v = list(buf)
-names = ["P0(t): PE, rd_fc, A1 -> TMEM", "A(t-1): scores, softmax, ctx", "wait L1", "E1(t)", "B(t-1): wv + fc GEMMs", "wait L2", "E2(t)",
-         "C1(t-1): LN, weights, out", "C2(t): q + q~ GEMMs", "wait L3", "E3(t): pf -> smem"]
-for i in range(11):
-    print(f"{names[i]:36s} {v[i+1]-v[i]:8d} clk")
-print("slot total", v[11] - v[0])
-print("C1 detail: weights", v[12]-v[7], "LN", v[13]-v[12], "barrier", v[14]-v[13], "out", v[8]-v[14])
+if os.environ.get("NLB_NB_V1"):
+    names = ["P0(t): PE, rd_fc, A1 -> TMEM", "A(t-1): scores, softmax, ctx", "wait L1", "E1(t)", "B(t-1): wv + fc GEMMs", "wait L2", "E2(t)",
+             "C1(t-1): LN, weights, out", "C2(t): q + q~ GEMMs", "wait L3", "E3(t): pf -> smem"]
+    for i in range(11):
+        print(f"{names[i]:36s} {v[i+1]-v[i]:8d} clk")
+    print("slot total", v[11] - v[0])
+    print("C1 detail: weights", v[12]-v[7], "LN", v[13]-v[12], "barrier", v[14]-v[13], "out", v[8]-v[14])
+else:
+    names = ["P0 (both sub-tiles) + q rows", "wait L1 (sub-tile 0)", "E1 (both)", "E2 (both, incl. waits)", "E3 (both, incl. waits)",
+             "wait key projection", "scores + softmax (both)", "wait value projection", "context + weights (both)"]
+    for i in range(9):
+        print(f"nb2 {names[i]:36s} {v[i+1]-v[i]:8d} clk")
+    print("nb2 super-tile (32 samples) total", v[9] - v[0])
 
 an = ["proj", "vis gather", "decoder GEMMs+heads", "view weights", "rgb/feat gather", "blend partial", "mean/var", "out_fc"]
 for i in range(8):
