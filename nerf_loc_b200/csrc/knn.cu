@@ -5,14 +5,17 @@
 // bounding-volume hierarchy that is rebuilt once per frame:
 //   * support points are sorted along a 30-bit Morton curve (cub radix sort, per-frame setup);
 //   * leaves hold LEAF consecutive sorted points, inner levels group FAN consecutive children; every node
-//     stores its AABB as two float4;
-//   * one thread per query walks the tree with a small stack, nearest child first, pruning a node only when
-//     its box distance is STRICTLY larger than the current K-th distance.
+//     stores an ORIENTED bounding box (centre, principal axes of its points, half extents: four float4).  The
+//     support points are samples of surfaces: an axis-aligned box around a tilted patch is as thick as the
+//     patch is wide, and a far query's search sphere (tangent to the surface) then cuts through dozens of boxes
+//     that hold no neighbour; along the patch's own normal the box is as thin as the surface is rough;
+//   * the tree is walked nearest child first, pruning a node only when its box distance is STRICTLY larger than
+//     the current K-th distance.
 // Results are identical to the reference definition: the K smallest squared distances by (distance, index),
 // ascending, with the squared distance accumulated as ((dx*dx + dy*dy) + dz*dz) with one rounding per
-// operation (no FMA), exactly like knn_cpu.cpp:43-47.  The box distance is evaluated with the same operation
-// order, so by monotonicity of rounding it is a true lower bound of every contained point's distance and the
-// pruning is exact, ties included.
+// operation (no FMA), exactly like knn_cpu.cpp:43-47.  The box distance is a lower bound of every contained
+// point's COMPUTED distance by construction: extents are inflated and the per-axis gaps deflated by more than
+// the rounding error of the projections (node_d2), so pruning is exact, ties included.
 #include <cub/cub.cuh>
 #include <float.h>
 #include <stdlib.h>
@@ -22,6 +25,7 @@ namespace nlb {
 
 constexpr int LEAF = 8;
 constexpr int FAN = 8;
+constexpr int NODE_F4 = 4;     // float4 per node: (centre, h0) (axis 0, h1) (axis 1, h2) (axis 2, -)
 
 // ---- index layout inside the caller-provided buffer -------------------------------------------------------
 // header (KnnHeader) | sorted points float4[M] (xyz, original index bits) | level 0 boxes | level 1 boxes ...
@@ -29,7 +33,7 @@ struct KnnHeader {
   int64_t M;
   int n_levels;
   int level_count[12];
-  int64_t level_off[12];  // float4 offsets (2 float4 per box) from the start of the box area
+  int64_t level_off[12];  // float4 offsets (NODE_F4 float4 per node) from the start of the box area
   int64_t pts_off;        // byte offsets from buffer start
   int64_t box_off;
   int64_t keys_off, vals_off, keys2_off, vals2_off, bbox_off, cub_off;
@@ -44,7 +48,7 @@ static void knn_layout(int64_t M, KnnHeader& h) {
   int64_t boxes = 0;
   while (true) {
     h.level_count[L] = (int)n;
-    h.level_off[L] = boxes * 2;
+    h.level_off[L] = boxes * NODE_F4;
     boxes += n;
     ++L;
     if (n <= FAN || L >= 12) break;
@@ -54,7 +58,7 @@ static void knn_layout(int64_t M, KnnHeader& h) {
   auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
   int64_t o = align(sizeof(KnnHeader));
   h.pts_off = o; o = align(o + M * 16);
-  h.box_off = o; o = align(o + boxes * 32);
+  h.box_off = o; o = align(o + boxes * 16 * NODE_F4);
   h.keys_off = o; o = align(o + M * 4);
   h.vals_off = o; o = align(o + M * 4);
   h.keys2_off = o; o = align(o + M * 4);
@@ -144,35 +148,125 @@ __global__ void knn_gather_kernel(const float* __restrict__ xyz, int64_t M, cons
   pts[i] = make_float4(xyz[(int64_t)j * 3], xyz[(int64_t)j * 3 + 1], xyz[(int64_t)j * 3 + 2], __uint_as_float(j));
 }
 
-__global__ void knn_leaf_boxes(const float4* __restrict__ pts, int64_t M, float4* boxes, int n) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n) return;
-  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int k = 0; k < LEAF; ++k) {
-    int64_t i = (int64_t)b * LEAF + k;
-    if (i >= M) break;
-    float4 p = pts[i];
-    lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
-    lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
-    lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+// One warp per node: oriented bounding box of the node's points (a contiguous run of `span` sorted points).
+//   pass 1: mean; pass 2: covariance about the mean, its eigenvectors (cyclic Jacobi, re-orthonormalised) are the box axes;
+//   pass 3: extent of the projections along each axis -> box centre (mid-range) and half extents;
+//   pass 4: the half extents are re-measured about the STORED centre with the arithmetic the queries use and inflated by more
+//           than its rounding error, so |a_i . (p - c)| <= h_i holds for every point in exact arithmetic.
+// aabb != 0 keeps the coordinate axes (an axis-aligned box in the same record; A/B switch NLB_KNN_AABB).
+__global__ void __launch_bounds__(256) knn_node_obb_kernel(const float4* __restrict__ pts, int64_t M, int64_t span, int n_nodes,
+                                                           float4* __restrict__ out, int aabb) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= n_nodes) return;
+  const int64_t p0 = (int64_t)b * span, p1 = min(M, p0 + span);
+  const float n = (float)(p1 - p0);
+  auto wsum = [](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
+  auto wmax = [](float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+  };
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int64_t i = p0 + lane; i < p1; i += 32) { const float4 p = pts[i]; sx += p.x; sy += p.y; sz += p.z; }
+  const float mx = wsum(sx) / n, my = wsum(sy) / n, mz = wsum(sz) / n;
+  float ax[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};   // rows: box axes
+  if (!aabb) {
+    float c00 = 0.f, c01 = 0.f, c02 = 0.f, c11 = 0.f, c12 = 0.f, c22 = 0.f;
+    for (int64_t i = p0 + lane; i < p1; i += 32) {
+      const float4 p = pts[i];
+      const float dx = p.x - mx, dy = p.y - my, dz = p.z - mz;
+      c00 += dx * dx; c01 += dx * dy; c02 += dx * dz; c11 += dy * dy; c12 += dy * dz; c22 += dz * dz;
+    }
+    float A[3][3];
+    A[0][0] = wsum(c00); A[0][1] = A[1][0] = wsum(c01); A[0][2] = A[2][0] = wsum(c02);
+    A[1][1] = wsum(c11); A[1][2] = A[2][1] = wsum(c12); A[2][2] = wsum(c22);
+    float V[3][3] = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};   // columns: eigenvectors
+    // every lane runs the same deterministic iteration on the same (shuffled) numbers
+    for (int sweep = 0; sweep < 6; ++sweep) {
+#pragma unroll
+      for (int pq = 0; pq < 3; ++pq) {
+        const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+        const float apq = A[p][q];
+        if (fabsf(apq) <= 1e-30f) continue;
+        const float theta = (A[q][q] - A[p][p]) / (2.f * apq);
+        const float t = (theta >= 0.f ? 1.f : -1.f) / (fabsf(theta) + sqrtf(theta * theta + 1.f));
+        const float cs = 1.f / sqrtf(t * t + 1.f), sn = t * cs;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {   // A <- A J
+          const float akp = A[k][p], akq = A[k][q];
+          A[k][p] = cs * akp - sn * akq; A[k][q] = sn * akp + cs * akq;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {   // A <- J^T A
+          const float apk = A[p][k], aqk = A[q][k];
+          A[p][k] = cs * apk - sn * aqk; A[q][k] = sn * apk + cs * aqk;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {   // V <- V J
+          const float vkp = V[k][p], vkq = V[k][q];
+          V[k][p] = cs * vkp - sn * vkq; V[k][q] = sn * vkp + cs * vkq;
+        }
+      }
+    }
+    // Gram-Schmidt on the columns of V; a degenerate column falls back to a coordinate axis / cross product
+    float e0[3] = {V[0][0], V[1][0], V[2][0]}, e1[3] = {V[0][1], V[1][1], V[2][1]};
+    float l0 = sqrtf(e0[0] * e0[0] + e0[1] * e0[1] + e0[2] * e0[2]);
+    if (!(l0 > 1e-20f)) { e0[0] = 1.f; e0[1] = 0.f; e0[2] = 0.f; l0 = 1.f; }
+    e0[0] /= l0; e0[1] /= l0; e0[2] /= l0;
+    float dp = e1[0] * e0[0] + e1[1] * e0[1] + e1[2] * e0[2];
+    e1[0] -= dp * e0[0]; e1[1] -= dp * e0[1]; e1[2] -= dp * e0[2];
+    float l1 = sqrtf(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+    if (!(l1 > 1e-6f)) {   // pick the coordinate axis least aligned with e0
+      const int m = fabsf(e0[0]) <= fabsf(e0[1]) ? (fabsf(e0[0]) <= fabsf(e0[2]) ? 0 : 2) : (fabsf(e0[1]) <= fabsf(e0[2]) ? 1 : 2);
+      e1[0] = m == 0; e1[1] = m == 1; e1[2] = m == 2;
+      dp = e1[0] * e0[0] + e1[1] * e0[1] + e1[2] * e0[2];
+      e1[0] -= dp * e0[0]; e1[1] -= dp * e0[1]; e1[2] -= dp * e0[2];
+      l1 = sqrtf(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]);
+    }
+    e1[0] /= l1; e1[1] /= l1; e1[2] /= l1;
+    ax[0][0] = e0[0]; ax[0][1] = e0[1]; ax[0][2] = e0[2];
+    ax[1][0] = e1[0]; ax[1][1] = e1[1]; ax[1][2] = e1[2];
+    ax[2][0] = e0[1] * e1[2] - e0[2] * e1[1]; ax[2][1] = e0[2] * e1[0] - e0[0] * e1[2]; ax[2][2] = e0[0] * e1[1] - e0[1] * e1[0];
   }
-  boxes[2 * b] = make_float4(lo[0], lo[1], lo[2], 0.f);
-  boxes[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
-}
-
-__global__ void knn_inner_boxes(const float4* __restrict__ child, int n_child, float4* boxes, int n) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= n) return;
+  // extent of the projections about the mean -> centre at the mid-range
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-  for (int k = 0; k < FAN; ++k) {
-    int c = b * FAN + k;
-    if (c >= n_child) break;
-    float4 a = child[2 * c], z = child[2 * c + 1];
-    lo[0] = fminf(lo[0], a.x); lo[1] = fminf(lo[1], a.y); lo[2] = fminf(lo[2], a.z);
-    hi[0] = fmaxf(hi[0], z.x); hi[1] = fmaxf(hi[1], z.y); hi[2] = fmaxf(hi[2], z.z);
+  for (int64_t i = p0 + lane; i < p1; i += 32) {
+    const float4 p = pts[i];
+    const float dx = p.x - mx, dy = p.y - my, dz = p.z - mz;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const float t = ax[a][0] * dx + ax[a][1] * dy + ax[a][2] * dz;
+      lo[a] = fminf(lo[a], t); hi[a] = fmaxf(hi[a], t);
+    }
   }
-  boxes[2 * b] = make_float4(lo[0], lo[1], lo[2], 0.f);
-  boxes[2 * b + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+  float cx = mx, cy = my, cz = mz;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const float mid = 0.5f * (-wmax(-lo[a]) + wmax(hi[a]));
+    cx += mid * ax[a][0]; cy += mid * ax[a][1]; cz += mid * ax[a][2];
+  }
+  float h[3] = {0.f, 0.f, 0.f}, span1 = 0.f;
+  for (int64_t i = p0 + lane; i < p1; i += 32) {
+    const float4 p = pts[i];
+    const float dx = p.x - cx, dy = p.y - cy, dz = p.z - cz;
+    span1 = fmaxf(span1, fabsf(dx) + fabsf(dy) + fabsf(dz));
+#pragma unroll
+    for (int a = 0; a < 3; ++a) h[a] = fmaxf(h[a], fabsf(fmaf(ax[a][2], dz, fmaf(ax[a][1], dy, ax[a][0] * dx))));
+  }
+  span1 = wmax(span1);
+#pragma unroll
+  for (int a = 0; a < 3; ++a) h[a] = wmax(h[a]) * 1.00001f + 2e-6f * span1;
+  if (lane == 0) {
+    out[(size_t)b * NODE_F4 + 0] = make_float4(cx, cy, cz, h[0]);
+    out[(size_t)b * NODE_F4 + 1] = make_float4(ax[0][0], ax[0][1], ax[0][2], h[1]);
+    out[(size_t)b * NODE_F4 + 2] = make_float4(ax[1][0], ax[1][1], ax[1][2], h[2]);
+    out[(size_t)b * NODE_F4 + 3] = make_float4(ax[2][0], ax[2][1], ax[2][2], 0.f);
+  }
 }
 
 int knn_build(const float* xyz, int64_t M, void* buf, size_t bytes, cudaStream_t st) {
@@ -198,10 +292,10 @@ int knn_build(const float* xyz, int64_t M, void* buf, size_t bytes, cudaStream_t
   cudaError_t e = cub::DeviceRadixSort::SortPairs(base + h.cub_off, cub_bytes, keys, keys2, vals, vals2, (int)M, 0, 30, st);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   knn_gather_kernel<<<G, T, 0, st>>>(xyz, M, vals2, pts);
-  knn_leaf_boxes<<<(h.level_count[0] + T - 1) / T, T, 0, st>>>(pts, M, boxes + h.level_off[0], h.level_count[0]);
-  for (int l = 1; l < h.n_levels; ++l)
-    knn_inner_boxes<<<(h.level_count[l] + T - 1) / T, T, 0, st>>>(boxes + h.level_off[l - 1], h.level_count[l - 1],
-                                                               boxes + h.level_off[l], h.level_count[l]);
+  static const int aabb = getenv("NLB_KNN_AABB") ? 1 : 0;   // A/B switch: axis-aligned instead of oriented boxes
+  int64_t span = LEAF;
+  for (int l = 0; l < h.n_levels; ++l, span *= FAN)
+    knn_node_obb_kernel<<<(h.level_count[l] + 7) / 8, 256, 0, st>>>(pts, M, span, h.level_count[l], boxes + h.level_off[l], aabb);
   e = cudaMemcpyAsync(buf, &h, sizeof(h), cudaMemcpyHostToDevice, st);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   // the header is read back from pageable host memory: make sure the copy has consumed it
@@ -225,12 +319,19 @@ __device__ __forceinline__ float d2_exact(float ax, float ay, float az, float bx
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-__device__ __forceinline__ float box_d2(float qx, float qy, float qz, float4 lo, float4 hi) {
-  // per-axis gap, written so that for a point on the face the value equals |q - p| bit for bit
-  const float dx = fmaxf(fmaxf(__fsub_rn(lo.x, qx), __fsub_rn(qx, hi.x)), 0.f);
-  const float dy = fmaxf(fmaxf(__fsub_rn(lo.y, qy), __fsub_rn(qy, hi.y)), 0.f);
-  const float dz = fmaxf(fmaxf(__fsub_rn(lo.z, qz), __fsub_rn(qz, hi.z)), 0.f);
-  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+// Lower bound of the computed squared distance from q to every point of a node.  d = q - c is a correctly rounded difference
+// of exact inputs; the three projections carry a rounding error below 3e-7 |d|_1, the stored half extents exceed the exact ones
+// (knn_node_obb_kernel), so every per-axis gap below is an underestimate; the final factor covers the axes' deviation from
+// orthonormality and the rounding of the point distance itself.
+__device__ __forceinline__ float node_d2(float qx, float qy, float qz, const float4* __restrict__ nd) {
+  const float4 f0 = nd[0], f1 = nd[1], f2 = nd[2], f3 = nd[3];
+  const float dx = qx - f0.x, dy = qy - f0.y, dz = qz - f0.z;
+  const float eps = 2e-6f * (fabsf(dx) + fabsf(dy) + fabsf(dz));
+  const float l0 = fabsf(fmaf(f1.z, dz, fmaf(f1.y, dy, f1.x * dx)));
+  const float l1 = fabsf(fmaf(f2.z, dz, fmaf(f2.y, dy, f2.x * dx)));
+  const float l2 = fabsf(fmaf(f3.z, dz, fmaf(f3.y, dy, f3.x * dx)));
+  const float g0 = fmaxf(l0 - f0.w - eps, 0.f), g1 = fmaxf(l1 - f1.w - eps, 0.f), g2 = fmaxf(l2 - f2.w - eps, 0.f);
+  return (g0 * g0 + g1 * g1 + g2 * g2) * 0.99999f;
 }
 
 template <int K>
@@ -269,7 +370,7 @@ __device__ __forceinline__ float knn_greedy_bound(const KnnTree& t, float qx, fl
   {
     float bd = FLT_MAX;
     for (int n = 0; n < t.level_count[lvl]; ++n) {
-      const float d = box_d2(qx, qy, qz, t.boxes[t.level_off[lvl] + 2 * n], t.boxes[t.level_off[lvl] + 2 * n + 1]);
+      const float d = node_d2(qx, qy, qz, t.boxes + t.level_off[lvl] + NODE_F4 * n);
       if (d < bd) { bd = d; node = n; }
     }
   }
@@ -280,7 +381,7 @@ __device__ __forceinline__ float knn_greedy_bound(const KnnTree& t, float qx, fl
 #pragma unroll
     for (int k = 0; k < FAN; ++k) {
       if (k < nc) {
-        const float d = box_d2(qx, qy, qz, t.boxes[t.level_off[cl] + 2 * (c0 + k)], t.boxes[t.level_off[cl] + 2 * (c0 + k) + 1]);
+        const float d = node_d2(qx, qy, qz, t.boxes + t.level_off[cl] + NODE_F4 * (c0 + k));
         if (d < bd) { bd = d; bestc = c0 + k; }
       }
     }
@@ -307,8 +408,7 @@ __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy,
   const int top = t.n_levels - 1;
   // push the top level (<= FAN nodes unless the level cap was hit), farthest first
   for (int n = t.level_count[top] - 1; n >= 0; --n) {
-    const float4 lo = t.boxes[t.level_off[top] + 2 * n], hi = t.boxes[t.level_off[top] + 2 * n + 1];
-    if (sp < STACK) { stk_node[sp] = ((unsigned)top << 28) | (unsigned)n; stk_d[sp] = box_d2(qx, qy, qz, lo, hi); ++sp; }
+    if (sp < STACK) { stk_node[sp] = ((unsigned)top << 28) | (unsigned)n; stk_d[sp] = node_d2(qx, qy, qz, t.boxes + t.level_off[top] + NODE_F4 * n); ++sp; }
   }
   while (sp > 0) {
     --sp;
@@ -338,8 +438,7 @@ __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy,
       for (int k = 0; k < FAN; ++k) {
         cd[k] = FLT_MAX;
         if (k < nc) {
-          const float4 lo = t.boxes[t.level_off[cl] + 2 * (c0 + k)], hi = t.boxes[t.level_off[cl] + 2 * (c0 + k) + 1];
-          cd[k] = box_d2(qx, qy, qz, lo, hi);
+          cd[k] = node_d2(qx, qy, qz, t.boxes + t.level_off[cl] + NODE_F4 * (c0 + k));
           if (cd[k] < nearest_d) { nearest_d = cd[k]; nearest = k; }
         }
       }
@@ -531,7 +630,7 @@ __global__ void __launch_bounds__(128) knn_query_rays_g8_kernel(const void* __re
         const int c0 = lvl == top ? 0 : node * FAN;
         const int nc = min(FAN, tree.level_count[lvl] - c0);
         float d = FLT_MAX;
-        if (gl < nc) d = box_d2(qx, qy, qz, tree.boxes[tree.level_off[lvl] + 2 * (c0 + gl)], tree.boxes[tree.level_off[lvl] + 2 * (c0 + gl) + 1]);
+        if (gl < nc) d = node_d2(qx, qy, qz, tree.boxes + tree.level_off[lvl] + NODE_F4 * (c0 + gl));
         int ml = gl;
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) {
@@ -554,7 +653,7 @@ __global__ void __launch_bounds__(128) knn_query_rays_g8_kernel(const void* __re
     {
       const int nc = min(FAN, tree.level_count[top]);
       float d = FLT_MAX;
-      if (gl < nc) d = box_d2(qx, qy, qz, tree.boxes[tree.level_off[top] + 2 * gl], tree.boxes[tree.level_off[top] + 2 * gl + 1]);
+      if (gl < nc) d = node_d2(qx, qy, qz, tree.boxes + tree.level_off[top] + NODE_F4 * gl);
       g8.push(((unsigned)top << 28) | (unsigned)gl, d, gl < nc && d <= bound);
     }
     while (g8.sp > 0) {
@@ -596,7 +695,7 @@ __global__ void __launch_bounds__(128) knn_query_rays_g8_kernel(const void* __re
         const int c0 = node * FAN;
         const int nc = min(FAN, tree.level_count[cl] - c0);
         float d = FLT_MAX;
-        if (gl < nc) d = box_d2(qx, qy, qz, tree.boxes[tree.level_off[cl] + 2 * (c0 + gl)], tree.boxes[tree.level_off[cl] + 2 * (c0 + gl) + 1]);
+        if (gl < nc) d = node_d2(qx, qy, qz, tree.boxes + tree.level_off[cl] + NODE_F4 * (c0 + gl));
         g8.push(((unsigned)cl << 28) | (unsigned)(c0 + gl), d, gl < nc && d <= w);
       }
     }

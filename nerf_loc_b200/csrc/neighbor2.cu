@@ -40,7 +40,7 @@ __device__ __forceinline__ void fast_sincos2(float x, float& s, float& c) {
   c = ((q + 1) & 2) ? -b : b;
 }
 
-constexpr int NS = 8;                        // weight stages: two layers' worth of tiles
+constexpr int NS = 10;                       // weight stages: a layer's tiles stay until both sub-tiles used them, 6 more run ahead
 constexpr uint32_t STG_BYTES = 16384;        // one [128 x 32] hi | lo tile
 constexpr int TP = 16;                       // samples per sub-tile
 constexpr int LDQ = 132;
@@ -52,7 +52,9 @@ constexpr uint32_t Q_OFF = STG_OFF + NS * STG_BYTES;                  // q [32][
 constexpr uint32_t D_OFF = Q_OFF + 2 * TP * LDQ * 4;                  // [2][256]: squared distances | confidences per sub-tile
 constexpr uint32_t W_OFF = D_OFF + 2 * 256 * 4;                       // ray_diff_fc weights (544 floats)
 constexpr uint32_t IDX_OFF = W_OFF + 544 * 4;                         // int idx[2][128]
-constexpr uint32_t SYNC_OFF = IDX_OFF + 2 * 128 * 4;
+constexpr int ROW_LD = 20;                                            // floats per staged row record (16 used; 20: conflict-free float4 reads)
+constexpr uint32_t ROW_OFF = IDX_OFF + 2 * 128 * 4;                   // [2][128][ROW_LD]: g0 | g1 | x y z dx dy dz d2 id of the NEXT super-tile
+constexpr uint32_t SYNC_OFF = ROW_OFF + 2 * 128 * ROW_LD * 4;
 constexpr uint32_t SMEM_BYTES = SYNC_OFF + 256;
 static_assert(SMEM_BYTES <= 232448, "neighbor2_kernel: shared memory budget");
 
@@ -66,7 +68,7 @@ static_assert(sizeof(Sync) <= 256, "nb2::Sync");
 constexpr int N_LAYERS = 5;                  // base_mlp 0, 2, 4; key projection; value projection
 __device__ __forceinline__ int layer_tiles(int l) { return l == 0 ? 3 : 4; }
 
-__global__ void __launch_bounds__(NT + 64, 1)
+__global__ void __launch_bounds__(NT + 128, 1)
 neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int K,
                  const int* __restrict__ knn_idx, const float* __restrict__ knn_d2, const float* __restrict__ q_in,
                  float* __restrict__ o_out, float* __restrict__ wsum_out, float* __restrict__ weights_out) {
@@ -76,6 +78,7 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   float* sD = reinterpret_cast<float*>(smraw + D_OFF);
   float* sW = reinterpret_cast<float*>(smraw + W_OFF);
   int* sIdx = reinterpret_cast<int*>(smraw + IDX_OFF);
+  float* sRow = reinterpret_cast<float*>(smraw + ROW_OFF);
   Sync& sy = *reinterpret_cast<Sync*>(smraw + SYNC_OFF);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -93,7 +96,10 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   const int64_t nst = (N + 2 * TP - 1) / (2 * TP);                              // super-tiles
   const int nmy = (int)((nst - blockIdx.x + gridDim.x - 1) / gridDim.x);        // of this CTA (grid <= nst)
 
-  if (warp == 9) {
+  if (warp >= 8) {
+   // service warpgroup (warps 10, 11 are only there so that the register hand-over is warpgroup-aligned)
+   tc::reg_dec<56>();
+   if (warp == 9) {
     // ------------------------------------------------ weight producer: 19 tiles of 16 KB per super-tile ------------------------
     uint32_t empty_par = 0;
     int i = 0;
@@ -116,7 +122,7 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         }
       }
     }
-  } else if (warp == 8) {
+   } else if (warp == 8) {
     // ------------------------------------------------ MMA issuer: bf16x3, A from tensor memory --------------------------------
     // layer l of sub-tile 0 on the layer's tiles (kept in the ring), then the same tiles for sub-tile 1 (released one by one)
     uint32_t full_par = 0, a_par = 0;
@@ -160,8 +166,10 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         i += nkt;
       }
     }
+   }
   } else {
     // ------------------------------------------------ compute warps ------------------------------------------------------
+    tc::reg_inc<224>();
     const float range = sc.far_ - sc.near_;
     const int row = (warp & 3) * 32 + lane;            // TMEM lane == (sample, neighbour) row of a sub-tile
     const int half = warp >> 2;                         // column half owned in the epilogues
@@ -178,19 +186,17 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     };
     auto a_ready = [&](int u) { tc::fence_before_sync(); tc::mbar_arrive(&sy.a_ready[u]); };
 
-    // this thread's (sample, neighbour) record of a sub-tile: neighbour id + geometry, sample position and viewing direction
-    struct RowRec { int id; bool live; float4 g0, g1; float x, y, z, dx, dy, dz, d2; };
-    auto load_row = [&](const int64_t n0t) {
-      RowRec q;
-      q.id = -1; q.g0 = make_float4(0.f, 0.f, 0.f, 0.f); q.g1 = q.g0;
-      q.x = q.y = q.z = q.dx = q.dy = q.dz = 0.f; q.d2 = 1.f;
+    // The (sample, neighbour) records of the NEXT super-tile are staged in shared memory by the half-0 threads in two steps, so
+    // that neither the index -> geometry dependency nor the records themselves cost registers or stalls in the phases between:
+    //   fetch_ids(n0)   neighbour id, sample position and direction -> a few registers (loads in flight)
+    //   stage_rows()    id / position / direction -> sRow, geometry (two 16-byte pieces) and squared distance by cp.async
+    struct RowPre { int id; float x, y, z, dx, dy, dz; };
+    auto fetch_ids = [&](const int64_t n0t) {
+      RowPre q;
+      q.id = -1; q.x = q.y = q.z = q.dx = q.dy = q.dz = 0.f;
       const int64_t n = n0t + p;
-      q.live = n < N && k < K;
-      if (q.live) {
+      if (n < N && k < K) {
         q.id = knn_idx[n * K + k];
-        q.d2 = knn_d2[n * K + k];
-        q.g0 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)q.id * 8));
-        q.g1 = __ldg(reinterpret_cast<const float4*>(sc.sup_geo + (size_t)q.id * 8 + 4));
         if (ps.xyz) {
           q.x = ps.xyz[n * 3]; q.y = ps.xyz[n * 3 + 1]; q.z = ps.xyz[n * 3 + 2];
         } else {
@@ -214,36 +220,64 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
       return q;
     };
+    auto stage_rows = [&](const int u, const RowPre& q, const int64_t n0t) {
+      float* rr = sRow + (u * 128 + row) * ROW_LD;
+      *reinterpret_cast<float4*>(rr + 8) = make_float4(q.x, q.y, q.z, q.dx);
+      *reinterpret_cast<float4*>(rr + 12) = make_float4(q.dy, q.dz, 1.f, __int_as_float(q.id));
+      if (q.id >= 0) {
+        cp_async16(rr, sc.sup_geo + (size_t)q.id * 8);
+        cp_async16(rr + 4, sc.sup_geo + (size_t)q.id * 8 + 4);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(rr + 14);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(knn_d2 + (n0t + p) * K + k));
+      } else {
+        *reinterpret_cast<float4*>(rr) = make_float4(0.f, 0.f, 0.f, 0.f);
+        *reinterpret_cast<float4*>(rr + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
 
     // ---- P0: per (sample, neighbour) geometry -> A operand of layer 1 (PE 63 | ray_diff_fc 27 | 0 x 6, permuted) in tensor memory.
     // Two threads per row, each with half of the work: positional-encoding octaves 0-4 / 5-9 and ray_diff_fc outputs 0-13 / 14-26
     // (K order: pack.cu::tcb_src_index); 48 values = 24 packed columns per plane and thread.
-    auto phase0 = [&](const int u, const RowRec& rr) {
-      const bool live = rr.live;
-      const float4 g0 = rr.g0, g1 = rr.g1;
+    auto phase0 = [&](const int u) {
+      const float* rrow = sRow + (u * 128 + row) * ROW_LD;
+      const float4 g0 = *reinterpret_cast<const float4*>(rrow), g1 = *reinterpret_cast<const float4*>(rrow + 4);
+      const float4 r2 = *reinterpret_cast<const float4*>(rrow + 8), r3 = *reinterpret_cast<const float4*>(rrow + 12);
+      const int rid = __float_as_int(r3.w);
+      const bool live = rid >= 0;
+      struct { float x, y, z, dx, dy, dz; } rr = {r2.x, r2.y, r2.z, r2.w, r3.x, r3.y};
       float vals[48];
       const float off[3] = {live ? __fdiv_rn(__fsub_rn(rr.x, g0.x), range) : 0.f, live ? __fdiv_rn(__fsub_rn(rr.y, g0.y), range) : 0.f,
                             live ? __fdiv_rn(__fsub_rn(rr.z, g0.z), range) : 0.f};
       if (half == 0) {
-        sD[u * 256 + row] = rr.d2;
+        sD[u * 256 + row] = live ? r3.z : 1.f;
         sD[u * 256 + 128 + row] = live ? g1.z : 0.f;   // confidence
-        sIdx[u * 128 + row] = rr.id;
+        sIdx[u * 128 + row] = rid;
         vals[0] = off[0]; vals[1] = off[1]; vals[2] = off[2]; vals[3] = 0.f;
       } else {
 #pragma unroll
         for (int c = 43; c < 48; ++c) vals[c] = 0.f;
       }
+      // octaves 5 * half + {0, 2, 4} by range-reduced sincos, {1, 3} from their predecessors by the double-angle identities
+      // (absolute error doubles: 4e-7 -> 8e-7, two orders below what the 1e-4 parity bar needs)
       float f = half ? 32.f : 1.f;
 #pragma unroll
-      for (int ii = 0; ii < 5; ++ii) {
+      for (int c = 0; c < 3; ++c) {
+        float sn[5], co[5];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          float sn = 0.f, co = 0.f;
-          if (live) fast_sincos2(off[c] * f, sn, co);
-          if (half == 0) { vals[4 + ii * 6 + c] = sn; vals[4 + ii * 6 + 3 + c] = co; }
-          else { vals[ii * 6 + c] = sn; vals[ii * 6 + 3 + c] = co; }
+        for (int ii = 0; ii < 5; ii += 2) {
+          sn[ii] = 0.f; co[ii] = 0.f;
+          if (live) fast_sincos2(off[c] * (f * (float)(1 << ii)), sn[ii], co[ii]);
         }
-        f *= 2.f;
+#pragma unroll
+        for (int ii = 1; ii < 5; ii += 2) {
+          sn[ii] = 2.f * sn[ii - 1] * co[ii - 1];
+          co[ii] = live ? fmaf(-2.f * sn[ii - 1], sn[ii - 1], 1.f) : 0.f;
+        }
+#pragma unroll
+        for (int ii = 0; ii < 5; ++ii) {
+          if (half == 0) { vals[4 + ii * 6 + c] = sn[ii]; vals[4 + ii * 6 + 3 + c] = co[ii]; }
+          else { vals[ii * 6 + c] = sn[ii]; vals[ii * 6 + 3 + c] = co[ii]; }
+        }
       }
       {
         // ray difference (model.py:396-399) and ray_diff_fc (4 -> 16 -> 27, LeakyReLU)
@@ -254,10 +288,8 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         float h1[16];
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
-          float a = sW[64 + o];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) a = fmaf(sW[o * 4 + c], rd[c], a);
-          h1[o] = leaky(a);
+          const float4 w4 = *reinterpret_cast<const float4*>(sW + o * 4);
+          h1[o] = leaky(fmaf(w4.w, rd[3], fmaf(w4.z, rd[2], fmaf(w4.y, rd[1], fmaf(w4.x, rd[0], sW[64 + o])))));
         }
 #pragma unroll
         for (int oo = 0; oo < 14; ++oo) {
@@ -265,7 +297,10 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           if (o < 27) {
             float a = sW[512 + o];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) a = fmaf(sW[80 + o * 16 + c], h1[c], a);
+            for (int c = 0; c < 16; c += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(sW + 80 + o * 16 + c);
+              a = fmaf(w4.x, h1[c], a); a = fmaf(w4.y, h1[c + 1], a); a = fmaf(w4.z, h1[c + 2], a); a = fmaf(w4.w, h1[c + 3], a);
+            }
             const float v = live ? leaky(a) : 0.f;
             if (half == 0) vals[34 + oo] = v; else vals[30 + oo] = v;
           }
@@ -288,18 +323,30 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       const int c0 = half * 64;
       const int id = sIdx[u * 128 + row];
       const float* add = mode == 0 ? (id >= 0 ? sc.sup_pre + (size_t)id * W_HID : nullptr) : (mode == 1 ? w.b2 : w.b3);
+      // the whole 64-column addend of the row (layer 1: the gathered per-frame support part) is requested before the accumulator
+      // is waited for: one L2 round trip per sub-tile, underneath the MMA
+      float4 a4[8], b4n[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a4[j] = add ? __ldg(reinterpret_cast<const float4*>(add + c0 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      wait_d(u);
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 32) {
-        float4 a4[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) a4[j] = add ? __ldg(reinterpret_cast<const float4*>(add + c0 + cc + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float v[32];
         tc::tmem_ld32(trow + u * TM_SUB + TM_D + (uint32_t)(c0 + cc), v);
+        if (cc == 0) {   // second half of the row: requested before the first half is consumed
+#pragma unroll
+          for (int j = 0; j < 8; ++j) b4n[j] = add ? __ldg(reinterpret_cast<const float4*>(add + c0 + 32 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          tc::split_bf16x2(leaky(v[4 * j] + a4[j].x), leaky(v[4 * j + 1] + a4[j].y), hi[2 * j], lo[2 * j]);
-          tc::split_bf16x2(leaky(v[4 * j + 2] + a4[j].z), leaky(v[4 * j + 3] + a4[j].w), hi[2 * j + 1], lo[2 * j + 1]);
+          const float4 b4 = a4[j];
+          tc::split_bf16x2(leaky(v[4 * j] + b4.x), leaky(v[4 * j + 1] + b4.y), hi[2 * j], lo[2 * j]);
+          tc::split_bf16x2(leaky(v[4 * j + 2] + b4.z), leaky(v[4 * j + 3] + b4.w), hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        if (cc == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a4[j] = b4n[j];
         }
         tc::tmem_st16_u(trow + u * TM_SUB + TM_AHI + (uint32_t)((c0 + cc) / 2), hi);
         tc::tmem_st16_u(trow + u * TM_SUB + TM_ALO + (uint32_t)((c0 + cc) / 2), lo);
@@ -395,9 +442,15 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
     };
 
-    RowRec nxt[2];
-    nxt[0] = load_row((int64_t)blockIdx.x * 2 * TP);
-    nxt[1] = load_row((int64_t)blockIdx.x * 2 * TP + TP);
+    if (half == 0) {
+      const int64_t n00 = (int64_t)blockIdx.x * 2 * TP;
+      const RowPre a = fetch_ids(n00), b = fetch_ids(n00 + TP);
+      stage_rows(0, a, n00);
+      stage_rows(1, b, n00 + TP);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    cta_sync();
     for (int it = 0; it < nmy; ++it) {
       const bool stamp = it == 1 && blockIdx.x == gridDim.x / 2 && tid == 0;
       const int64_t n0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 2 * TP;
@@ -409,26 +462,27 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         else *reinterpret_cast<float4*>(sQ + pp * LDQ + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       cp_async_commit();
-      phase0(0, nxt[0]);
+      phase0(0);
       a_ready(0);
-      phase0(1, nxt[1]);
+      phase0(1);
       a_ready(1);
       NB2_STAMP(1);
-      cta_sync();   // sIdx / sD of this super-tile visible
-      if (it + 1 < nmy) {
-        const int64_t n0n = ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * 2 * TP;
-        nxt[0] = load_row(n0n);
-        nxt[1] = load_row(n0n + TP);
-      }
+      cta_sync();   // sIdx / sD of this super-tile visible; sRow consumed
+      const bool more = it + 1 < nmy;
+      const int64_t n0n = ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * 2 * TP;
+      RowPre pre0, pre1;
+      if (more && half == 0) { pre0 = fetch_ids(n0n); pre1 = fetch_ids(n0n + TP); }
+      NB2_STAMP(2);
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {
-        wait_d(0);
-        if (l == 0) NB2_STAMP(2);
-        mlp_epilogue(0, l);
+        mlp_epilogue(0, l);   // (waits for the accumulator of sub-tile 0 itself)
         a_ready(0);
-        wait_d(1);
         mlp_epilogue(1, l);
         a_ready(1);
+        if (l == 0) {
+          if (more && half == 0) { stage_rows(0, pre0, n0n); stage_rows(1, pre1, n0n + TP); }
+          cp_async_commit();
+        }
         NB2_STAMP(3 + l);
       }
       cp_async_wait<0>();
@@ -636,7 +690,7 @@ int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   if (check_launch("qproj_kernel")) return 1;
   const int64_t nst = (N + 2 * nb2::TP - 1) / (2 * nb2::TP);
   const unsigned grid = (unsigned)(nst < sms ? nst : sms);   // persistent: one CTA per SM
-  nb2::neighbor2_kernel<<<grid, NT + 64, nb2::SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, q, o, wsum, weights);
+  nb2::neighbor2_kernel<<<grid, NT + 128, nb2::SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, q, o, wsum, weights);
   if (check_launch("neighbor2_kernel")) return 1;
   nb2::row_gemm128_kernel<1><<<g128, NT, nb2::RG_SMEM, st>>>(o, w.tb_wfc, N, agg, w.ln_g, w.ln_b, wsum, fagg, feature);
   return check_launch("attn_tail_kernel");

@@ -31,6 +31,15 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- register reallocation between warpgroups (setmaxnreg) ---------------------------------------------------------------
+// A CTA of 8 compute warps + 2 service warps is limited to 168 registers per thread (three warps share a scheduler's 16 K
+// registers).  Launched with a full third warpgroup (384 threads), the service warpgroup hands its registers back and the two
+// compute warpgroups take them: 232 x 256 + 40 x 128 <= 64 K.  Every warp of a warpgroup must execute the same instruction.
+template <int R>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+
 // ---- mbarrier ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -1,4 +1,4 @@
-T=${1:-r2e}
+T=${1:-r2g}
 timeout 300 python -m pytest tests/test_gpu_render.py -m gpu -x -q -k "knn" > gpurun_out/${T}_knn.log 2>&1; tail -3 gpurun_out/${T}_knn.log
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1; tail -30 gpurun_out/${T}_tests.log | cut -c1-300
 B="python bench.py --steps 1 --warmup 1 --cpu-rays 0 --cpu-match-n3 0"
@@ -6,11 +6,11 @@ k() { python -c "
 import json,sys
 l=sys.stdin.readline()
 try:
-    d=json.loads(l); print('$1', d['value'], d['kernels_ms_per_step'])
+    d=json.loads(l); print('$1', d['value'], d['kernels_ms_per_step'], d['config']['per_frame_setup_ms'])
 except Exception as e: print('$1', 'FAILED', l[:200])"; }
 $B 2>gpurun_out/${T}_b1.err | k default; tail -3 gpurun_out/${T}_b1.err
-NLB_NB_V1=1 $B 2>/dev/null | k nb_v1
-NLB_KNN_V1=1 $B 2>/dev/null | k knn_v1
+NLB_KNN_AABB=1 $B 2>/dev/null | k aabb
+NLB_KNN_V1=1 $B 2>/dev/null | k knn_v1_obb
 NLB_KNN_SEG=8 $B 2>/dev/null | k g8_seg8
 NLB_KNN_SEG=32 $B 2>/dev/null | k g8_seg32
 python bench.py --steps 2 --warmup 2 2>/dev/null | python -c "
@@ -19,3 +19,4 @@ l=sys.stdin.readline()
 try:
     d=json.loads(l); print('full', d['value'], d['kernels_ms_per_step'], d['parity_on_sample'])
 except Exception as e: print('full FAILED', l[:200])"
+timeout 300 python tools/phase_prof.py 2>&1 | head -12
