@@ -8,7 +8,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnerfloc_b200.so")
+LIB_PATH = os.environ.get("NLB_LIB") or os.path.join(_HERE, "libnerfloc_b200.so")   # NLB_LIB: A/B builds of the same ABI
 
 c_void_p, c_int, c_int64, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_size_t, ctypes.c_float
 c_uint64 = ctypes.c_uint64

@@ -190,7 +190,7 @@ int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S,
   if (knn_query(sc.knn, xyz, N, K, nullptr, idx, d2, st)) return 1;
   if (launch_aggregate(sc, w, ps, N, 0, agg, nullptr, nullptr, nullptr, mv_feature, mv_visibility, st)) return 1;
   if (nb_v1()) return launch_neighbor(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, st);
-  return launch_neighbor2(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, nb2, st);
+  return launch_neighbor2(sc, w, ps, N, K, idx, d2, agg, feature_agg, nullptr, 0, feature, weights, nb2, st);
 }
 
 int nlb_aggregate_points(const nlb_scene* scene, const float* packed_weights, int S, const float* xyz, int64_t N,
@@ -311,6 +311,11 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
     const float* zc = z_vals + r0 * z_stride;
     PointSrc ps{nullptr, nullptr, ro, rd, zc, S, z_stride};
     float* fa = dbg_feature_agg ? dbg_feature_agg + r0 * S * W_HID : fagg;
+    // the pair ray kernel takes feature_agg pre-split into its bf16 operand layout (written into the same scratch by the
+    // attention tail); an fp32 copy is only produced for the debug output
+    const bool split_x = S <= 128 && !ray_v1 && !nb_v1();
+    unsigned char* fsplit = split_x ? reinterpret_cast<unsigned char*>(fagg) : nullptr;
+    float* fa32 = split_x ? (dbg_feature_agg ? fa : nullptr) : fa;
     int* idx = idx2[i & 1];
     float* d2 = d22[i & 1];
     prof.mark();
@@ -320,11 +325,11 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
     prof.mark();
     if (overlap) cudaStreamWaitEvent(st, ev_knn[i & 1], 0);
     if (nb_v1() ? launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)
-                : launch_neighbor2(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, nb2, st)) { rc_err = 1; break; }
+                : launch_neighbor2(sc, w, ps, nc, KNN_K, idx, d2, agg, fa32, fsplit, S, nullptr, nullptr, nb2, st)) { rc_err = 1; break; }
     if (overlap) cudaEventRecord(ev_nb, st);
     prof.mark();
-    if (S <= 128 && !ray_v1) {
-      if (launch_ray2(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
+    if (split_x) {
+      if (launch_ray2(sc, w, zc, z_stride, rc, S, white_bkgd, fsplit, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                       weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
                       dbg_sigma ? dbg_sigma + r0 * S : nullptr, peers_at(peers, feat_row0 + r0), st)) { rc_err = 1; break; }
     } else if (S <= 128) {

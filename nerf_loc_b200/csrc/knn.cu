@@ -23,8 +23,14 @@
 
 namespace nlb {
 
-constexpr int LEAF = 8;
-constexpr int FAN = 8;
+#ifndef NLB_KNN_LEAF
+#define NLB_KNN_LEAF 8
+#endif
+#ifndef NLB_KNN_FAN
+#define NLB_KNN_FAN 8
+#endif
+constexpr int LEAF = NLB_KNN_LEAF;
+constexpr int FAN = NLB_KNN_FAN;
 constexpr int NODE_F4 = 4;     // float4 per node: (centre, h0) (axis 0, h1) (axis 1, h2) (axis 2, -)
 
 // ---- index layout inside the caller-provided buffer -------------------------------------------------------
@@ -364,7 +370,7 @@ struct TopK {
 // nearest child box at every level and measure the points of the leaf that is reached (LEAF >= K real support points).
 template <int K>
 __device__ __forceinline__ float knn_greedy_bound(const KnnTree& t, float qx, float qy, float qz) {
-  static_assert(K <= LEAF, "greedy bound needs a full leaf of at least K points");
+  if (K > LEAF) return FLT_MAX;
   int lvl = t.n_levels - 1;
   int node = 0;
   {
@@ -731,8 +737,7 @@ int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, 
   static const int greedy = getenv("NLB_KNN_GREEDY") ? atoi(getenv("NLB_KNN_GREEDY")) : 0;
   static const bool v1 = getenv("NLB_KNN_V1") != nullptr;   // A/B switch: one thread per query
   const int SEG = seg_env > 0 ? seg_env : (S >= 64 ? 16 : 8);
-  if (!v1) {
-    static_assert(LEAF == 8 && FAN == 8 && KNN_K == 8, "the cooperative search maps children, leaf points and results to 8 lanes");
+  if (!v1 && LEAF == 8 && FAN == 8) {
     const int64_t groups = R * ((S + SEG - 1) / SEG);
     knn_query_rays_g8_kernel<<<(unsigned)((groups + 15) / 16), 128, 0, st>>>(index, rays_o, rays_d, z_vals, sup_geo, R, S, SEG, zs,
                                                                             idx32, dist2);

@@ -526,7 +526,7 @@ template <int MODE>
 __global__ void __launch_bounds__(NT, 1)
 row_gemm128_kernel(const float* __restrict__ A, const float* __restrict__ wpacked, const int64_t N, const float* __restrict__ resid,
                    const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ wsum,
-                   float* __restrict__ out, float* __restrict__ out_feature) {
+                   float* __restrict__ out, float* __restrict__ out_feature, unsigned char* __restrict__ out_split, const int S_split) {
   extern __shared__ __align__(1024) unsigned char smraw[];
   unsigned char* sWt = smraw + RG_W_OFF;
   unsigned char* aHi = smraw + RG_A_OFF;
@@ -635,15 +635,30 @@ row_gemm128_kernel(const float* __restrict__ A, const float* __restrict__ wpacke
       const float rstd = 1.f / sqrtf((sRed[row] + sRed[128 + row]) * (1.f / 128.f) + 1e-6f);
       const float ws = n < N ? wsum[n] : 0.f;
       if (n < N) {
+        // pre-split copy for the pair ray kernel: sample s of ray r -> plane | chunk | row s, 16 bytes per (plane, chunk)
+        unsigned char* sp = nullptr;
+        if (out_split) {
+          const int64_t r = n / S_split;
+          sp = out_split + (size_t)r * S_split * 512 + (size_t)(n - r * S_split) * 16;
+        }
 #pragma unroll
-        for (int j = 0; j < 64; j += 4) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_g + c0 + j));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(ln_b + c0 + j));
-          float4 f;
-          f.x = (v[j] - mean) * rstd * g4.x + b4.x; f.y = (v[j + 1] - mean) * rstd * g4.y + b4.y;
-          f.z = (v[j + 2] - mean) * rstd * g4.z + b4.z; f.w = (v[j + 3] - mean) * rstd * g4.w + b4.w;
-          if (out_feature) *reinterpret_cast<float4*>(out_feature + n * W_HID + c0 + j) = f;
-          __stcs(reinterpret_cast<float4*>(out + n * W_HID + c0 + j), make_float4(f.x * ws, f.y * ws, f.z * ws, f.w * ws));
+        for (int j = 0; j < 64; j += 8) {
+          float o8[8];
+#pragma unroll
+          for (int h4 = 0; h4 < 8; h4 += 4) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(ln_g + c0 + j + h4));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ln_b + c0 + j + h4));
+            float4 f;
+            f.x = (v[j + h4] - mean) * rstd * g4.x + b4.x; f.y = (v[j + h4 + 1] - mean) * rstd * g4.y + b4.y;
+            f.z = (v[j + h4 + 2] - mean) * rstd * g4.z + b4.z; f.w = (v[j + h4 + 3] - mean) * rstd * g4.w + b4.w;
+            if (out_feature) *reinterpret_cast<float4*>(out_feature + n * W_HID + c0 + j + h4) = f;
+            o8[h4] = f.x * ws; o8[h4 + 1] = f.y * ws; o8[h4 + 2] = f.z * ws; o8[h4 + 3] = f.w * ws;
+            if (out) __stcs(reinterpret_cast<float4*>(out + n * W_HID + c0 + j + h4), make_float4(o8[h4], o8[h4 + 1], o8[h4 + 2], o8[h4 + 3]));
+          }
+          if (sp) {
+            const size_t co = (size_t)((c0 + j) >> 3) * S_split * 16;
+            tc::split_store8(sp + co, sp + (size_t)S_split * 256 + co, o8);
+          }
         }
       }
     }
@@ -669,8 +684,8 @@ size_t neighbor2_scratch_floats(int64_t N) { return (size_t)N * W_HID * 2 + (siz
 
 // scratch: q [N][128] | o [N][128] | wsum [N]  (neighbor2_scratch_floats(N) floats)
 int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
-                     const float* d2, const float* agg, float* fagg, float* feature, float* weights, float* scratch,
-                     cudaStream_t st) {
+                     const float* d2, const float* agg, float* fagg, unsigned char* fagg_split, int S_split, float* feature,
+                     float* weights, float* scratch, cudaStream_t st) {
   if (N <= 0) return 0;
   if (K < 1 || K > 8) return set_error("neighbor: K must be in 1..8");
   if (!scratch) return set_error("neighbor: scratch is NULL");
@@ -686,13 +701,15 @@ int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
   const int64_t t128 = (N + 127) / 128;
   const unsigned g128 = (unsigned)(t128 < sms ? t128 : sms);
-  nb2::row_gemm128_kernel<0><<<g128, NT, nb2::RG_SMEM, st>>>(agg, w.tb_wq, N, nullptr, nullptr, nullptr, nullptr, q, nullptr);
+  if (fagg_split && (S_split < 1 || N % S_split != 0)) return set_error("neighbor: the pre-split output needs whole rays");
+  nb2::row_gemm128_kernel<0><<<g128, NT, nb2::RG_SMEM, st>>>(agg, w.tb_wq, N, nullptr, nullptr, nullptr, nullptr, q, nullptr, nullptr, 1);
   if (check_launch("qproj_kernel")) return 1;
   const int64_t nst = (N + 2 * nb2::TP - 1) / (2 * nb2::TP);
   const unsigned grid = (unsigned)(nst < sms ? nst : sms);   // persistent: one CTA per SM
   nb2::neighbor2_kernel<<<grid, NT + 128, nb2::SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, q, o, wsum, weights);
   if (check_launch("neighbor2_kernel")) return 1;
-  nb2::row_gemm128_kernel<1><<<g128, NT, nb2::RG_SMEM, st>>>(o, w.tb_wfc, N, agg, w.ln_g, w.ln_b, wsum, fagg, feature);
+  nb2::row_gemm128_kernel<1><<<g128, NT, nb2::RG_SMEM, st>>>(o, w.tb_wfc, N, agg, w.ln_g, w.ln_b, wsum, fagg, feature, fagg_split,
+                                                             S_split < 1 ? 1 : S_split);
   return check_launch("attn_tail_kernel");
 }
 

@@ -31,9 +31,11 @@ int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, in
 // second generation (neighbor2.cu): q projection, 32-sample super-tiles with the attention projections on tcgen05, fc + LayerNorm
 // tail; `scratch` holds neighbor2_scratch_floats(N) floats
 size_t neighbor2_scratch_floats(int64_t N);
+// outputs: `fagg` fp32 [N][128] and / or `fagg_split` (the pair ray kernel's operand layout, samples grouped into rays of
+// `S_split`); either may be null
 int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
-                     const float* d2, const float* agg, float* fagg, float* feature, float* weights, float* scratch,
-                     cudaStream_t st);
+                     const float* d2, const float* agg, float* fagg, unsigned char* fagg_split, int S_split, float* feature,
+                     float* weights, float* scratch, cudaStream_t st);
 int launch_blend_project(const float* feat, int64_t P, const float* bl1v, float* out, cudaStream_t st);
 int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,
                   float* out, int ldo, cudaStream_t st);
@@ -44,8 +46,9 @@ int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_
                const FeatPeers& peers, cudaStream_t st);
 
 // pair kernel (render_ray2.cu): two rays per CTA, bf16x3 tcgen05; same contract as launch_ray
+// `xsplit`: feature_agg pre-split into bf16 hi | lo planes per ray, [R][2][16 chunks][S][8] (written by launch_neighbor2)
 int launch_ray2(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
-                const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
+                const unsigned char* xsplit, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                 float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
                 const FeatPeers& peers, cudaStream_t st);
 

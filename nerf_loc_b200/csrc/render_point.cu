@@ -16,6 +16,7 @@
 //   (2) in base_mlp_attn the query is the same vector for all K positions (model.py:413-414), so the K and V
 //       projections are folded onto the query / context side and `feature` has one distinct row per sample.
 #include <float.h>
+#include <stdlib.h>
 #include "nlb_common.cuh"
 #include "nlb_internal.h"
 #include "render_kernels.h"
@@ -94,9 +95,11 @@ constexpr int LDG = 420;   // 393 -> 416 (+4)
 
 // ROWS = (sample, view) rows per CTA.  128 rows fill the SM with one CTA; 64 rows fit two CTAs per SM (about 110 KB each), which
 // doubles the resident warps for the latency-bound gather phases.
-template <int ROWS>
+// FUSED (V <= 8): the gather of phase 5 feeds the mean / variance of phase 6 through registers, so the [ROWS][LDF] tile of
+// interpolated features does not exist and the arena only holds the decoder input; the 50 KB it saves per CTA go to the L1.
+template <int ROWS, bool FUSED>
 constexpr int agg_smem_floats() {
-  return STAGE_FLOATS + ROWS * LDF + (ROWS / 8) * LDG + (ROWS / 8) * 68 + ROWS * RI_N + (ROWS / 8) * 4;
+  return STAGE_FLOATS + ROWS * (FUSED ? LDX : LDF) + (ROWS / 8) * LDG + (ROWS / 8) * 68 + ROWS * RI_N + (ROWS / 8) * 4;
 }
 
 // visibility-weighted mean / variance over the views of one sample (ibrnet.py:8-12): one warp, lanes over channels
@@ -135,7 +138,7 @@ __device__ __forceinline__ void mean_var_rows(const float* __restrict__ f0, cons
   }
 }
 
-template <int ROWS>
+template <int ROWS, bool FUSED>
 __global__ void __launch_bounds__(NT, 128 / ROWS)
 aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int with_blend,
                  float* __restrict__ agg_out, float* __restrict__ partial_out, float* __restrict__ rgbvis_out,
@@ -145,7 +148,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   float* arena = sB + STAGE_FLOATS;
   constexpr int TP_MAX = ROWS / 8;
   constexpr int PARTS = NT / ROWS;  // threads per row in the per-row scalar phases
-  float* sG = arena + ROWS * LDF;
+  float* sG = arena + ROWS * (FUSED ? LDX : LDF);
   float* sO1 = sG + TP_MAX * LDG;
   float* sRI = sO1 + TP_MAX * 68;
   float* sPt = sRI + ROWS * RI_N;
@@ -155,8 +158,16 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int V = sc.V;
   const int TP = min(TP_MAX, ROWS / V);
-  const int64_t n0 = (int64_t)blockIdx.x * TP;
-  const int np = (int)min((int64_t)TP, N - n0);
+  // Which samples a tile holds.  Explicit point lists: TP consecutive points.  Ray samples (n = ray * S + s): the SAME sample
+  // index of TP consecutive rays - neighbouring rays at one depth project onto the same few pixels of a reference view (a
+  // quarter of a feature-map pixel apart for adjacent query pixels), consecutive samples of one ray do not (more than a pixel
+  // apart along the epipolar line), and the bilinear gathers of a tile are what this kernel waits for.
+  const bool by_ray = ps.xyz == nullptr;
+  const int64_t tile_g = by_ray ? (int64_t)blockIdx.x / ps.S : (int64_t)blockIdx.x;
+  const int tile_s = by_ray ? (int)((int64_t)blockIdx.x - tile_g * ps.S) : 0;
+  const int64_t n_items = by_ray ? N / ps.S : N;                     // rays or points
+  const int np = (int)min((int64_t)TP, n_items - tile_g * TP);
+  auto nidx = [&](int p) -> int64_t { return by_ray ? (tile_g * TP + p) * ps.S + tile_s : tile_g * TP + p; };
   const int rows = np * V;
   const float near_ = sc.near_, far_ = sc.far_;
 
@@ -182,7 +193,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     if (r < rows) {
       const int p = r / V, v = r - p * V;
       float x, y, z;
-      load_point(ps, n0 + p, x, y, z);
+      load_point(ps, nidx(p), x, y, z);
       const float* cam = sc.cams + v * 32;
       for (int job = part; job < 3; job += PARTS) {
         if (job == 0) {
@@ -413,7 +424,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     if (live) {
       ri[RI_DD] = dd;
       ri[RI_VIS] = vis;
-      if (mvv_out) mvv_out[n0 * V + tid] = vis;
+      if (mvv_out) mvv_out[nidx(tid / V) * V + (tid - (tid / V) * V)] = vis;
     }
     if (fused_w) {
       // ---- phase 4 fused (V == 8): per-sample view weights over the 8 lanes of a sample (same summation tree as warp_sum) --
@@ -437,7 +448,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         float* g = sG + p * LDG;
         if (v == 0) {
           g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
-          if (nvalid_out) nvalid_out[n0 + p] = (unsigned char)nval;
+          if (nvalid_out) nvalid_out[nidx(p)] = (unsigned char)nval;
         }
 #pragma unroll
         for (int j = 0; j < 3; ++j)
@@ -464,7 +475,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       float* g = sG + p * LDG;
       if (lane == 0) {
         g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
-        if (nvalid_out) nvalid_out[n0 + p] = (unsigned char)nval;
+        if (nvalid_out) nvalid_out[nidx(p)] = (unsigned char)nval;
       }
       if (lane < 23) g[393 + lane] = 0.f;
     }
@@ -473,6 +484,140 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   cta_sync();  // sX (arena) is dead from here on; view weights visible
 
   AGG_STAMP(4);
+  if (FUSED) {
+    // ---- phases 5 + 6 fused (V <= 8): one warp per SAMPLE.  The warp walks the sample's views two at a time (24 independent
+    // 8-byte loads in flight per lane), keeps the interpolated 192 map channels of all views in registers (lane l: channels
+    // 3 + 64 j + 2 l, + 1) and takes the visibility-weighted mean / variance (ibrnet.py:8-12) from there.  The warps of a CTA
+    // work on CONSECUTIVE samples of a ray at the same time: their footprints in a reference view are the same few pixels, so
+    // most of the 29 KB a sample gathers are L1 hits on lines a neighbouring warp has just requested.
+    float wb[8], bias = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wb[i] = 0.f;
+    if (with_blend) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) wb[i] = __ldg(w.bl1v + i * 32 + lane);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) wb[3 + i] = __ldg(w.bl1v + (195 + i) * 32 + lane);
+      bias = __ldg(w.bl1_b + lane);
+    }
+    for (int p = warp; p < np; p += NT / 32) {
+      float2 f[8][3];
+      float rgbv[8], wvv[8];
+#pragma unroll
+      for (int v0 = 0; v0 < 8; v0 += 2) {
+        float2 q[2][4][3];
+        float wt[2][4], bq[2][4];
+        float4 cq[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int v = v0 + u;
+          cq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            wt[u][t] = 0.f; bq[u][t] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) q[u][t][j] = make_float2(0.f, 0.f);
+          }
+          if (v < V) {
+            const float* ri = sRI + (p * V + v) * RI_N;
+            const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TF);
+            const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TF + 4);
+            const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
+            const float* tp[4] = {fb + (size_t)ti.x * C_FEAT, fb + (size_t)ti.y * C_FEAT, fb + (size_t)ti.z * C_FEAT, fb + (size_t)ti.w * C_FEAT};
+            const float twv[4] = {tw.x, tw.y, tw.z, tw.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              wt[u][t] = twv[t];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) q[u][t][j] = __ldg(reinterpret_cast<const float2*>(tp[t] + j * 64));
+            }
+            if (lane < 4) {
+              const float wi = ri[RI_TI + 4 + lane];
+              if (wi != 0.f) {
+                const int pix = __float_as_int(ri[RI_TI + lane]);
+                const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc.images + ((size_t)v * sc.H * sc.W + pix) * 4));
+                cq[u] = make_float4(c4.x * wi, c4.y * wi, c4.z * wi, 0.f);
+              }
+            }
+            if (with_blend) {
+              const float* bb = sc.featb + ((size_t)v * sc.h * sc.w) * 32 + lane;
+              bq[u][0] = __ldg(bb + (size_t)ti.x * 32);
+              bq[u][1] = __ldg(bb + (size_t)ti.y * 32);
+              bq[u][2] = __ldg(bb + (size_t)ti.z * 32);
+              bq[u][3] = __ldg(bb + (size_t)ti.w * 32);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int v = v0 + u;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              acc.x = fmaf(q[u][t][j].x, wt[u][t], acc.x);
+              acc.y = fmaf(q[u][t][j].y, wt[u][t], acc.y);
+            }
+            f[v][j] = acc;
+          }
+          rgbv[v] = 0.f; wvv[v] = 0.f;
+          if (v < V) {   // warp-uniform
+            float4 c = cq[u];
+            c.x += __shfl_xor_sync(0xffffffffu, c.x, 1); c.y += __shfl_xor_sync(0xffffffffu, c.y, 1); c.z += __shfl_xor_sync(0xffffffffu, c.z, 1);
+            c.x += __shfl_xor_sync(0xffffffffu, c.x, 2); c.y += __shfl_xor_sync(0xffffffffu, c.y, 2); c.z += __shfl_xor_sync(0xffffffffu, c.z, 2);
+            c.x = __shfl_sync(0xffffffffu, c.x, 0); c.y = __shfl_sync(0xffffffffu, c.y, 0); c.z = __shfl_sync(0xffffffffu, c.z, 0);
+            const float* ri = sRI + (p * V + v) * RI_N;
+            rgbv[v] = lane == 0 ? c.x : (lane == 1 ? c.y : c.z);
+            wvv[v] = ri[RI_W];
+            if (lane == 0 && rgbvis_out) __stcs(reinterpret_cast<float4*>(rgbvis_out + (nidx(p) * V + v) * 4), make_float4(c.x, c.y, c.z, ri[RI_VIS]));
+            if (with_blend) {
+              float a = 0.f;
+#pragma unroll
+              for (int t = 0; t < 4; ++t) a = fmaf(bq[u][t], wt[u][t], a);
+              a = fmaf(c.x, wb[0], a); a = fmaf(c.y, wb[1], a); a = fmaf(c.z, wb[2], a);
+              a = fmaf(ri[RI_VIS], wb[3], a);
+              a = fmaf(ri[RI_RD0], wb[4], a); a = fmaf(ri[RI_RD1], wb[5], a); a = fmaf(ri[RI_RD2], wb[6], a); a = fmaf(ri[RI_RD3], wb[7], a);
+              __stcs(partial_out + (nidx(p) * V + v) * 32 + lane, a + bias);
+            }
+            if (mvf_out) {
+              float* mo = mvf_out + (nidx(p) * V + v) * C_RGBF;
+              if (lane < 3) mo[lane] = rgbv[v];
+#pragma unroll
+              for (int j = 0; j < 3; ++j) { mo[3 + j * 64 + lane * 2] = f[v][j].x; mo[3 + j * 64 + lane * 2 + 1] = f[v][j].y; }
+            }
+          }
+        }
+      }
+      // visibility-weighted mean / variance over the views, same summation order as mean_var_rows
+      float* g = sG + p * LDG;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float mx = 0.f, my = 0.f;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) { mx += f[v][j].x * wvv[v]; my += f[v][j].y * wvv[v]; }
+        float vx = 0.f, vy = 0.f;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+          const float dx = f[v][j].x - mx, dy = f[v][j].y - my;
+          vx += wvv[v] * (dx * dx); vy += wvv[v] * (dy * dy);
+        }
+        const int c = 3 + j * 64 + lane * 2;
+        g[c] = mx; g[c + 1] = my;
+        g[C_RGBF + c] = vx; g[C_RGBF + c + 1] = vy;
+      }
+      if (lane < 3) {
+        float m = 0.f;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) m += rgbv[v] * wvv[v];
+        float var = 0.f;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) { const float d = rgbv[v] - m; var += wvv[v] * (d * d); }
+        g[lane] = m;
+        g[C_RGBF + lane] = var;
+      }
+    }
+  } else {
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
   // A warp handles two rows per iteration and requests everything they need before it consumes any of it: 2 x 4 taps x 3
   // chunks of the feature map (24 independent 8-byte loads per lane), the rgb taps (lanes 0..3, one tap each) and, for
@@ -564,7 +709,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           const int p = __float_as_int(ri[RI_P]), v = __float_as_int(ri[RI_V]);
           if (lane == 0) {
             frow[0] = c.x; frow[1] = c.y; frow[2] = c.z;
-            if (rgbvis_out) __stcs(reinterpret_cast<float4*>(rgbvis_out + ((n0 + p) * V + v) * 4), make_float4(c.x, c.y, c.z, ri[RI_VIS]));
+            if (rgbvis_out) __stcs(reinterpret_cast<float4*>(rgbvis_out + (nidx(p) * V + v) * 4), make_float4(c.x, c.y, c.z, ri[RI_VIS]));
           }
           if (with_blend) {
             float a = 0.f;
@@ -575,7 +720,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
             a = fmaf(ri[RI_RD0], wb[4], a); a = fmaf(ri[RI_RD1], wb[5], a); a = fmaf(ri[RI_RD2], wb[6], a); a = fmaf(ri[RI_RD3], wb[7], a);
             // per-chunk intermediates are written once and read once by the next kernel: streaming stores keep them from
             // evicting the reference feature maps (118 MB, gathered by every sample) out of the 126 MB L2
-            __stcs(partial_out + ((n0 + p) * V + v) * 32 + lane, a + bias);
+            __stcs(partial_out + (nidx(p) * V + v) * 32 + lane, a + bias);
           }
         }
       }
@@ -585,7 +730,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   if (mvf_out) {
     for (int i = tid; i < rows * C_RGBF; i += NT) {
       const int r = i / C_RGBF, c = i - r * C_RGBF;
-      mvf_out[(n0 * V + r) * C_RGBF + c] = sF[r * LDF + c];
+      mvf_out[(nidx(r / V) * V + (r - (r / V) * V)) * C_RGBF + c] = sF[r * LDF + c];
     }
   }
 
@@ -596,6 +741,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     if (V <= 8) mean_var_rows<8>(sF + (p * V) * LDF, sRI + (p * V) * RI_N, V, lane, sG + p * LDG);
     else mean_var_rows<16>(sF + (p * V) * LDF, sRI + (p * V) * RI_N, V, lane, sG + p * LDG);
   }
+  }
   for (int i = tid; i < (TP_MAX - np) * LDG; i += NT) sG[np * LDG + i] = 0.f;
 
   AGG_STAMP(7);
@@ -605,7 +751,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
                   [&](int r, int c, float v) { sO1[r * 68 + c] = elu(v + __ldg(w.fc1_b + c)); });
   cta_sync();
   rows16_gemm<128, TP_MAX, 64, 8>([&](int r, int) { return sO1 + r * 68; }, w.fc2, 128, sB, [&](int r, int c, float v) {
-    if (r < np) __stcs(agg_out + (n0 + r) * W_HID + c, elu(v + __ldg(w.fc2_b + c)));
+    if (r < np) __stcs(agg_out + nidx(r) * W_HID + c, elu(v + __ldg(w.fc2_b + c)));
   });
 
   AGG_STAMP(8);
@@ -688,11 +834,21 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   if (sc.V < 1 || sc.V > 16) return set_error("aggregate: number of reference views must be in 1..16");
   if (with_blend && !sc.featb) return set_error("aggregate: scene.featmaps_blend is NULL (call nlb_blend_prepare once per frame)");
   constexpr int ROWS = AGG_ROWS;
-  const size_t smem = agg_smem_floats<ROWS>() * sizeof(float);
-  if (set_smem(aggregate_kernel<ROWS>, smem)) return 1;
   const int TP = ROWS / 8 < ROWS / sc.V ? ROWS / 8 : ROWS / sc.V;
-  const unsigned grid = (unsigned)((N + TP - 1) / TP);
-  aggregate_kernel<ROWS><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
+  if (!ps.xyz && (ps.S < 1 || N % ps.S != 0)) return set_error("aggregate: ray samples must come as whole rays");
+  const int64_t tiles = ps.xyz ? (N + TP - 1) / TP : ((N / ps.S + TP - 1) / TP) * ps.S;
+  if (tiles > 0x7fffffffLL) return set_error("aggregate: too many tiles for one launch");
+  const unsigned grid = (unsigned)tiles;
+  static const bool unfused = getenv("NLB_AGG_UNFUSED") != nullptr;   // A/B switch
+  if (sc.V <= 8 && !unfused) {
+    const size_t smem = agg_smem_floats<ROWS, true>() * sizeof(float);
+    if (set_smem(aggregate_kernel<ROWS, true>, smem)) return 1;
+    aggregate_kernel<ROWS, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
+  } else {
+    const size_t smem = agg_smem_floats<ROWS, false>() * sizeof(float);
+    if (set_smem(aggregate_kernel<ROWS, false>, smem)) return 1;
+    aggregate_kernel<ROWS, false><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
+  }
   return check_launch("aggregate_kernel");
 }
 

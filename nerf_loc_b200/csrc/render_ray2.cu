@@ -79,6 +79,7 @@ struct Sync2 {
   uint64_t full[NS], empty[NS];
   uint64_t a_ready;
   uint64_t d_bar[N_DBAR];
+  uint64_t x_full;           // the x tiles of both rays have landed (bulk copies of the pre-split feature_agg)
   uint32_t tmem_slot;
   int nseg;
 };
@@ -120,36 +121,17 @@ __device__ __forceinline__ void zero_rows(unsigned char* hi, unsigned char* lo, 
   }
 }
 
-// x tile of one ray: rows 1 .. S of the chunk-major tile <- feature_agg [S][128] (fp32, streamed), split into bf16 hi | lo
-__device__ __forceinline__ void load_x(unsigned char* tile, const float* __restrict__ fagg, int64_t s0, int S, bool live, int tid) {
+// The x tile of a ray arrives by bulk copies (feature_agg is written pre-split by attn_tail_kernel, one [S x 8] bf16 run per
+// plane and chunk): the compute warps only clear the zero rows before and after the data - or the whole tile of a missing ray.
+__device__ __forceinline__ void prep_x(unsigned char* tile, int S, bool live, int tid) {
   unsigned char* hi = tile;
   unsigned char* lo = tile + X_PLANE;
-  // lanes run over rows of one chunk: 32-byte global sectors, conflict-free 16-byte shared stores; 4 items in flight per thread
-  for (int i0 = tid; i0 < S * 16; i0 += 4 * NT) {
-    float4 a[4][2];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * NT;
-      a[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); a[u][1] = a[u][0];
-      if (live && i < S * 16) {
-        const int s = i % S, c = i / S;
-        const float4* p = reinterpret_cast<const float4*>(fagg + (s0 + s) * W_HID + c * 8);
-        a[u][0] = __ldcs(p); a[u][1] = __ldcs(p + 1);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * NT;
-      if (i < S * 16) {
-        const int s = i % S, c = i / S;
-        const float v[8] = {a[u][0].x, a[u][0].y, a[u][0].z, a[u][0].w, a[u][1].x, a[u][1].y, a[u][1].z, a[u][1].w};
-        const uint32_t o = (uint32_t)c * RA_X * 16u + (uint32_t)(s + 1) * 16u;
-        tc::split_store8(hi + o, lo + o, v);
-      }
-    }
+  if (live) {
+    zero_rows(hi, lo, RA_X, 16, 0, 1, tid);
+    zero_rows(hi, lo, RA_X, 16, S + 1, 1, tid);
+  } else {
+    zero_rows(hi, lo, RA_X, 16, 0, S + 2, tid);
   }
-  zero_rows(hi, lo, RA_X, 16, 0, 1, tid);
-  zero_rows(hi, lo, RA_X, 16, S + 1, 1, tid);
 }
 
 // ---- encoder block at level 1 (conv1): per-ray accumulators [128 x 64] at TMEM columns 64 * ray -> LayerNorm([64, S]) + ELU +
@@ -357,9 +339,9 @@ __device__ __forceinline__ void epi_dec(const Ctx& c, const uint32_t tmem, const
   }
 }
 
-__global__ void __launch_bounds__(NT + 64, 1)
+__global__ void __launch_bounds__(NT + 128, 1)
 ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals, const int64_t zs, const int S, const int64_t R,
-            const int white_bkgd, const float* __restrict__ fagg, const float* __restrict__ partial,
+            const int white_bkgd, const unsigned char* __restrict__ xsplit, const float* __restrict__ partial,
             const float* __restrict__ rgbvis, const unsigned char* __restrict__ nvalid, float* __restrict__ rgb_out,
             float* __restrict__ depth_out, float* __restrict__ weights_out, unsigned char* __restrict__ mask_out,
             float* __restrict__ unc_out, float* __restrict__ feat_out, float* __restrict__ sigma_dbg, const FeatPeers peers) {
@@ -383,6 +365,7 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
     if (lane == 0) {
       for (int i = 0; i < NS; ++i) { tc::mbar_init(&sy.full[i], 1); tc::mbar_init(&sy.empty[i], 1); }
       tc::mbar_init(&sy.a_ready, NT);
+      tc::mbar_init(&sy.x_full, 1);
       for (int i = 0; i < N_DBAR; ++i) tc::mbar_init(&sy.d_bar[i], 1);
     }
   } else if (warp == 9 && lane == 0) {
@@ -449,7 +432,27 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
   tc::fence_after_sync();
   const uint32_t tmem = sy.tmem_slot;
 
-  if (warp == 9) {
+  if (warp >= 8) {
+   // service warpgroup: 8 = MMA issuer, 9 = weight producer, 10 = x loader (11 only keeps the register hand-over aligned)
+   tc::reg_dec<56>();
+   if (warp == 10) {
+    // ------------------------------------------------ x loader: pre-split feature_agg -> the two x tiles, twice -----------------
+    const int nlive = live1 ? 2 : 1;
+    for (int round = 0; round < 2; ++round) {
+      if (round == 1) { tc::mbar_wait(&sy.d_bar[D_TCONV1], 0); }     // region P is free again (trans_conv1 has consumed x1)
+      if (tc::elect_one()) {
+        tc::mbar_expect_tx(&sy.x_full, (uint32_t)(nlive * S * 512));
+        for (int ray = 0; ray < nlive; ++ray) {
+          const unsigned char* src = xsplit + (size_t)(ray0 + ray) * S * 512;
+          for (int pl = 0; pl < 2; ++pl)
+            for (int cch = 0; cch < 16; ++cch)
+              tc::bulk_copy(sm + ray * X_TILE + pl * X_PLANE + (uint32_t)cch * RA_X * 16u + 16u, src + (size_t)pl * S * 256 + (size_t)cch * S * 16,
+                            (uint32_t)(S * 16), &sy.x_full);
+        }
+      }
+      __syncwarp();
+    }
+   } else if (warp == 9) {
     // ------------------------------------------------ weight producer ---------------------------------------------------------
     uint32_t empty_par = 0;
     int i = 0;
@@ -470,7 +473,7 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
         __syncwarp();
       }
     }
-  } else if (warp == 8) {
+   } else if (warp == 8) {
     // ------------------------------------------------ MMA issuer -----------------------------------------------------------------
     uint32_t full_par = 0, a_par = 0;
     int i = 0;
@@ -523,8 +526,10 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
         __syncwarp();
       }
     }
+   }
   } else {
     // ------------------------------------------------ compute warps ------------------------------------------------------
+    tc::reg_inc<224>();
     Ctx c;
     c.sm = sm; c.red = red; c.tid = tid; c.lane = lane; c.warp = warp; c.wq = warp & 3; c.half = warp >> 2;
     c.m = c.wq * 32 + lane; c.trow = (uint32_t)(c.wq * 32) << 16; c.S = S;
@@ -533,12 +538,13 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
     const int64_t sbase[2] = {ray0 * S, (ray0 + 1) * S};
 
     R2_STAMP(0);
-    load_x(sm, fagg, sbase[0], S, true, tid);
-    load_x(sm + X_TILE, fagg, sbase[1], S, live1, tid);
+    prep_x(sm, S, true, tid);
+    prep_x(sm + X_TILE, S, live1, tid);
     {
       const int ray = tid >> 7, s = tid & 127;
       if (s < S) sV[ray * 512 + 384 + s] = (ray == 0 || live1) ? z_vals[(ray0 + ray) * zs + s] : 0.f;
     }
+    tc::mbar_wait(&sy.x_full, 0);
     a_ready();                                                             // a#0: x of both rays
     R2_STAMP(1);
 
@@ -561,17 +567,28 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
         for (int j = 0; j < 16; ++j) sBl[c.m * 36 + c.half * 16 + j] = v[j];
       }
       cta_sync();
-      for (int i0 = tid; i0 < S * V; i0 += 2 * NT) {
-        const int i1 = i0 + NT;
-        const bool two = i1 < S * V;
-        const int ib[2] = {i0, two ? i1 : i0};
-        float4 pa[2][8];
+      // two (sample, view) items per thread and iteration; the rows of `partial` (streamed from HBM, written by aggregate_kernel
+      // a chunk ago) of the NEXT iteration are requested before the current one is evaluated
+      const int n_it = (S * V + 2 * NT - 1) / (2 * NT);
+      float4 pa[2][8], pn[2][8];
+      auto fetch = [&](int it, float4 (&dst)[2][8]) {
+        const int i0 = it * 2 * NT + tid, i1 = i0 + NT;
+        const int ib[2] = {i0 < S * V ? i0 : 0, i1 < S * V ? i1 : (i0 < S * V ? i0 : 0)};
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const float4* pp = reinterpret_cast<const float4*>(partial + (s0 * V + ib[u]) * 32);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) pa[u][q] = __ldcs(pp + q);   // streamed once
+          for (int q = 0; q < 8; ++q) dst[u][q] = __ldcs(pp + q);   // streamed once
         }
+      };
+      fetch(0, pa);
+      for (int it = 0; it < n_it; ++it) {
+        const int i0 = it * 2 * NT + tid, i1 = i0 + NT;
+        const bool one = i0 < S * V, two = i1 < S * V;
+        const int ib[2] = {one ? i0 : 0, two ? i1 : (one ? i0 : 0)};
+        const float vis0 = one ? __ldg(rgbvis + (s0 * V + i0) * 4 + 3) : 0.f;
+        const float vis1 = two ? __ldg(rgbvis + (s0 * V + i1) * 4 + 3) : 0.f;
+        if (it + 1 < n_it) fetch(it + 1, pn);
         float h1[2][32];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -600,18 +617,31 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
           logit0 = fmaf(w3, leaky(a + a1), logit0);
           logit1 = fmaf(w3, leaky(cacc + c1), logit1);
         }
-        sLogit[i0] = __ldg(rgbvis + (s0 * V + i0) * 4 + 3) == 0.f ? -1e9f : logit0;
-        if (two) sLogit[i1] = __ldg(rgbvis + (s0 * V + i1) * 4 + 3) == 0.f ? -1e9f : logit1;
+        if (one) sLogit[i0] = vis0 == 0.f ? -1e9f : logit0;
+        if (two) sLogit[i1] = vis1 == 0.f ? -1e9f : logit1;
+        if (it + 1 < n_it) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) pa[u][q] = pn[u][q];
+        }
       }
       cta_sync();
       if (tid < S) {
+        // softmax over the views and the blended colour; the V colour rows are requested together, ahead of the exponentials
+        float4 cv[16];
+#pragma unroll
+        for (int v = 0; v < 16; ++v)
+          cv[v] = v < V ? __ldg(reinterpret_cast<const float4*>(rgbvis + ((s0 + tid) * V + v) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float mx = -FLT_MAX;
         for (int v = 0; v < V; ++v) mx = fmaxf(mx, sLogit[tid * V + v]);
         float den = 0.f, r = 0.f, g = 0.f, bl = 0.f;
-        for (int v = 0; v < V; ++v) {
-          const float e = expf(sLogit[tid * V + v] - mx);
-          const float4 cv = __ldg(reinterpret_cast<const float4*>(rgbvis + ((s0 + tid) * V + v) * 4));
-          den += e; r += cv.x * e; g += cv.y * e; bl += cv.z * e;
+#pragma unroll
+        for (int v = 0; v < 16; ++v) {
+          if (v < V) {
+            const float e = expf(sLogit[tid * V + v] - mx);
+            den += e; r += cv[v].x * e; g += cv[v].y * e; bl += cv[v].z * e;
+          }
         }
         sRGB[ray * 512 + tid * 4] = r / den; sRGB[ray * 512 + tid * 4 + 1] = g / den; sRGB[ray * 512 + tid * 4 + 2] = bl / den;
       }
@@ -648,8 +678,9 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
     wait_d(D_TCONV1);
     R2_STAMP(14);
     epi_dec<32, true>(c, tmem, S / 2, w.u[5], sm + Q_OFF, sm + Q_OFF + X2_PLANE, RA_X, X2_TILE);
-    load_x(sm, fagg, sbase[0], S, true, tid);                              // x again (region P was recycled)
-    load_x(sm + X_TILE, fagg, sbase[1], S, live1, tid);
+    prep_x(sm, S, true, tid);                                              // x again (region P was recycled)
+    prep_x(sm + X_TILE, S, live1, tid);
+    tc::mbar_wait(&sy.x_full, 1);
     a_ready();                                                             // a#6: x | x2
     R2_STAMP(15);
 
@@ -823,7 +854,7 @@ int read_prof_ray2(long long* out, int n) {
 }
 
 int launch_ray2(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
-                const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
+                const unsigned char* xsplit, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
                 float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
                 const FeatPeers& peers, cudaStream_t st) {
   if (R <= 0) return 0;
@@ -832,7 +863,7 @@ int launch_ray2(const SceneDev& sc, const RenderW& w, const float* z_vals, int64
   if (sc.V > 16) return set_error("ray stage: at most 16 reference views");
   cudaError_t e = cudaFuncSetAttribute(r2::ray2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r2::SMEM_BYTES);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-  r2::ray2_kernel<<<(unsigned)((R + 1) / 2), NT + 64, r2::SMEM_BYTES, st>>>(sc, w, z_vals, zs, S, R, white_bkgd, fagg, partial, rgbvis,
+  r2::ray2_kernel<<<(unsigned)((R + 1) / 2), NT + 128, r2::SMEM_BYTES, st>>>(sc, w, z_vals, zs, S, R, white_bkgd, xsplit, partial, rgbvis,
                                                                            nvalid, rgb, depth, weights, mask, depth_unc, feat,
                                                                            sigma_dbg, peers);
   return check_launch("ray2_kernel");
