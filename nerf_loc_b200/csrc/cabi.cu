@@ -166,7 +166,7 @@ int nlb_blend_prepare(const float* packed_weights, int S, const float* featmaps,
 size_t nlb_query_scratch_bytes(int64_t N, int K) {
   if (N < 1) N = 1;
   return align256((size_t)N * K * 4) + align256((size_t)N * K * 4) + align256((size_t)N * W_HID * 4) +
-         align256(neighbor2_scratch_floats(N) * 4) + 1024;
+         align256(neighbor2_scratch_floats(N) * 4) + align256((size_t)N * 16 * 8) + 1024;   // visibility | depth difference: <= 16 views
 }
 
 int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S, const float* xyz,
@@ -183,12 +183,13 @@ int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S,
   float* d2 = knn_d2 ? knn_d2 : c.take<float>((size_t)N * K);
   float* agg = aggregated ? aggregated : c.take<float>((size_t)N * W_HID);
   float* nb2 = c.take<float>(neighbor2_scratch_floats(N));
+  float* visdd = c.take<float>((size_t)N * scene->V * 2);
   if (!c.ok) return set_error("nlb_query_points: scratch too small (see nlb_query_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
   PointSrc ps{xyz, direction, nullptr, nullptr, nullptr, 1, 0};
   if (knn_query(sc.knn, xyz, N, K, nullptr, idx, d2, st)) return 1;
-  if (launch_aggregate(sc, w, ps, N, 0, agg, nullptr, nullptr, nullptr, mv_feature, mv_visibility, st)) return 1;
+  if (launch_aggregate(sc, w, ps, N, 0, agg, nullptr, nullptr, nullptr, mv_feature, mv_visibility, visdd, st)) return 1;
   if (nb_v1()) return launch_neighbor(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, st);
   return launch_neighbor2(sc, w, ps, N, K, idx, d2, agg, feature_agg, nullptr, 0, feature, weights, nb2, st);
 }
@@ -201,7 +202,8 @@ int nlb_aggregate_points(const nlb_scene* scene, const float* packed_weights, in
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
   PointSrc ps{xyz, nullptr, nullptr, nullptr, nullptr, 1, 0};
-  return launch_aggregate(sc, w, ps, N, 0, aggregated, nullptr, nullptr, nullptr, mv_feature, mv_visibility,
+  // (no scratch in this entry point's signature: the decoder stays inside aggregate_kernel)
+  return launch_aggregate(sc, w, ps, N, 0, aggregated, nullptr, nullptr, nullptr, mv_feature, mv_visibility, nullptr,
                           (cudaStream_t)stream);
 }
 
@@ -226,13 +228,15 @@ size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
   const size_t slabs = S > 128 ? align256((size_t)RL_MAX_GRID * ray_long_slab_floats(S) * 4) : 0;
   // KNN lists are double buffered: the search of chunk i+1 runs on a side stream underneath the ray kernel of chunk i
   return align256(n * KNN_K * 4) * 4 + align256(n * W_HID * 4) * 2 + align256(n * V * 32 * 4) + align256(n * V * 16) +
-         align256(n) + align256(neighbor2_scratch_floats((int64_t)n) * 4) + slabs + 2048;
+         align256(n) + align256(neighbor2_scratch_floats((int64_t)n) * 4) + align256(n * V * 8) + slabs + 2048;
 }
 
 int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays) {
   if (R <= 0) return 0;
   if (chunk_rays < 1) chunk_rays = R;
-  return (nb_v1() ? 4 : 6) * ((R + chunk_rays - 1) / chunk_rays);   // KNN, aggregate, [q projection,] neighbour, [attention tail,] ray
+  static const bool agg_v1 = getenv("NLB_AGG_V1") != nullptr;
+  // KNN, [visibility,] aggregate, [q projection,] neighbour, [attention tail,] ray
+  return ((nb_v1() ? 4 : 6) + (agg_v1 ? 0 : 1)) * ((R + chunk_rays - 1) / chunk_rays);
 }
 
 static int render_rays_impl(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
@@ -269,6 +273,7 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
   float* rgbvis = c.take<float>(n * V * 4);
   unsigned char* nvalid = c.take<unsigned char>(n);
   float* nb2 = c.take<float>(neighbor2_scratch_floats((int64_t)n));
+  float* visdd = c.take<float>(n * V * 2);
   float* slabs = S > 128 ? c.take<float>((size_t)RL_MAX_GRID * ray_long_slab_floats(S)) : nullptr;
   if (!c.ok) return set_error("nlb_render_rays: scratch too small (see nlb_render_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
@@ -321,7 +326,7 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
     prof.mark();
     if (!overlap && knn_chunk(i, st)) { rc_err = 1; break; }
     prof.mark();
-    if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, st)) { rc_err = 1; break; }
+    if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, visdd, st)) { rc_err = 1; break; }
     prof.mark();
     if (overlap) cudaStreamWaitEvent(st, ev_knn[i & 1], 0);
     if (nb_v1() ? launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)

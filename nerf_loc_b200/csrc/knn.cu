@@ -27,7 +27,7 @@ namespace nlb {
 #define NLB_KNN_LEAF 8
 #endif
 #ifndef NLB_KNN_FAN
-#define NLB_KNN_FAN 8
+#define NLB_KNN_FAN 4      // measured on the 153,600-point frame (ray search, ms): fan-out 8: 134, 4: 116, 3: 116, 2: 142
 #endif
 constexpr int LEAF = NLB_KNN_LEAF;
 constexpr int FAN = NLB_KNN_FAN;
@@ -366,44 +366,6 @@ struct TopK {
 
 // `bound`: a squared distance that at least K support points are known to lie within (FLT_MAX if unknown).  Nothing
 // strictly farther than it can be part of the answer, so it prunes exactly like the running K-th distance does.
-// Cheap exact upper bound of the K-th distance for a search that has nothing to start from: walk down the tree taking the
-// nearest child box at every level and measure the points of the leaf that is reached (LEAF >= K real support points).
-template <int K>
-__device__ __forceinline__ float knn_greedy_bound(const KnnTree& t, float qx, float qy, float qz) {
-  if (K > LEAF) return FLT_MAX;
-  int lvl = t.n_levels - 1;
-  int node = 0;
-  {
-    float bd = FLT_MAX;
-    for (int n = 0; n < t.level_count[lvl]; ++n) {
-      const float d = node_d2(qx, qy, qz, t.boxes + t.level_off[lvl] + NODE_F4 * n);
-      if (d < bd) { bd = d; node = n; }
-    }
-  }
-  for (; lvl > 0; --lvl) {
-    const int cl = lvl - 1, c0 = node * FAN, nc = min(FAN, t.level_count[cl] - c0);
-    float bd = FLT_MAX;
-    int bestc = c0;
-#pragma unroll
-    for (int k = 0; k < FAN; ++k) {
-      if (k < nc) {
-        const float d = node_d2(qx, qy, qz, t.boxes + t.level_off[cl] + NODE_F4 * (c0 + k));
-        if (d < bd) { bd = d; bestc = c0 + k; }
-      }
-    }
-    node = bestc;
-  }
-  const int64_t p0 = (int64_t)node * LEAF;
-  if (p0 + K > t.M) return FLT_MAX;
-  float b = 0.f;
-#pragma unroll
-  for (int k = 0; k < K; ++k) {
-    const float4 p = t.pts[p0 + k];
-    b = fmaxf(b, d2_exact(qx, qy, qz, p.x, p.y, p.z));
-  }
-  return b;
-}
-
 template <int K>
 __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy, float qz, TopK<K>& best,
                                            const float bound = FLT_MAX) {
@@ -505,7 +467,7 @@ template <int K>
 __global__ void __launch_bounds__(128) knn_query_rays_kernel(const void* __restrict__ index, const float* __restrict__ rays_o,
                                                              const float* __restrict__ rays_d, const float* __restrict__ z_vals,
                                                              const float* __restrict__ sup_geo, int64_t R, int S, int SEG,
-                                                             int64_t zs, int* idx32, float* dist2, const int greedy) {
+                                                             int64_t zs, int* idx32, float* dist2) {
   __shared__ KnnTree tree;
   if (threadIdx.x == 0) tree = load_tree(index);
   __syncthreads();
@@ -524,7 +486,6 @@ __global__ void __launch_bounds__(128) knn_query_rays_kernel(const void* __restr
     const float qy = __fadd_rn(oy, __fmul_rn(dy, z));
     const float qz = __fadd_rn(oz, __fmul_rn(dz, z));
     float bound = FLT_MAX;
-    if (!have_prev && greedy) bound = knn_greedy_bound<K>(tree, qx, qy, qz);
     if (have_prev) {
       bound = 0.f;
 #pragma unroll
@@ -547,172 +508,6 @@ __global__ void __launch_bounds__(128) knn_query_rays_kernel(const void* __restr
 }
 
 
-// ---- cooperative variant: EIGHT lanes per query (K = LEAF = FAN = 8) ---------------------------------------------------------
-// The per-thread walk above is bound by the load/store unit: every node visit is 16 divergent 16-byte loads per lane plus
-// local-memory stack traffic (ncu r1i: LSU data pipe 73 %, L1 hit 96 %).  Here a group of 8 lanes shares one query: lane j
-// tests child j of an inner node (its two box corners: the group reads one contiguous 256-byte run) or point j of a leaf, the
-// running K best are held one per lane, sorted by (distance, index) across the group, the traversal stack lives in shared
-// memory (one entry pushed per passing child, nearest on top) and all decisions are group-wide ballots / shuffles.  Same
-// distance arithmetic, same pruning rule, same tie-break as knn_search: the results are identical bit for bit.
-constexpr int G8_STACK = 88;     // 8 + 7 per level below the top, 12 levels at most
-
-__device__ __forceinline__ unsigned g8_ballot(unsigned gmask, int gshift, bool p) { return (__ballot_sync(gmask, p) >> gshift) & 0xffu; }
-
-struct G8 {
-  unsigned gmask;
-  int gshift, gl;
-  uint2* stk;
-  int sp;
-  // pushes the children whose `passed` is set; the nearest one ends on top of the stack
-  __device__ __forceinline__ void push(const unsigned code, const float dist, const bool passed) {
-    float md = passed ? dist : FLT_MAX;
-    int ml = gl;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      const float od = __shfl_xor_sync(gmask, md, o);
-      const int ol = __shfl_xor_sync(gmask, ml, o);
-      if (od < md || (od == md && ol < ml)) { md = od; ml = ol; }
-    }
-    const unsigned pm = g8_ballot(gmask, gshift, passed);
-    if (pm) {
-      const unsigned others = pm & ~(1u << ml);
-      if (passed) {
-        const int pos = gl == ml ? __popc(others) : __popc(others & ((1u << gl) - 1u));
-        stk[sp + pos] = make_uint2(code, __float_as_uint(dist));
-      }
-      sp += __popc(pm);
-    }
-    __syncwarp(gmask);
-  }
-};
-
-__global__ void __launch_bounds__(128) knn_query_rays_g8_kernel(const void* __restrict__ index, const float* __restrict__ rays_o,
-                                                                const float* __restrict__ rays_d, const float* __restrict__ z_vals,
-                                                                const float* __restrict__ sup_geo, int64_t R, int S, int SEG,
-                                                                int64_t zs, int* idx32, float* dist2) {
-  __shared__ KnnTree tree;
-  __shared__ uint2 stack_mem[16][G8_STACK];
-  if (threadIdx.x == 0) tree = load_tree(index);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 3;
-  G8 g8;
-  g8.gl = lane & 7;
-  g8.gshift = lane & 24;
-  g8.gmask = 0xffu << g8.gshift;
-  g8.stk = stack_mem[grp];
-  const unsigned gmask = g8.gmask;
-  const int gshift = g8.gshift, gl = g8.gl;
-  const int64_t g = blockIdx.x * 16ll + grp;
-  const int nseg = (S + SEG - 1) / SEG;
-  if (g >= R * nseg) return;     // a whole group leaves together
-  const int64_t r = g % R;
-  const int s0 = (int)(g / R) * SEG;
-  const float ox = rays_o[r * 3 + 0], oy = rays_o[r * 3 + 1], oz = rays_o[r * 3 + 2];
-  const float dx = rays_d[r * 3 + 0], dy = rays_d[r * 3 + 1], dz = rays_d[r * 3 + 2];
-  const int top = tree.n_levels - 1;
-  float bd = FLT_MAX;            // this lane's entry (rank gl) of the sorted K-best list
-  int bi = 0x7fffffff;
-  bool have_prev = false;
-  auto group_max = [&](float v) {
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(gmask, v, o));
-    return v;
-  };
-  for (int s = s0; s < min(S, s0 + SEG); ++s) {
-    const float z = z_vals[r * zs + s];
-    const float qx = __fadd_rn(ox, __fmul_rn(dx, z));
-    const float qy = __fadd_rn(oy, __fmul_rn(dy, z));
-    const float qz = __fadd_rn(oz, __fmul_rn(dz, z));
-    // exact pruning radius: the previous sample's K neighbours are real points (one per lane); without them, the leaf reached
-    // by always taking the nearest child box
-    float bound = FLT_MAX;
-    if (have_prev) {
-      const float4 p = __ldg(reinterpret_cast<const float4*>(sup_geo + (size_t)bi * 8));
-      bound = group_max(d2_exact(qx, qy, qz, p.x, p.y, p.z));
-    } else {
-      int node = 0;
-      for (int lvl = top; lvl >= 0; --lvl) {
-        // candidates: the nodes of the top level, later the children of `node`
-        const int c0 = lvl == top ? 0 : node * FAN;
-        const int nc = min(FAN, tree.level_count[lvl] - c0);
-        float d = FLT_MAX;
-        if (gl < nc) d = node_d2(qx, qy, qz, tree.boxes + tree.level_off[lvl] + NODE_F4 * (c0 + gl));
-        int ml = gl;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-          const float od = __shfl_xor_sync(gmask, d, o);
-          const int ol = __shfl_xor_sync(gmask, ml, o);
-          if (od < d || (od == d && ol < ml)) { d = od; ml = ol; }
-        }
-        node = c0 + ml;
-      }
-      const int64_t p0 = (int64_t)node * LEAF;
-      if (p0 + LEAF <= tree.M) {
-        const float4 p = tree.pts[p0 + gl];
-        bound = group_max(d2_exact(qx, qy, qz, p.x, p.y, p.z));
-      }
-    }
-    bd = FLT_MAX; bi = 0x7fffffff;
-    float worst = FLT_MAX;
-    int worst_i = 0x7fffffff;
-    g8.sp = 0;
-    {
-      const int nc = min(FAN, tree.level_count[top]);
-      float d = FLT_MAX;
-      if (gl < nc) d = node_d2(qx, qy, qz, tree.boxes + tree.level_off[top] + NODE_F4 * gl);
-      g8.push(((unsigned)top << 28) | (unsigned)gl, d, gl < nc && d <= bound);
-    }
-    while (g8.sp > 0) {
-      --g8.sp;
-      const uint2 e = g8.stk[g8.sp];
-      const float nd = __uint_as_float(e.y);
-      const float w = fminf(worst, bound);
-      if (nd > w) continue;      // strict: equal distance may still hide a smaller index
-      const int lvl = e.x >> 28;
-      const int node = e.x & 0x0fffffffu;
-      if (lvl == 0) {
-        const int64_t pi = (int64_t)node * LEAF + gl;
-        const bool valid = pi < tree.M;
-        float d = FLT_MAX;
-        int id = 0x7fffffff;
-        if (valid) {
-          const float4 p = tree.pts[pi];
-          d = d2_exact(qx, qy, qz, p.x, p.y, p.z);
-          id = __float_as_int(p.w);
-        }
-        unsigned m = g8_ballot(gmask, gshift, valid && d <= bound && (d < worst || (d == worst && id < worst_i)));
-        while (m) {
-          const int j = __ffs(m) - 1;
-          m &= m - 1;
-          const float cd = __shfl_sync(gmask, d, gshift + j);
-          const int ci = __shfl_sync(gmask, id, gshift + j);
-          if (!(cd < worst || (cd == worst && ci < worst_i))) continue;   // the list may have tightened since the ballot
-          // entries smaller than the candidate are a prefix of the sorted list: its length is the insert position
-          const int pos = __popc(g8_ballot(gmask, gshift, bd < cd || (bd == cd && bi < ci)));
-          const float pd = __shfl_up_sync(gmask, bd, 1, 8);
-          const int pidx = __shfl_up_sync(gmask, bi, 1, 8);
-          if (gl > pos) { bd = pd; bi = pidx; }
-          else if (gl == pos) { bd = cd; bi = ci; }
-          worst = __shfl_sync(gmask, bd, gshift + 7);
-          worst_i = __shfl_sync(gmask, bi, gshift + 7);
-        }
-      } else {
-        const int cl = lvl - 1;
-        const int c0 = node * FAN;
-        const int nc = min(FAN, tree.level_count[cl] - c0);
-        float d = FLT_MAX;
-        if (gl < nc) d = node_d2(qx, qy, qz, tree.boxes + tree.level_off[cl] + NODE_F4 * (c0 + gl));
-        g8.push(((unsigned)cl << 28) | (unsigned)(c0 + gl), d, gl < nc && d <= w);
-      }
-    }
-    const int64_t i = r * S + s;
-    have_prev = worst_i != 0x7fffffff;
-    const bool ok = bi != 0x7fffffff;   // fewer than K support points: pad with zeros like the reference
-    __stcs(idx32 + i * 8 + gl, ok ? bi : 0);
-    __stcs(dist2 + i * 8 + gl, ok ? bd : 0.f);
-  }
-}
-
 int knn_query(const void* index, const float* p1, int64_t N, int K, int64_t* idx64, int* idx32, float* dist2,
               cudaStream_t st) {
   if (N <= 0) return 0;
@@ -733,19 +528,11 @@ int knn_query_rays(const void* index, const float* rays_o, const float* rays_d, 
                    const float* sup_geo, int64_t R, int S, int* idx32, float* dist2, cudaStream_t st) {
   if (R * S <= 0) return 0;
   const int T = 128;
-  static const int seg_env = getenv("NLB_KNN_SEG") ? atoi(getenv("NLB_KNN_SEG")) : 0;
-  static const int greedy = getenv("NLB_KNN_GREEDY") ? atoi(getenv("NLB_KNN_GREEDY")) : 0;
-  static const bool v1 = getenv("NLB_KNN_V1") != nullptr;   // A/B switch: one thread per query
+  static const int seg_env = getenv("NLB_KNN_SEG") ? atoi(getenv("NLB_KNN_SEG")) : 0;   // A/B switch
   const int SEG = seg_env > 0 ? seg_env : (S >= 64 ? 16 : 8);
-  if (!v1 && LEAF == 8 && FAN == 8) {
-    const int64_t groups = R * ((S + SEG - 1) / SEG);
-    knn_query_rays_g8_kernel<<<(unsigned)((groups + 15) / 16), 128, 0, st>>>(index, rays_o, rays_d, z_vals, sup_geo, R, S, SEG, zs,
-                                                                            idx32, dist2);
-    return check_launch("knn_query_rays_g8");
-  }
   const int64_t threads = R * ((S + SEG - 1) / SEG);
   knn_query_rays_kernel<8><<<(unsigned)((threads + T - 1) / T), T, 0, st>>>(index, rays_o, rays_d, z_vals, sup_geo, R, S, SEG,
-                                                                           zs, idx32, dist2, greedy);
+                                                                           zs, idx32, dist2);
   return check_launch("knn_query_rays");
 }
 

@@ -69,6 +69,8 @@ struct RenderW {
   // bf16x3 copies for the neighbour kernels (neighbor2.cu): [N = 128][K] operands as K-tiles of 32 ([hi | lo], 16 KB each);
   // tb_w1b in the K order neighbor2_kernel writes its layer-1 operand (pack.cu::tcb_src_index)
   const float *tb_w1b, *tb_w2, *tb_w3, *tb_wq, *tb_wk, *tb_wv, *tb_wfc;
+  // visibility decoder (visibility.cu): layer 1 of the four heads as one [128 x 32] tile, layer 2 as four [32 x 32] tiles
+  const float *tb_dec1, *tb_dec2;
   const float *sig_w, *sig_b;   // [128], [1]
   const float *ft1, *ft1_b;     // [128][128], [128]
   const float *ft2, *ft2_b;     // [128][192], [192]

@@ -84,6 +84,7 @@ static RenderW layout(const float* base, int S, size_t* total) {
   w.tb_ft1 = a.take(128 * 128);
   w.tb_w1b = a.take(128 * 96);
   w.tb_w2 = a.take(128 * 128); w.tb_w3 = a.take(128 * 128);
+  w.tb_dec1 = a.take(128 * 32); w.tb_dec2 = a.take(4 * 32 * 32);
   w.tb_wq = a.take(128 * 128); w.tb_wk = a.take(128 * 128); w.tb_wv = a.take(128 * 128); w.tb_wfc = a.take(128 * 128);
   w.sig_w = a.take(128); w.sig_b = a.take(1);
   w.ft1 = a.take(128 * 128); w.ft1_b = a.take(128);
@@ -158,13 +159,14 @@ __global__ void pack_tcb_kernel(float* dst, const float* __restrict__ src, int N
 
 // bf16x3 B operand (tc_bf16.cuh): W [N][K] -> per K-tile of `ktile` columns: hi tile then lo tile, each in the weight-tile
 // layout (8-row x 16-byte core matrices, adjacent in K contiguous, 8-row groups ktile*16 bytes apart); hi = bf16(x), lo = bf16(x - hi)
+// (n_off, N_total): the N rows packed by this call are rows n_off.. of a tile with N_total rows (several sources side by side)
 __global__ void pack_tcb16_kernel(uint16_t* dst, const float* __restrict__ src, int N, int K, int src_ld, int src_off, int src_ks,
-                                  int ktile, int Kv, int perm) {
+                                  int ktile, int Kv, int perm, int n_off, int N_total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
-  const int n = i / K, k = i % K;
+  const int n0 = i / K, k = i % K, n = n0 + n_off;
   const int ksrc = tcb_src_index(k, perm);
-  const float x = (ksrc >= 0 && ksrc < Kv) ? src[(size_t)n * src_ld + src_off + (size_t)ksrc * src_ks] : 0.f;
+  const float x = (ksrc >= 0 && ksrc < Kv) ? src[(size_t)n0 * src_ld + src_off + (size_t)ksrc * src_ks] : 0.f;
   const uint32_t xb = __float_as_uint(x);
   // round to nearest even by hand (identical to __float2bfloat16_rn for finite values)
   const uint32_t hb = (xb + 0x7FFFu + ((xb >> 16) & 1u)) >> 16;
@@ -172,10 +174,10 @@ __global__ void pack_tcb16_kernel(uint16_t* dst, const float* __restrict__ src, 
   const uint32_t rb = __float_as_uint(r);
   const uint32_t lb = (rb + 0x7FFFu + ((rb >> 16) & 1u)) >> 16;
   const int kt = k / ktile, kl = k % ktile;
-  const size_t base = (size_t)kt * (2 * N * ktile);
+  const size_t base = (size_t)kt * (2 * N_total * ktile);
   const size_t off = (size_t)(n / 8) * (ktile * 8) + (size_t)(kl / 8) * 64 + (n % 8) * 8 + (kl % 8);
   dst[base + off] = (uint16_t)hb;
-  dst[base + (size_t)N * ktile + off] = (uint16_t)lb;
+  dst[base + (size_t)N_total * ktile + off] = (uint16_t)lb;
 }
 
 namespace {
@@ -196,10 +198,11 @@ struct Packer {
     pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv, src_ks,
                                                      2048 / N, perm);
   }
-  void tcb16(const float* dst, int src, int N, int K, int src_ld, int src_off, int src_ks, int ktile, int Kv = -1, int perm = 0) {
+  void tcb16(const float* dst, int src, int N, int K, int src_ld, int src_off, int src_ks, int ktile, int Kv = -1, int perm = 0,
+             int n_off = 0, int N_total = -1) {
     const int n = N * K;
     pack_tcb16_kernel<<<(n + 255) / 256, 256, 0, st>>>(reinterpret_cast<uint16_t*>(const_cast<float*>(dst)), p[src], N, K, src_ld,
-                                                       src_off, src_ks, ktile, Kv < 0 ? K : Kv, perm);
+                                                       src_off, src_ks, ktile, Kv < 0 ? K : Kv, perm, n_off, N_total < 0 ? N : N_total);
   }
   void conv(const float* dst, int src, int Cin, int Cout, int ntaps, int t0, int t1, int t2, bool tr) {
     const int n = ntaps * Cin * Cout;
@@ -297,6 +300,10 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
         else k.tcb16(w.tb_u[l][t], b, co, ci, ci * 3, t, 3, KT16[l]);             // Conv1d weight [co][ci][3]
       }
     }
+  }
+  for (int h = 0; h < 4; ++h) {
+    k.tcb16(w.tb_dec1, DEC + 6 * h + 0, 32, 32, 32, 0, 1, 32, -1, 0, 32 * h, 128);   // rows 32 h .. of the [128 x 32] tile
+    k.tcb16(w.tb_dec2 + 32 * 32 * h, DEC + 6 * h + 2, 32, 32, 32, 0, 1, 32);
   }
   k.tcb16(w.tb_w1b, BM0_W, 128, 96, 285, 195, 1, 32, 90, 1);
   k.tcb16(w.tb_w2, BM2_W, 128, 128, 128, 0, 1, 32);

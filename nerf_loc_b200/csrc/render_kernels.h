@@ -24,8 +24,12 @@ struct FeatPeers {
   int64_t row0;
 };
 
+// `visdd_scratch` ([N][V] float2, or null): visibility / depth difference per (sample, view) computed by visibility_kernel
+// (visibility.cu, decoder on tcgen05) ahead of aggregate_kernel; null keeps the decoder inside aggregate_kernel
 int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int with_blend, float* agg,
-                     float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, cudaStream_t st);
+                     float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, float* visdd_scratch,
+                     cudaStream_t st);
+int launch_visibility(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, float* visdd, float* mvv, cudaStream_t st);
 int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
                     const float* d2, const float* agg, float* fagg, float* feature, float* weights, cudaStream_t st);
 // second generation (neighbor2.cu): q projection, 32-sample super-tiles with the attention projections on tcgen05, fc + LayerNorm

@@ -138,9 +138,12 @@ __device__ __forceinline__ void mean_var_rows(const float* __restrict__ f0, cons
   }
 }
 
-template <int ROWS, bool FUSED>
+// EXT: visibility and depth difference per (sample, view) come from visibility_kernel (`visdd_in`, [N][V] float2) - the NeuRay
+// projection, the visibility-feature gather and the decoder are compiled out.
+template <int ROWS, bool FUSED, bool EXT>
 __global__ void __launch_bounds__(NT, 128 / ROWS)
 aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int with_blend,
+                 const float2* __restrict__ visdd_in,
                  float* __restrict__ agg_out, float* __restrict__ partial_out, float* __restrict__ rgbvis_out,
                  unsigned char* __restrict__ nvalid_out, float* __restrict__ mvf_out, float* __restrict__ mvv_out) {
   extern __shared__ __align__(16) float smem[];
@@ -176,15 +179,17 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   // side), dec2 as 4 x [32][32].  Both are read as mma.sync B fragments (thread (g, t) reads rows t / t + 4 resp. 2t / 2t + 1,
   // column g), so 8-column groups are XOR-swizzled with the row to keep those reads bank-conflict free without padding:
   // dec1 (k, n) -> k * 128 + (n ^ 8 (k & 3)), dec2 (k, n) -> k * 32 + (n ^ 8 ((k >> 1) & 3)).  Requested now, consumed in phase 3.
-  for (int i = tid; i < 1024; i += NT) {
-    const int k = i >> 5, n = (i & 31) * 4;
-    cp_async16(sB + k * 128 + (n ^ ((k & 3) << 3)), w.dec1 + i * 4);
+  if (!EXT) {
+    for (int i = tid; i < 1024; i += NT) {
+      const int k = i >> 5, n = (i & 31) * 4;
+      cp_async16(sB + k * 128 + (n ^ ((k & 3) << 3)), w.dec1 + i * 4);
+    }
+    for (int i = tid; i < 1024; i += NT) {
+      const int k = (i >> 3) & 31, n = (i & 7) * 4;
+      cp_async16(sB + 4096 + (i >> 3) * 32 + (n ^ (((k >> 1) & 3) << 3)), w.dec2 + i * 4);
+    }
+    cp_async_commit();
   }
-  for (int i = tid; i < 1024; i += NT) {
-    const int k = (i >> 3) & 31, n = (i & 7) * 4;
-    cp_async16(sB + 4096 + (i >> 3) * 32 + (n ^ (((k >> 1) & 3) << 3)), w.dec2 + i * 4);
-  }
-  cp_async_commit();
 
   // ---- phase 1: projections; PARTS threads per (sample, view) row share the three independent pieces -------------
   {
@@ -215,6 +220,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           store_taps(ri + RI_TI, make_taps(((gx + 1.f) / 2.f) * (float)(sc.W - 1), ((gy + 1.f) / 2.f) * (float)(sc.H - 1), sc.W, sc.H, true), sc.W, sc.H);
           store_taps(ri + RI_TF, make_taps(((gx + 1.f) / 2.f) * (float)(sc.w - 1), ((gy + 1.f) / 2.f) * (float)(sc.h - 1), sc.w, sc.h, true), sc.w, sc.h);
         } else if (job == 1) {
+          if (EXT) continue;
           // NeuRay convention
           const float* kr = cam + 12;
           const float c0 = fmaf(kr[2], z, fmaf(kr[1], y, kr[0] * x)) + kr[3];
@@ -258,6 +264,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   cta_sync();
 
   AGG_STAMP(1);
+  if (!EXT) {
   // ---- phase 2: 32-channel visibility features (border padding), one warp per row ------------------------------
   // All four taps of all ROWS / 8 rows of a warp are requested before any is consumed (addresses clamped into the map, taps
   // outside carry weight 0): one L2 round trip for the whole phase.
@@ -402,29 +409,38 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
     }
   }
+  }
   AGG_STAMP(10);
   AGG_STAMP(11);
   cta_sync();
   const bool fused_w = V == 8;   // rows of a sample are 8 consecutive lanes: the view weights follow in the same threads
   if (tid < ROWS && (fused_w || tid < rows)) {
-    const float m0 = sO1[tid * 6], m1 = sO1[tid * 6 + 1], v0 = sO1[tid * 6 + 2], v1 = sO1[tid * 6 + 3];
-    const float aw = sO1[tid * 6 + 4], vs = sO1[tid * 6 + 5];
     float* ri = sRI + tid * RI_N;
     const bool live = tid < rows;
-    const float dep = ri[RI_DEPTH];
-    const float near_inv = -1.f / near_, far_inv = -1.f / far_;
-    // (divisions of this serial per-row tail use the hardware reciprocal: 2 ulp, operands far from the denormal range)
-    float refd = __fdividef(-1.f, m0 * (far_inv - near_inv) + near_inv);
-    refd = fminf(fmaxf(refd, near_), far_);
-    const float dd = live ? __fdividef(fabsf(dep - refd), far_ - near_) : 0.f;
-    const float dn = __fdividef(__fdividef(-1.f, fmaxf(dep, 1e-5f)) - near_inv, far_inv - near_inv);
-    const float cdf0 = (0.5f + 0.5f * tanh_fast((dn - m0) * v0)) * vs;
-    const float cdf1 = (0.5f + 0.5f * tanh_fast((dn - m1) * v1)) * vs;
-    const float vis = live ? ((1.f - cdf0) * aw + (1.f - cdf1) * (1.f - aw)) * ri[RI_VALID] : 0.f;
+    float vis = 0.f, dd = 0.f;
+    if (EXT) {
+      if (live) {
+        const float2 vd = __ldcs(visdd_in + nidx(tid / V) * V + (tid - (tid / V) * V));   // written once by visibility_kernel
+        vis = vd.x; dd = vd.y;
+      }
+    } else {
+      const float m0 = sO1[tid * 6], m1 = sO1[tid * 6 + 1], v0 = sO1[tid * 6 + 2], v1 = sO1[tid * 6 + 3];
+      const float aw = sO1[tid * 6 + 4], vs = sO1[tid * 6 + 5];
+      const float dep = ri[RI_DEPTH];
+      const float near_inv = -1.f / near_, far_inv = -1.f / far_;
+      // (divisions of this serial per-row tail use the hardware reciprocal: 2 ulp, operands far from the denormal range)
+      float refd = __fdividef(-1.f, m0 * (far_inv - near_inv) + near_inv);
+      refd = fminf(fmaxf(refd, near_), far_);
+      dd = live ? __fdividef(fabsf(dep - refd), far_ - near_) : 0.f;
+      const float dn = __fdividef(__fdividef(-1.f, fmaxf(dep, 1e-5f)) - near_inv, far_inv - near_inv);
+      const float cdf0 = (0.5f + 0.5f * tanh_fast((dn - m0) * v0)) * vs;
+      const float cdf1 = (0.5f + 0.5f * tanh_fast((dn - m1) * v1)) * vs;
+      vis = live ? ((1.f - cdf0) * aw + (1.f - cdf1) * (1.f - aw)) * ri[RI_VALID] : 0.f;
+    }
     if (live) {
       ri[RI_DD] = dd;
       ri[RI_VIS] = vis;
-      if (mvv_out) mvv_out[nidx(tid / V) * V + (tid - (tid / V) * V)] = vis;
+      if (!EXT && mvv_out) mvv_out[nidx(tid / V) * V + (tid - (tid / V) * V)] = vis;
     }
     if (fused_w) {
       // ---- phase 4 fused (V == 8): per-sample view weights over the 8 lanes of a sample (same summation tree as warp_sum) --
@@ -829,7 +845,8 @@ static int set_smem(Kern k, size_t bytes) {
 }
 
 int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int with_blend, float* agg,
-                     float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, cudaStream_t st) {
+                     float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, float* visdd_scratch,
+                     cudaStream_t st) {
   if (N <= 0) return 0;
   if (sc.V < 1 || sc.V > 16) return set_error("aggregate: number of reference views must be in 1..16");
   if (with_blend && !sc.featb) return set_error("aggregate: scene.featmaps_blend is NULL (call nlb_blend_prepare once per frame)");
@@ -839,15 +856,29 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   const int64_t tiles = ps.xyz ? (N + TP - 1) / TP : ((N / ps.S + TP - 1) / TP) * ps.S;
   if (tiles > 0x7fffffffLL) return set_error("aggregate: too many tiles for one launch");
   const unsigned grid = (unsigned)tiles;
-  static const bool unfused = getenv("NLB_AGG_UNFUSED") != nullptr;   // A/B switch
+  static const bool unfused = getenv("NLB_AGG_UNFUSED") != nullptr;   // A/B switches
+  static const bool one_kernel = getenv("NLB_AGG_V1") != nullptr;      // visibility decoder inside aggregate_kernel (mma.sync)
+  const bool ext = !one_kernel && visdd_scratch != nullptr;
+  if (ext && launch_visibility(sc, w, ps, N, visdd_scratch, mvv, st)) return 1;
+  const float2* vd = reinterpret_cast<const float2*>(visdd_scratch);
   if (sc.V <= 8 && !unfused) {
     const size_t smem = agg_smem_floats<ROWS, true>() * sizeof(float);
-    if (set_smem(aggregate_kernel<ROWS, true>, smem)) return 1;
-    aggregate_kernel<ROWS, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
+    if (ext) {
+      if (set_smem(aggregate_kernel<ROWS, true, true>, smem)) return 1;
+      aggregate_kernel<ROWS, true, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, agg, partial, rgbvis, nvalid, mvf, mvv);
+    } else {
+      if (set_smem(aggregate_kernel<ROWS, true, false>, smem)) return 1;
+      aggregate_kernel<ROWS, true, false><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
+    }
   } else {
     const size_t smem = agg_smem_floats<ROWS, false>() * sizeof(float);
-    if (set_smem(aggregate_kernel<ROWS, false>, smem)) return 1;
-    aggregate_kernel<ROWS, false><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, agg, partial, rgbvis, nvalid, mvf, mvv);
+    if (ext) {
+      if (set_smem(aggregate_kernel<ROWS, false, true>, smem)) return 1;
+      aggregate_kernel<ROWS, false, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, agg, partial, rgbvis, nvalid, mvf, mvv);
+    } else {
+      if (set_smem(aggregate_kernel<ROWS, false, false>, smem)) return 1;
+      aggregate_kernel<ROWS, false, false><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
+    }
   }
   return check_launch("aggregate_kernel");
 }

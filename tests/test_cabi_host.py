@@ -11,15 +11,15 @@ def test_scratch_size_and_launch_count():
     S, V = 128, 8
     small, big = L.nlb_render_scratch_bytes(18944, S, V), L.nlb_render_scratch_bytes(37888, S, V)
     # per sample: 2 x (idx + d2) [8] double buffered, aggregator output + feature_agg [128], blend partials [V][32], rgb|vis [V][4],
-    # view count, attention query + context [128] and the neighbour-weight sum
-    per_sample = 4 * 8 * 4 + 2 * 128 * 4 + V * 32 * 4 + V * 16 + 1 + 2 * 128 * 4 + 4
+    # view count, attention query + context [128] and the neighbour-weight sum, visibility | depth difference [V][2]
+    per_sample = 4 * 8 * 4 + 2 * 128 * 4 + V * 32 * 4 + V * 16 + 1 + 2 * 128 * 4 + 4 + V * 8
     assert small >= 18944 * S * per_sample and small < 18944 * S * per_sample + (1 << 16)
     assert abs(big - 2 * small) < (1 << 16)
     assert L.nlb_render_scratch_bytes(0, S, V) == L.nlb_render_scratch_bytes(1, S, V)      # clamped, never zero
     assert L.nlb_render_scratch_bytes(1024, 192, V) > L.nlb_render_scratch_bytes(1024, 128, V) * 1.5   # S > 128 adds the slabs
-    # six kernels per chunk: KNN search, aggregate, q projection, neighbour, attention tail, ray
-    assert L.nlb_render_launch_count(307200, 37888) == 6 * 9
-    assert L.nlb_render_launch_count(307200, 0) == 6      # chunk_rays < 1: one chunk
+    # seven kernels per chunk: KNN search, visibility, aggregate, q projection, neighbour, attention tail, ray
+    assert L.nlb_render_launch_count(307200, 37888) == 7 * 9
+    assert L.nlb_render_launch_count(307200, 0) == 7      # chunk_rays < 1: one chunk
     assert L.nlb_render_launch_count(0, 37888) == 0
 
 
