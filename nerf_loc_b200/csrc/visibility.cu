@@ -3,10 +3,10 @@
 // DepthFusionNet channels, the mixture-of-logistics visibility decoder (visibility_decoder.py:62-148) and the visibility /
 // depth-difference outputs - split off aggregate_kernel so that the decoder runs on tcgen05.
 //
-// A tile is 128 (sample, view) rows = 128 / V samples x V views, one persistent CTA per SM:
-//   gather     one warp per row, lane = channel (a row's four taps are four coalesced 128-byte reads); the loads of tile t+1 are
-//              issued while tile t is in the decoder, and are turned into the bf16 hi | lo layer-1 operand (chunk-major shared
-//              memory tile) when tile t+1 starts;
+// A tile is 128 (sample, view) rows = 128 / V samples x V views; persistent CTAs, two per SM (256 TMEM columns and 66 KB of
+// shared memory each), so that one CTA's gather latency and MMA waits are covered by the other's epilogues:
+//   gather     one warp per row, lane = channel (a row's four taps are four coalesced 128-byte reads), eight rows of a warp in
+//              flight at a time, interpolated into the bf16 hi | lo layer-1 operand (chunk-major shared memory tile);
 //   layer 1    [128 x 32] x [32 x 128] (the four heads side by side), bf16x3, accumulator in tensor memory;
 //   E1         + bias, ELU, split -> layer-2 operand in tensor memory (two bf16 per column);
 //   layer 2    block diagonal: four [128 x 32] x [32 x 32] products into the accumulator columns of their head;
@@ -47,7 +47,7 @@ struct Sync {
 
 __device__ __forceinline__ int tile_rows_samples(int V) { return 128 / V; }
 
-__global__ void __launch_bounds__(NT + 128, 1)
+__global__ void __launch_bounds__(NT + 32, 2)
 visibility_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, float2* __restrict__ visdd_out,
                   float* __restrict__ mvv_out) {
   extern __shared__ __align__(1024) unsigned char sm[];
@@ -88,8 +88,7 @@ visibility_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const i
   const int nmy = (int)((ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
 
   if (warp >= 8) {
-    tc::reg_dec<56>();
-    if (warp == 8) {
+    {
       // ------------------------------------------------ MMA issuer ---------------------------------------------------------------
       uint32_t a_par = 0;
       const uint32_t a_hi32 = tc::desc_hi(128u);
@@ -138,7 +137,6 @@ visibility_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const i
     }
   } else {
     // ------------------------------------------------ compute warps ------------------------------------------------------
-    tc::reg_inc<224>();
     const int row = (warp & 3) * 32 + lane, half = warp >> 2;
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const float near_ = sc.near_, far_ = sc.far_;
@@ -151,10 +149,8 @@ visibility_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const i
     };
     auto nidx = [&](int64_t g, int s, int p) -> int64_t { return by_ray ? (g * TP + p) * ps.S + s : g * TP + p; };
 
-    // NeuRay projection of this thread's row (threads 0..127) of tile `it` -> tap record; then every warp requests the taps of its
-    // 16 rows (lane = channel): 64 independent 4-byte loads per lane
-    float q[16][4];
-    auto project_and_request = [&](int it) {
+    // NeuRay projection of this thread's row (threads 0..127) of tile `it` -> tap record
+    auto project = [&](int it) {
       int64_t g; int s;
       tile_of(it, g, s);
       const int np = (int)min((int64_t)TP, n_items - g * TP);
@@ -218,17 +214,8 @@ visibility_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const i
         }
       }
       cta_sync();
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int4 ti = *reinterpret_cast<const int4*>(tp + (warp * 16 + u) * TAP_LD);
-        q[u][0] = __ldg(sc.vis + (size_t)ti.x * C_VIS + lane);
-        q[u][1] = __ldg(sc.vis + (size_t)ti.y * C_VIS + lane);
-        q[u][2] = __ldg(sc.vis + (size_t)ti.z * C_VIS + lane);
-        q[u][3] = __ldg(sc.vis + (size_t)ti.w * C_VIS + lane);
-      }
     };
 
-    if (nmy > 0) project_and_request(0);
     for (int it = 0; it < nmy; ++it) {
       const bool stamp = it == 1 && blockIdx.x == gridDim.x / 2 && tid == 0;
       VIS_STAMP(0);
@@ -236,32 +223,43 @@ visibility_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const i
       tile_of(it, g, s);
       const int np = (int)min((int64_t)TP, n_items - g * TP);
       const float* tp = sTap + (it & 1) * 128 * TAP_LD;
-      // ---- X: interpolate the requested taps -> layer-1 operand (bf16 hi | lo, chunk-major).  Lane c holds channel c of a row;
-      // pairs of lanes are packed with a shuffle and the even lane stores 4 bytes per plane.
+      project(it);
+      VIS_STAMP(1);
+      // ---- X: gather the taps of this warp's 16 rows (lane = channel), eight rows in flight, and interpolate -> layer-1 operand
+      // (bf16 hi | lo, chunk-major).  Pairs of lanes are packed with a shuffle and the even lane stores 4 bytes per plane.
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int r = warp * 16 + u;
-        const float4 tw = *reinterpret_cast<const float4*>(tp + r * TAP_LD + 4);
-        float a = q[u][0] * tw.x;
-        a += q[u][1] * tw.y;
-        a += q[u][2] * tw.z;
-        a += q[u][3] * tw.w;
-        a *= tp[r * TAP_LD + 8];   // valid
-        const float b = __shfl_down_sync(0xffffffffu, a, 1);
-        if ((lane & 1) == 0) {
-          uint32_t hi, lo;
-          tc::split_bf16x2(a, b, hi, lo);
-          const uint32_t o = tc::cm_off(r, lane, RA);
-          *reinterpret_cast<uint32_t*>(sm + A1_OFF + o) = hi;
-          *reinterpret_cast<uint32_t*>(sm + A1_OFF + 8192 + o) = lo;
+      for (int ub = 0; ub < 16; ub += 8) {
+        float q[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int4 ti = *reinterpret_cast<const int4*>(tp + (warp * 16 + ub + u) * TAP_LD);
+          q[u][0] = __ldg(sc.vis + (size_t)ti.x * C_VIS + lane);
+          q[u][1] = __ldg(sc.vis + (size_t)ti.y * C_VIS + lane);
+          q[u][2] = __ldg(sc.vis + (size_t)ti.z * C_VIS + lane);
+          q[u][3] = __ldg(sc.vis + (size_t)ti.w * C_VIS + lane);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int r = warp * 16 + ub + u;
+          const float4 tw = *reinterpret_cast<const float4*>(tp + r * TAP_LD + 4);
+          float a = q[u][0] * tw.x;
+          a += q[u][1] * tw.y;
+          a += q[u][2] * tw.z;
+          a += q[u][3] * tw.w;
+          a *= tp[r * TAP_LD + 8];   // valid
+          const float b = __shfl_down_sync(0xffffffffu, a, 1);
+          if ((lane & 1) == 0) {
+            uint32_t hi, lo;
+            tc::split_bf16x2(a, b, hi, lo);
+            const uint32_t o = tc::cm_off(r, lane, RA);
+            *reinterpret_cast<uint32_t*>(sm + A1_OFF + o) = hi;
+            *reinterpret_cast<uint32_t*>(sm + A1_OFF + 8192 + o) = lo;
+          }
         }
       }
       tc::fence_async_smem();
       tc::fence_before_sync();
       tc::mbar_arrive(&sy.a_ready);
-      VIS_STAMP(1);
-      // ---- the next tile's projections and tap requests run underneath layer 1
-      if (it + 1 < nmy) project_and_request(it + 1);
       VIS_STAMP(2);
       // ---- E1: + bias, ELU -> layer-2 operand in tensor memory
       wait_d();
@@ -371,8 +369,8 @@ int launch_visibility(const SceneDev& sc, const RenderW& w, const PointSrc& ps, 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-  vis::visibility_kernel<<<grid, NT + 128, vis::SMEM_BYTES, st>>>(sc, w, ps, N, reinterpret_cast<float2*>(visdd), mvv);
+  const unsigned grid = (unsigned)(tiles < 2 * sms ? tiles : 2 * sms);   // persistent, two CTAs per SM
+  vis::visibility_kernel<<<grid, NT + 32, vis::SMEM_BYTES, st>>>(sc, w, ps, N, reinterpret_cast<float2*>(visdd), mvv);
   return check_launch("visibility_kernel");
 }
 
