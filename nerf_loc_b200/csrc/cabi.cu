@@ -166,7 +166,8 @@ int nlb_blend_prepare(const float* packed_weights, int S, const float* featmaps,
 size_t nlb_query_scratch_bytes(int64_t N, int K) {
   if (N < 1) N = 1;
   return align256((size_t)N * K * 4) + align256((size_t)N * K * 4) + align256((size_t)N * W_HID * 4) +
-         align256(neighbor2_scratch_floats(N) * 4) + align256((size_t)N * 16 * 8) + 1024;   // visibility | depth difference: <= 16 views
+         align256(neighbor2_scratch_floats(N) * 4) + align256((size_t)N * 16 * 8) +   // visibility | depth difference: <= 16 views
+         align256((size_t)N * 416 * 4) + 1024;                                            // out_fc input of fc_tail_kernel
 }
 
 int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S, const float* xyz,
@@ -184,14 +185,17 @@ int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S,
   float* agg = aggregated ? aggregated : c.take<float>((size_t)N * W_HID);
   float* nb2 = c.take<float>(neighbor2_scratch_floats(N));
   float* visdd = c.take<float>((size_t)N * scene->V * 2);
+  float* gvec = c.take<float>((size_t)N * 416);
   if (!c.ok) return set_error("nlb_query_points: scratch too small (see nlb_query_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
   PointSrc ps{xyz, direction, nullptr, nullptr, nullptr, 1, 0};
   if (knn_query(sc.knn, xyz, N, K, nullptr, idx, d2, st)) return 1;
-  if (launch_aggregate(sc, w, ps, N, 0, agg, nullptr, nullptr, nullptr, mv_feature, mv_visibility, visdd, st)) return 1;
+  const int ar = launch_aggregate(sc, w, ps, N, 0, agg, nullptr, nullptr, nullptr, mv_feature, mv_visibility, visdd,
+                                  nb_v1() ? nullptr : gvec, nb2, st);
+  if (ar == 1) return 1;
   if (nb_v1()) return launch_neighbor(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, st);
-  return launch_neighbor2(sc, w, ps, N, K, idx, d2, agg, feature_agg, nullptr, 0, feature, weights, nb2, st);
+  return launch_neighbor2(sc, w, ps, N, K, idx, d2, agg, feature_agg, nullptr, 0, feature, weights, nb2, ar == 2, st);
 }
 
 int nlb_aggregate_points(const nlb_scene* scene, const float* packed_weights, int S, const float* xyz, int64_t N,
@@ -203,8 +207,8 @@ int nlb_aggregate_points(const nlb_scene* scene, const float* packed_weights, in
   const RenderW w = render_weights_view(packed_weights, S);
   PointSrc ps{xyz, nullptr, nullptr, nullptr, nullptr, 1, 0};
   // (no scratch in this entry point's signature: the decoder stays inside aggregate_kernel)
-  return launch_aggregate(sc, w, ps, N, 0, aggregated, nullptr, nullptr, nullptr, mv_feature, mv_visibility, nullptr,
-                          (cudaStream_t)stream);
+  return launch_aggregate(sc, w, ps, N, 0, aggregated, nullptr, nullptr, nullptr, mv_feature, mv_visibility, nullptr, nullptr,
+                          nullptr, (cudaStream_t)stream);
 }
 
 int nlb_descriptor_head(const float* packed_weights, int S, int level, const float* x, int64_t N, float* out,
@@ -228,7 +232,7 @@ size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
   const size_t slabs = S > 128 ? align256((size_t)RL_MAX_GRID * ray_long_slab_floats(S) * 4) : 0;
   // KNN lists are double buffered: the search of chunk i+1 runs on a side stream underneath the ray kernel of chunk i
   return align256(n * KNN_K * 4) * 4 + align256(n * W_HID * 4) * 2 + align256(n * V * 32 * 4) + align256(n * V * 16) +
-         align256(n) + align256(neighbor2_scratch_floats((int64_t)n) * 4) + align256(n * V * 8) + slabs + 2048;
+         align256(n) + align256(neighbor2_scratch_floats((int64_t)n) * 4) + align256(n * V * 8) + align256(n * 416 * 4) + slabs + 2048;
 }
 
 int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays) {
@@ -274,6 +278,7 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
   unsigned char* nvalid = c.take<unsigned char>(n);
   float* nb2 = c.take<float>(neighbor2_scratch_floats((int64_t)n));
   float* visdd = c.take<float>(n * V * 2);
+  float* gvec = c.take<float>(n * 416);
   float* slabs = S > 128 ? c.take<float>((size_t)RL_MAX_GRID * ray_long_slab_floats(S)) : nullptr;
   if (!c.ok) return set_error("nlb_render_rays: scratch too small (see nlb_render_scratch_bytes)");
   const SceneDev sc = to_dev(scene);
@@ -326,11 +331,13 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
     prof.mark();
     if (!overlap && knn_chunk(i, st)) { rc_err = 1; break; }
     prof.mark();
-    if (launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, visdd, st)) { rc_err = 1; break; }
+    const int ar = launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, visdd, nb_v1() ? nullptr : gvec,
+                                    nb2, st);
+    if (ar == 1) { rc_err = 1; break; }
     prof.mark();
     if (overlap) cudaStreamWaitEvent(st, ev_knn[i & 1], 0);
     if (nb_v1() ? launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)
-                : launch_neighbor2(sc, w, ps, nc, KNN_K, idx, d2, agg, fa32, fsplit, S, nullptr, nullptr, nb2, st)) { rc_err = 1; break; }
+                : launch_neighbor2(sc, w, ps, nc, KNN_K, idx, d2, agg, fa32, fsplit, S, nullptr, nullptr, nb2, ar == 2, st)) { rc_err = 1; break; }
     if (overlap) cudaEventRecord(ev_nb, st);
     prof.mark();
     if (split_x) {

@@ -685,7 +685,7 @@ size_t neighbor2_scratch_floats(int64_t N) { return (size_t)N * W_HID * 2 + (siz
 // scratch: q [N][128] | o [N][128] | wsum [N]  (neighbor2_scratch_floats(N) floats)
 int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
                      const float* d2, const float* agg, float* fagg, unsigned char* fagg_split, int S_split, float* feature,
-                     float* weights, float* scratch, cudaStream_t st) {
+                     float* weights, float* scratch, bool q_ready, cudaStream_t st) {
   if (N <= 0) return 0;
   if (K < 1 || K > 8) return set_error("neighbor: K must be in 1..8");
   if (!scratch) return set_error("neighbor: scratch is NULL");
@@ -702,8 +702,10 @@ int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   const int64_t t128 = (N + 127) / 128;
   const unsigned g128 = (unsigned)(t128 < sms ? t128 : sms);
   if (fagg_split && (S_split < 1 || N % S_split != 0)) return set_error("neighbor: the pre-split output needs whole rays");
-  nb2::row_gemm128_kernel<0><<<g128, NT, nb2::RG_SMEM, st>>>(agg, w.tb_wq, N, nullptr, nullptr, nullptr, nullptr, q, nullptr, nullptr, 1);
-  if (check_launch("qproj_kernel")) return 1;
+  if (!q_ready) {
+    nb2::row_gemm128_kernel<0><<<g128, NT, nb2::RG_SMEM, st>>>(agg, w.tb_wq, N, nullptr, nullptr, nullptr, nullptr, q, nullptr, nullptr, 1);
+    if (check_launch("qproj_kernel")) return 1;
+  }
   const int64_t nst = (N + 2 * nb2::TP - 1) / (2 * nb2::TP);
   const unsigned grid = (unsigned)(nst < sms ? nst : sms);   // persistent: one CTA per SM
   nb2::neighbor2_kernel<<<grid, NT + 128, nb2::SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, q, o, wsum, weights);

@@ -71,6 +71,8 @@ struct RenderW {
   const float *tb_w1b, *tb_w2, *tb_w3, *tb_wq, *tb_wk, *tb_wv, *tb_wfc;
   // visibility decoder (visibility.cu): layer 1 of the four heads as one [128 x 32] tile, layer 2 as four [32 x 32] tiles
   const float *tb_dec1, *tb_dec2;
+  // out_fc (fc_tail.cu): layer 1 [64 x 416] in the column order of aggregate_kernel's statistics vector, layer 2 [128 x 64]
+  const float *tb_fc1, *tb_fc2;
   const float *sig_w, *sig_b;   // [128], [1]
   const float *ft1, *ft1_b;     // [128][128], [128]
   const float *ft2, *ft2_b;     // [128][192], [192]

@@ -85,6 +85,7 @@ static RenderW layout(const float* base, int S, size_t* total) {
   w.tb_w1b = a.take(128 * 96);
   w.tb_w2 = a.take(128 * 128); w.tb_w3 = a.take(128 * 128);
   w.tb_dec1 = a.take(128 * 32); w.tb_dec2 = a.take(4 * 32 * 32);
+  w.tb_fc1 = a.take(64 * 416); w.tb_fc2 = a.take(128 * 64);
   w.tb_wq = a.take(128 * 128); w.tb_wk = a.take(128 * 128); w.tb_wv = a.take(128 * 128); w.tb_wfc = a.take(128 * 128);
   w.sig_w = a.take(128); w.sig_b = a.take(1);
   w.ft1 = a.take(128 * 128); w.ft1_b = a.take(128);
@@ -133,6 +134,16 @@ __global__ void pack_conv_kernel(float* dst, const float* __restrict__ src, int 
 // ray_diff_fc 14-26 | 0 x 5]; the source order is [offset xyz | PE octaves 0-9 | ray_diff_fc 0-26].
 __device__ __forceinline__ int tcb_src_index(int k, int perm) {
   if (perm == 0) return k;
+  if (perm == 2) {
+    // out_fc input as aggregate_kernel (GOUT) writes it: map-channel means, map-channel variances, rgb mean, rgb variance,
+    // extras; the source order is [rgb + map means (195) | rgb + map variances (195) | extras (3)]
+    if (k < 192) return 3 + k;
+    if (k < 384) return 195 + 3 + (k - 192);
+    if (k < 387) return k - 384;
+    if (k < 390) return 195 + (k - 387);
+    if (k < 393) return k;
+    return -1;
+  }
   if (k < 3) return k;
   if (k == 3) return -1;
   if (k < 34) return k - 1;
@@ -305,6 +316,8 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
     k.tcb16(w.tb_dec1, DEC + 6 * h + 0, 32, 32, 32, 0, 1, 32, -1, 0, 32 * h, 128);   // rows 32 h .. of the [128 x 32] tile
     k.tcb16(w.tb_dec2 + 32 * 32 * h, DEC + 6 * h + 2, 32, 32, 32, 0, 1, 32);
   }
+  k.tcb16(w.tb_fc1, FC0_W, 64, 416, 393, 0, 1, 32, 393, 2);
+  k.tcb16(w.tb_fc2, FC2_W, 128, 64, 64, 0, 1, 32);
   k.tcb16(w.tb_w1b, BM0_W, 128, 96, 285, 195, 1, 32, 90, 1);
   k.tcb16(w.tb_w2, BM2_W, 128, 128, 128, 0, 1, 32);
   k.tcb16(w.tb_w3, BM4_W, 128, 128, 128, 0, 1, 32);

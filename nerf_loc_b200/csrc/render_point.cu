@@ -140,10 +140,13 @@ __device__ __forceinline__ void mean_var_rows(const float* __restrict__ f0, cons
 
 // EXT: visibility and depth difference per (sample, view) come from visibility_kernel (`visdd_in`, [N][V] float2) - the NeuRay
 // projection, the visibility-feature gather and the decoder are compiled out.
-template <int ROWS, bool FUSED, bool EXT>
+// GOUT (with FUSED and EXT): the per-sample statistics vector (mean | variance | 3 extras, the input of out_fc) goes to global
+// memory (`g_out`, [N][416]: map-channel means 0..191, variances 192..383, rgb mean / variance 384..389, extras 390..392, zeros)
+// and out_fc + the attention query projection run as 128-sample tensor-core GEMMs in fc_tail_kernel.
+template <int ROWS, bool FUSED, bool EXT, bool GOUT = false>
 __global__ void __launch_bounds__(NT, 128 / ROWS)
 aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int with_blend,
-                 const float2* __restrict__ visdd_in,
+                 const float2* __restrict__ visdd_in, float* __restrict__ g_out,
                  float* __restrict__ agg_out, float* __restrict__ partial_out, float* __restrict__ rgbvis_out,
                  unsigned char* __restrict__ nvalid_out, float* __restrict__ mvf_out, float* __restrict__ mvv_out) {
   extern __shared__ __align__(16) float smem[];
@@ -618,9 +621,15 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           const float dx = f[v][j].x - mx, dy = f[v][j].y - my;
           vx += wvv[v] * (dx * dx); vy += wvv[v] * (dy * dy);
         }
-        const int c = 3 + j * 64 + lane * 2;
-        g[c] = mx; g[c + 1] = my;
-        g[C_RGBF + c] = vx; g[C_RGBF + c + 1] = vy;
+        if (GOUT) {
+          float* go = g_out + nidx(p) * 416 + j * 64 + lane * 2;
+          __stcs(reinterpret_cast<float2*>(go), make_float2(mx, my));
+          __stcs(reinterpret_cast<float2*>(go + 192), make_float2(vx, vy));
+        } else {
+          const int c = 3 + j * 64 + lane * 2;
+          g[c] = mx; g[c + 1] = my;
+          g[C_RGBF + c] = vx; g[C_RGBF + c + 1] = vy;
+        }
       }
       if (lane < 3) {
         float m = 0.f;
@@ -629,9 +638,15 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         float var = 0.f;
 #pragma unroll
         for (int v = 0; v < 8; ++v) { const float d = rgbv[v] - m; var += wvv[v] * (d * d); }
-        g[lane] = m;
-        g[C_RGBF + lane] = var;
+        if (GOUT) {
+          g_out[nidx(p) * 416 + 384 + lane] = m;
+          g_out[nidx(p) * 416 + 387 + lane] = var;
+        } else {
+          g[lane] = m;
+          g[C_RGBF + lane] = var;
+        }
       }
+      if (GOUT && lane < 26) g_out[nidx(p) * 416 + 390 + lane] = lane < 3 ? g[390 + lane] : 0.f;   // extras (phase 4), zero padding up to 416
     }
   } else {
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
@@ -761,6 +776,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   for (int i = tid; i < (TP_MAX - np) * LDG; i += NT) sG[np * LDG + i] = 0.f;
 
   AGG_STAMP(7);
+  if (GOUT) return;
   // ---- phase 7: out_fc 393 -> 64 -> 128 (ELU) --------------------------------------------------------------------
   cta_sync();  // sG complete
   rows16_gemm<64, TP_MAX, 416, 8>([&](int r, int) { return sG + r * LDG; }, w.fc1, 64, sB,
@@ -846,7 +862,7 @@ static int set_smem(Kern k, size_t bytes) {
 
 int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int with_blend, float* agg,
                      float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, float* visdd_scratch,
-                     cudaStream_t st) {
+                     float* g_scratch, float* q_out, cudaStream_t st) {
   if (N <= 0) return 0;
   if (sc.V < 1 || sc.V > 16) return set_error("aggregate: number of reference views must be in 1..16");
   if (with_blend && !sc.featb) return set_error("aggregate: scene.featmaps_blend is NULL (call nlb_blend_prepare once per frame)");
@@ -861,23 +877,29 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   const bool ext = !one_kernel && visdd_scratch != nullptr;
   if (ext && launch_visibility(sc, w, ps, N, visdd_scratch, mvv, st)) return 1;
   const float2* vd = reinterpret_cast<const float2*>(visdd_scratch);
+  static const bool fc_inside = getenv("NLB_AGG_FC_V1") != nullptr;    // out_fc inside aggregate_kernel (FFMA2 small-M GEMMs)
   if (sc.V <= 8 && !unfused) {
     const size_t smem = agg_smem_floats<ROWS, true>() * sizeof(float);
-    if (ext) {
+    if (ext && g_scratch && q_out && !fc_inside) {
+      if (set_smem(aggregate_kernel<ROWS, true, true, true>, smem)) return 1;
+      aggregate_kernel<ROWS, true, true, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, g_scratch, agg, partial, rgbvis, nvalid, mvf, mvv);
+      if (check_launch("aggregate_kernel")) return 1;
+      return launch_fc_tail(w, g_scratch, N, agg, q_out, st) ? 1 : 2;   // 2: aggregated AND the attention query are done
+    } else if (ext) {
       if (set_smem(aggregate_kernel<ROWS, true, true>, smem)) return 1;
-      aggregate_kernel<ROWS, true, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, agg, partial, rgbvis, nvalid, mvf, mvv);
+      aggregate_kernel<ROWS, true, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
     } else {
       if (set_smem(aggregate_kernel<ROWS, true, false>, smem)) return 1;
-      aggregate_kernel<ROWS, true, false><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
+      aggregate_kernel<ROWS, true, false><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, nullptr, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
     }
   } else {
     const size_t smem = agg_smem_floats<ROWS, false>() * sizeof(float);
     if (ext) {
       if (set_smem(aggregate_kernel<ROWS, false, true>, smem)) return 1;
-      aggregate_kernel<ROWS, false, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, agg, partial, rgbvis, nvalid, mvf, mvv);
+      aggregate_kernel<ROWS, false, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
     } else {
       if (set_smem(aggregate_kernel<ROWS, false, false>, smem)) return 1;
-      aggregate_kernel<ROWS, false, false><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
+      aggregate_kernel<ROWS, false, false><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, nullptr, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
     }
   }
   return check_launch("aggregate_kernel");

@@ -1,6 +1,6 @@
 T=${1:-r2i}
-timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1; tail -30 gpurun_out/${T}_tests.log | cut -c1-300
-B="python bench.py --steps 1 --warmup 1 --cpu-rays 0 --cpu-match-n3 0"
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1; tail -6 gpurun_out/${T}_tests.log | cut -c1-300
+B="timeout 150 python bench.py --steps 1 --warmup 1 --cpu-rays 0 --cpu-match-n3 0"
 k() { python -c "
 import json,sys
 l=sys.stdin.readline()
@@ -8,7 +8,8 @@ try:
     d=json.loads(l); print('$1', d['value'], d['kernels_ms_per_step'], d['config']['per_frame_setup_ms'])
 except Exception as e: print('$1', 'FAILED', l[:200])"; }
 $B 2>gpurun_out/${T}_b1.err | k default; tail -3 gpurun_out/${T}_b1.err
-python bench.py --steps 2 --warmup 2 2>/dev/null | python -c "
+NLB_AGG_FC_V1=1 $B 2>/dev/null | k fc_inside
+timeout 300 python bench.py --steps 2 --warmup 2 2>/dev/null | python -c "
 import json,sys
 l=sys.stdin.readline()
 try:
