@@ -12,6 +12,7 @@
 //                         (fine_matching.py:122-149).
 #include <float.h>
 #include <limits.h>
+#include <stdlib.h>
 #include "match_kernels.h"
 #include "nlb_common.cuh"
 
@@ -31,6 +32,7 @@ static MatchW match_layout(const float* base, int C, size_t* total) {
   }
   const int Cp = (C + 31) / 32 * 32;
   w.projt = take((size_t)Cp * 192); w.proj_b = take(192);
+  w.tb_w2c = take(128 * 128);
   if (total) *total = off;
   return w;
 }
@@ -60,6 +62,8 @@ int match_weights_pack(const float* const* p, int n_params, int C, float* packed
   }
   const int Cp = (C + 31) / 32 * 32;
   T(w.projt, p[12], Cp, 192, C, C); Cpy(w.proj_b, p[13], 192);
+  pack_tcb16_kernel<<<(128 * 128 + 255) / 256, 256, 0, st>>>(reinterpret_cast<uint16_t*>(const_cast<float*>(w.tb_w2c)), p[2], 128, 128, 128, 0, 1,
+                                                           32, 128, 0, 0, 128);
   return check_launch("match_weights_pack");
 }
 
@@ -142,6 +146,8 @@ s2d_kernel(const PairMlp m, const float* __restrict__ desc0, const float* __rest
 
 int launch_s2d(const MatchW& w, const float* desc0, const float* desc1, int64_t N, int64_t M, float* score,
                cudaStream_t st) {
+  static const bool v1 = getenv("NLB_S2D_V1") != nullptr;   // A/B switch: the fp32 FFMA2 kernel below
+  if (!v1) return launch_s2d_tc(w, desc0, desc1, N, M, score, st);
   const size_t smem = S2D_SMEM_FLOATS * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(s2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));

@@ -12,6 +12,7 @@ struct PairMlp {          // 192 -> 128 -> 128 -> 1, ReLU
 struct MatchW {
   PairMlp coarse, fine;
   const float *projt, *proj_b;  // [Cp][192] (Cp = C rounded up to 32), [192]
+  const float* tb_w2c;          // coarse pair MLP, layer 2 [128 x 128] as bf16 hi | lo K-tiles of 32 (s2d_tc.cu)
   int C;
 };
 
@@ -22,6 +23,8 @@ MatchW match_weights_view(const float* packed, int C);
 
 int launch_s2d(const MatchW& w, const float* desc0, const float* desc1, int64_t N, int64_t M, float* score,
                cudaStream_t st);
+int launch_s2d_tc(const MatchW& w, const float* desc0, const float* desc1, int64_t N, int64_t M, float* score,
+                  cudaStream_t st);
 int launch_mutual(const float* score, int64_t N, int64_t M, float thr, int64_t* i_ids, int64_t* j_ids, int* count,
                   void* scratch, cudaStream_t st);
 int launch_fine_windows(const MatchW& w, const float* feat_fine, int h, int wd, int C, int stride, int coarse_w,
@@ -34,6 +37,8 @@ int launch_rowdot_sigmoid(const float* x, int64_t N, int K, const float* wv, con
 __global__ void pack_t_kernel(float* dst, const float* __restrict__ src, int Kp, int N, int dst_ld, int src_ld,
                               int src_off, int Kv);
 __global__ void pack_copy_kernel(float* dst, const float* __restrict__ src, int n);
+__global__ void pack_tcb16_kernel(uint16_t* dst, const float* __restrict__ src, int N, int K, int src_ld, int src_off, int src_ks,
+                                  int ktile, int Kv, int perm, int n_off, int N_total);
 
 // absolute pose (pnp.cu)
 size_t pnp_scratch_bytes(int iters);
