@@ -136,10 +136,11 @@ int nlb_hierarchical_depths(const nlb_scene* scene, const float* packed_weights,
 /* number of kernels nlb_render_rays launches for R rays (bench.py's gpu_launches claim) */
 int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays);
 
-/* Optional per-kernel device timing of nlb_render_rays (CUDA events on the launch stream, accumulated per kernel in the
- * order knn, aggregate, neighbor, ray).  Enabling resets the counters; while enabled every chunk synchronises. */
+/* Optional per-kernel device timing of nlb_render_rays (CUDA events on the launch stream after every kernel, accumulated per
+ * kernel name).  Enabling resets the table; while enabled every chunk ends with one synchronisation, the launch order is
+ * unchanged.  nlb_profile_report writes "name:milliseconds:launches;" records into `buf`. */
 void nlb_profile_enable(int on);
-int nlb_profile_read(double* ms /*[n]*/, int64_t* launches /*[n]*/, int n /*<= 4*/);
+int nlb_profile_report(char* buf, size_t n);
 
 /* ---- Matcher weights --------------------------------------------------------------------------------------------------
  * `params` is a HOST array of 14 device pointers, reference layouts (nerf_loc/models/matcher.py:22,40-61):

@@ -58,7 +58,7 @@ SIGNATURES = {
                                    c_void_p]),
     "nlb_debug_tc_gemm": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "nlb_profile_enable": (None, [c_int]),
-    "nlb_profile_read": (c_int, [c_void_p, c_void_p, c_int]),
+    "nlb_profile_report": (c_int, [ctypes.c_char_p, c_size_t]),
     "nlb_match_weights_floats": (c_size_t, [c_int]),
     "nlb_match_pack_weights": (c_int, [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "nlb_s2d_scores": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p]),

@@ -705,14 +705,18 @@ int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   if (!q_ready) {
     nb2::row_gemm128_kernel<0><<<g128, NT, nb2::RG_SMEM, st>>>(agg, w.tb_wq, N, nullptr, nullptr, nullptr, nullptr, q, nullptr, nullptr, 1);
     if (check_launch("qproj_kernel")) return 1;
+    prof_mark("qproj");
   }
   const int64_t nst = (N + 2 * nb2::TP - 1) / (2 * nb2::TP);
   const unsigned grid = (unsigned)(nst < sms ? nst : sms);   // persistent: one CTA per SM
   nb2::neighbor2_kernel<<<grid, NT + 128, nb2::SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, q, o, wsum, weights);
   if (check_launch("neighbor2_kernel")) return 1;
+  prof_mark("neighbor2");
   nb2::row_gemm128_kernel<1><<<g128, NT, nb2::RG_SMEM, st>>>(o, w.tb_wfc, N, agg, w.ln_g, w.ln_b, wsum, fagg, feature, fagg_split,
                                                              S_split < 1 ? 1 : S_split);
-  return check_launch("attn_tail_kernel");
+  if (check_launch("attn_tail_kernel")) return 1;
+  prof_mark("attn_tail");
+  return 0;
 }
 
 }  // namespace nlb

@@ -9,6 +9,7 @@ namespace nlb {
 
 int set_error(const char* msg);           // records the message, returns a non-zero code
 int check_launch(const char* what);       // cudaGetLastError() -> set_error
+void prof_mark(const char* name);         // per-kernel timing of nlb_render_rays (no-op unless nlb_profile_enable(1))
 
 // ---- exact KNN (knn.cu) ------------------------------------------------------------------------------------
 size_t knn_index_bytes(int64_t M);

@@ -875,7 +875,10 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   static const bool unfused = getenv("NLB_AGG_UNFUSED") != nullptr;   // A/B switches
   static const bool one_kernel = getenv("NLB_AGG_V1") != nullptr;      // visibility decoder inside aggregate_kernel (mma.sync)
   const bool ext = !one_kernel && visdd_scratch != nullptr;
-  if (ext && launch_visibility(sc, w, ps, N, visdd_scratch, mvv, st)) return 1;
+  if (ext) {
+    if (launch_visibility(sc, w, ps, N, visdd_scratch, mvv, st)) return 1;
+    prof_mark("visibility");
+  }
   const float2* vd = reinterpret_cast<const float2*>(visdd_scratch);
   static const bool fc_inside = getenv("NLB_AGG_FC_V1") != nullptr;    // out_fc inside aggregate_kernel (FFMA2 small-M GEMMs)
   if (sc.V <= 8 && !unfused) {
@@ -884,7 +887,10 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
       if (set_smem(aggregate_kernel<ROWS, true, true, true>, smem)) return 1;
       aggregate_kernel<ROWS, true, true, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, g_scratch, agg, partial, rgbvis, nvalid, mvf, mvv);
       if (check_launch("aggregate_kernel")) return 1;
-      return launch_fc_tail(w, g_scratch, N, agg, q_out, st) ? 1 : 2;   // 2: aggregated AND the attention query are done
+      prof_mark("aggregate");
+      if (launch_fc_tail(w, g_scratch, N, agg, q_out, st)) return 1;
+      prof_mark("fc_tail");
+      return 2;   // aggregated AND the attention query are done
     } else if (ext) {
       if (set_smem(aggregate_kernel<ROWS, true, true>, smem)) return 1;
       aggregate_kernel<ROWS, true, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
@@ -902,7 +908,9 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
       aggregate_kernel<ROWS, false, false><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, nullptr, nullptr, agg, partial, rgbvis, nvalid, mvf, mvv);
     }
   }
-  return check_launch("aggregate_kernel");
+  if (check_launch("aggregate_kernel")) return 1;
+  prof_mark("aggregate");
+  return 0;
 }
 
 int launch_blend_project(const float* feat, int64_t P, const float* bl1v, float* out, cudaStream_t st) {

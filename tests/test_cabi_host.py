@@ -10,9 +10,9 @@ def test_scratch_size_and_launch_count():
     L = _lib.load()
     S, V = 128, 8
     small, big = L.nlb_render_scratch_bytes(18944, S, V), L.nlb_render_scratch_bytes(37888, S, V)
-    # per sample: 2 x (idx + d2) [8] double buffered, aggregator output + feature_agg [128], blend partials [V][32], rgb|vis [V][4],
+    # per sample: KNN idx + d2 [8], aggregator output + feature_agg [128], blend partials [V][32], rgb|vis [V][4],
     # view count, attention query + context [128] and the neighbour-weight sum, visibility | depth difference [V][2], out_fc input [416]
-    per_sample = 4 * 8 * 4 + 2 * 128 * 4 + V * 32 * 4 + V * 16 + 1 + 2 * 128 * 4 + 4 + V * 8 + 416 * 4
+    per_sample = 2 * 8 * 4 + 2 * 128 * 4 + V * 32 * 4 + V * 16 + 1 + 2 * 128 * 4 + 4 + V * 8 + 416 * 4
     assert small >= 18944 * S * per_sample and small < 18944 * S * per_sample + (1 << 16)
     assert abs(big - 2 * small) < (1 << 16)
     assert L.nlb_render_scratch_bytes(0, S, V) == L.nlb_render_scratch_bytes(1, S, V)      # clamped, never zero
