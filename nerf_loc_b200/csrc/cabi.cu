@@ -92,11 +92,7 @@ void prof_mark(const char* name) { if (g_cur_prof) g_cur_prof->mark(name); }
 
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
-// A/B switch: the folded-attention neighbour kernel of neighbor_tc.cu instead of neighbor2.cu
-static bool nb_v1() {
-  static const bool v = getenv("NLB_NB_V1") != nullptr;
-  return v;
-}
+
 
 static FeatPeers peers_at(FeatPeers p, int64_t row0) {
   p.row0 = row0;
@@ -120,7 +116,7 @@ struct Carver {
 }  // namespace nlb
 
 namespace nlb { int launch_tc_test(const float* A, const float* W, int K, int mode, float* C, cudaStream_t st); }
-namespace nlb { int read_prof(long long* out, int n); int read_prof_ray(long long* out, int n); int read_prof_ray2(long long* out, int n); int read_prof_nb2(long long* out, int n); }
+namespace nlb { int read_prof(long long* out, int n); int read_prof_ray2(long long* out, int n); int read_prof_nb2(long long* out, int n); }
 using namespace nlb;
 
 extern "C" {
@@ -195,9 +191,8 @@ int nlb_query_points(const nlb_scene* scene, const float* packed_weights, int S,
   PointSrc ps{xyz, direction, nullptr, nullptr, nullptr, 1, 0};
   if (knn_query(sc.knn, xyz, N, K, nullptr, idx, d2, st)) return 1;
   const int ar = launch_aggregate(sc, w, ps, N, 0, agg, nullptr, nullptr, nullptr, mv_feature, mv_visibility, visdd,
-                                  nb_v1() ? nullptr : gvec, nb2, st);
+                                  gvec, nb2, st);
   if (ar == 1) return 1;
-  if (nb_v1()) return launch_neighbor(sc, w, ps, N, K, idx, d2, agg, feature_agg, feature, weights, st);
   return launch_neighbor2(sc, w, ps, N, K, idx, d2, agg, feature_agg, nullptr, 0, feature, weights, nb2, ar == 2, st);
 }
 
@@ -240,9 +235,8 @@ size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
 int64_t nlb_render_launch_count(int64_t R, int64_t chunk_rays) {
   if (R <= 0) return 0;
   if (chunk_rays < 1) chunk_rays = R;
-  static const bool agg_v1 = getenv("NLB_AGG_V1") != nullptr;
-  // KNN, [visibility,] aggregate, [q projection,] neighbour, [attention tail,] ray
-  return ((nb_v1() ? 4 : 6) + (agg_v1 ? 0 : 1)) * ((R + chunk_rays - 1) / chunk_rays);
+  // KNN search, visibility, aggregate, fc_tail, neighbor2, attention tail, ray
+  return 7 * ((R + chunk_rays - 1) / chunk_rays);
 }
 
 static int render_rays_impl(const nlb_scene* scene, const float* packed_weights, int S, const float* rays_o,
@@ -285,7 +279,6 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
   const SceneDev sc = to_dev(scene);
   const RenderW w = render_weights_view(packed_weights, S);
   const int64_t nchunks = (R + chunk_rays - 1) / chunk_rays;
-  static const bool ray_v1 = getenv("NLB_RAY_V1") != nullptr;   // A/B switch: the one-ray-per-CTA 3xTF32 kernel of render_ray.cu
   // (The KNN search of chunk i+1 used to run on a side stream underneath the ray kernel of chunk i; the pair ray kernel fills
   // the SM's registers and shared memory, so the overlap only cost launch gaps - measured 417 k vs 429 k rays/s - and is gone.)
   auto knn_chunk = [&](int64_t i, cudaStream_t s) {
@@ -308,26 +301,19 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
     float* fa = dbg_feature_agg ? dbg_feature_agg + r0 * S * W_HID : fagg;
     // the pair ray kernel takes feature_agg pre-split into its bf16 operand layout (written into the same scratch by the
     // attention tail); an fp32 copy is only produced for the debug output
-    const bool split_x = S <= 128 && !ray_v1 && !nb_v1();
+    const bool split_x = S <= 128;
     unsigned char* fsplit = split_x ? reinterpret_cast<unsigned char*>(fagg) : nullptr;
     float* fa32 = split_x ? (dbg_feature_agg ? fa : nullptr) : fa;
     prof.mark(nullptr);
     if (knn_chunk(i, st)) { rc_err = 1; break; }
     prof.mark("knn_query_rays");
-    const int ar = launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, visdd, nb_v1() ? nullptr : gvec,
-                                    nb2, st);
+    const int ar = launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, visdd, gvec, nb2, st);
     if (ar == 1) { rc_err = 1; break; }
-    if (nb_v1() ? launch_neighbor(sc, w, ps, nc, KNN_K, idx, d2, agg, fa, nullptr, nullptr, st)
-                : launch_neighbor2(sc, w, ps, nc, KNN_K, idx, d2, agg, fa32, fsplit, S, nullptr, nullptr, nb2, ar == 2, st)) { rc_err = 1; break; }
-    if (nb_v1()) prof.mark("neighbor");
+    if (launch_neighbor2(sc, w, ps, nc, KNN_K, idx, d2, agg, fa32, fsplit, S, nullptr, nullptr, nb2, ar == 2, st)) { rc_err = 1; break; }
     if (split_x) {
       if (launch_ray2(sc, w, zc, z_stride, rc, S, white_bkgd, fsplit, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                       weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
                       dbg_sigma ? dbg_sigma + r0 * S : nullptr, peers_at(peers, feat_row0 + r0), st)) { rc_err = 1; break; }
-    } else if (S <= 128) {
-      if (launch_ray(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
-                     weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
-                     dbg_sigma ? dbg_sigma + r0 * S : nullptr, peers_at(peers, feat_row0 + r0), st)) { rc_err = 1; break; }
     } else if (launch_ray_long(sc, w, zc, z_stride, rc, S, white_bkgd, fa, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                                weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,
                                dbg_sigma ? dbg_sigma + r0 * S : nullptr, slabs, peers_at(peers, feat_row0 + r0), st)) {
@@ -457,9 +443,8 @@ int nlb_debug_tc_gemm(const float* A, const float* W, int K, int mode, float* C,
 
 int nlb_debug_read_prof(long long* out, int n) {
   if (n <= 32) return read_prof(out, n);
-  const int e = getenv("NLB_RAY_V1") ? read_prof_ray(out + 32, n - 32) : read_prof_ray2(out + 32, n - 32);
-  if (e || read_prof(out, 32)) return 1;
-  return nb_v1() ? 0 : read_prof_nb2(out, 16);   // slots 0-15: neighbour stamps, 16-31: aggregate stamps
+  if (read_prof_ray2(out + 32, n - 32) || read_prof(out, 32)) return 1;
+  return read_prof_nb2(out, 16);   // slots 0-15: neighbour stamps, 16-31: aggregate stamps, 32-63: ray stamps
 }
 
 }  // extern "C"

@@ -295,57 +295,9 @@ __device__ __forceinline__ void rows16_gemm(ARow arow, const float* __restrict__
   }
 }
 
-// Split form of rows16_gemm for the case where a thread's whole K slice is ONE batch of weights (K / KSPLIT float2 registers):
-// rows16_load requests the slice, rows16_compute runs the FMA loop, calls `mid()` (the weights are dead by then: the caller
-// uses it to request the NEXT product's slice, whose L2 round trip then overlaps the reduction and the epilogue) and reduces.
-template <int COLS, int K>
-__device__ __forceinline__ void rows16_load(const float* __restrict__ Wt, const int ldb, float2 (&b)[K / (2 * NT / COLS)]) {
-  constexpr int KPER = K / (2 * NT / COLS);
-  const int tid = threadIdx.x;
-  const float* wp = Wt + (size_t)((tid / (COLS / 2)) * KPER) * ldb + (tid % (COLS / 2)) * 2;
-#pragma unroll
-  for (int j = 0; j < KPER; ++j) b[j] = __ldg(reinterpret_cast<const float2*>(wp + (size_t)j * ldb));
-}
-template <int COLS, int R, int K, class ARow, class Mid, class Epi>
-__device__ __forceinline__ void rows16_compute(float2 (&b)[K / (2 * NT / COLS)], ARow arow, float* red, Mid mid, Epi epi) {
-  constexpr int KSPLIT = 2 * NT / COLS;
-  constexpr int KPER = K / KSPLIT;
-  static_assert(K % KSPLIT == 0 && KPER % 4 == 0, "rows16_compute: bad K split");
-  const int tid = threadIdx.x;
-  const int c = (tid % (COLS / 2)) * 2, ks = tid / (COLS / 2);
-  float acc[R][2];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    acc[r][0] = 0.f; acc[r][1] = 0.f;
-    const float* ap = arow(r, c) + ks * KPER;
-#pragma unroll
-    for (int g = 0; g < KPER / 4; ++g) {
-      const float4 a = *reinterpret_cast<const float4*>(ap + 4 * g);
-      fma2_s(acc[r][0], acc[r][1], a.x, b[4 * g].x, b[4 * g].y);
-      fma2_s(acc[r][0], acc[r][1], a.y, b[4 * g + 1].x, b[4 * g + 1].y);
-      fma2_s(acc[r][0], acc[r][1], a.z, b[4 * g + 2].x, b[4 * g + 2].y);
-      fma2_s(acc[r][0], acc[r][1], a.w, b[4 * g + 3].x, b[4 * g + 3].y);
-    }
-  }
-  mid();
-  cta_sync();  // `red` may alias a buffer an earlier phase still reads
-#pragma unroll
-  for (int r = 0; r < R; ++r) *reinterpret_cast<float2*>(red + (ks * R + r) * COLS + c) = make_float2(acc[r][0], acc[r][1]);
-  cta_sync();
-  for (int i = tid; i < R * COLS; i += NT) {
-    float v = 0.f;
-#pragma unroll
-    for (int q = 0; q < KSPLIT; ++q) v += red[q * R * COLS + i];
-    epi(i / COLS, i % COLS, v);
-  }
-}
-
-// ---- 16-row GEMM on the warp-level tensor-core path (mma.sync.m16n8k8 tf32, 3xTF32 split) -----------------------------------
-// out[16][NCOLS] = A[16][K] * W[K][NCOLS].  M = 16 is exactly one MMA tile, so the per-sample projections of the neighbour
-// kernel (16 samples per tile) need no K split, no shared-memory reduction and no barrier: warp w owns columns
-// [w * NCOLS/8, (w+1) * NCOLS/8), reads its B fragments (W row-major [k][n], leading dimension ldb) straight from L2 in ONE
-// batch, its A fragments from shared memory (row stride % 32 == 4: conflict free), and keeps the fp32 accumulators in
-// registers.  3xTF32: hi = value with the low 13 mantissa bits cleared, lo = value - hi; lo*hi + hi*lo + hi*hi.
+// ---- warp-level tensor-core path (mma.sync.m16n8k8 tf32, 3xTF32 split): the in-kernel visibility decoder of aggregate_kernel
+// (V > 8 and the scratch-less nlb_aggregate_points entry point).  3xTF32: hi = value with the low 13 mantissa bits cleared,
+// lo = value - hi; lo*hi + hi*lo + hi*hi.
 __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const float (&a)[4], const float (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
@@ -356,125 +308,4 @@ __device__ __forceinline__ void split_hi_lo(const float x, float& hi, float& lo)
   hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
   lo = x - hi;
 }
-// HEADS > 1: HEADS independent products that share the output columns, head h using K rows of W starting at row h*K
-// (the folded key projection: q~_h = Wk_h^T q_h).  arow(r, n, h) -> shared-memory pointer to row r of A as seen by output
-// column n (multiple of 8) of head h; epi(r, n, value, h).  All B fragments of all heads are requested before the first MMA.
-template <int NCOLS, int K, int HEADS, class ARow, class Epi>
-__device__ __forceinline__ void rows16_mma(ARow arow, const float* __restrict__ W, const int ldb, Epi epi) {
-  constexpr int NTW = NCOLS / 64;          // 8-column tiles per warp (8 warps)
-  constexpr int KS = K / 8;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int n0 = warp * (NCOLS / 8);
-  float b[HEADS][KS][NTW][2];
-#pragma unroll
-  for (int h = 0; h < HEADS; ++h)
-#pragma unroll
-    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-      for (int nt = 0; nt < NTW; ++nt) {
-        b[h][ks][nt][0] = __ldg(W + (size_t)(h * K + ks * 8 + t) * ldb + n0 + nt * 8 + g);
-        b[h][ks][nt][1] = __ldg(W + (size_t)(h * K + ks * 8 + t + 4) * ldb + n0 + nt * 8 + g);
-      }
-  // MMAs into the same accumulator are dependent (and these asm statements keep their order), so two independent groups u are
-  // run side by side and the three 3xTF32 passes are issued pass-major over (u, n-tile): 2 * NTW independent MMAs sit between
-  // two dependent ones.  HEADS == 1: u = parity of the k-step (two partial accumulators, added at the end); HEADS > 1: u = head
-  // of a pair.
-  static_assert(HEADS == 1 ? KS % 2 == 0 : HEADS % 2 == 0, "rows16_mma: k-steps / heads are processed in pairs");
-  constexpr int NOUT = HEADS == 1 ? 1 : HEADS / 2;    // outer iterations (head pairs)
-  constexpr int KSTEP = HEADS == 1 ? 2 : 1;
-#pragma unroll
-  for (int op = 0; op < NOUT; ++op) {
-    float c[2][NTW][4];
-#pragma unroll
-    for (int u = 0; u < 2; ++u)
-#pragma unroll
-      for (int nt = 0; nt < NTW; ++nt) { c[u][nt][0] = 0.f; c[u][nt][1] = 0.f; c[u][nt][2] = 0.f; c[u][nt][3] = 0.f; }
-    const float* a_r0[2];
-    const float* a_r8[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int h = HEADS == 1 ? 0 : 2 * op + u;
-      a_r0[u] = arow(g, n0, h);         // rows g and g + 8 of the 16-row tile
-      a_r8[u] = arow(g + 8, n0, h);
-    }
-#pragma unroll
-    for (int ks0 = 0; ks0 < KS; ks0 += KSTEP) {
-      float ah[2][4], al[2][4], bh[2][NTW][2], bl[2][NTW][2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int h = HEADS == 1 ? 0 : 2 * op + u;
-        const int ks = HEADS == 1 ? ks0 + u : ks0;
-        split_hi_lo(a_r0[u][ks * 8 + t], ah[u][0], al[u][0]);
-        split_hi_lo(a_r8[u][ks * 8 + t], ah[u][1], al[u][1]);
-        split_hi_lo(a_r0[u][ks * 8 + t + 4], ah[u][2], al[u][2]);
-        split_hi_lo(a_r8[u][ks * 8 + t + 4], ah[u][3], al[u][3]);
-#pragma unroll
-        for (int nt = 0; nt < NTW; ++nt) {
-          split_hi_lo(b[h][ks][nt][0], bh[u][nt][0], bl[u][nt][0]);
-          split_hi_lo(b[h][ks][nt][1], bh[u][nt][1], bl[u][nt][1]);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int nt = 0; nt < NTW; ++nt) mma_tf32_16x8x8(c[u][nt], al[u], bh[u][nt]);
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int nt = 0; nt < NTW; ++nt) mma_tf32_16x8x8(c[u][nt], ah[u], bl[u][nt]);
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int nt = 0; nt < NTW; ++nt) mma_tf32_16x8x8(c[u][nt], ah[u], bh[u][nt]);
-    }
-    if (HEADS == 1) {
-#pragma unroll
-      for (int nt = 0; nt < NTW; ++nt) {
-        const int n = n0 + nt * 8 + 2 * t;
-        epi(g, n, c[0][nt][0] + c[1][nt][0], 0); epi(g, n + 1, c[0][nt][1] + c[1][nt][1], 0);
-        epi(g + 8, n, c[0][nt][2] + c[1][nt][2], 0); epi(g + 8, n + 1, c[0][nt][3] + c[1][nt][3], 0);
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int nt = 0; nt < NTW; ++nt) {
-          const int n = n0 + nt * 8 + 2 * t, h = 2 * op + u;
-          epi(g, n, c[u][nt][0], h); epi(g, n + 1, c[u][nt][1], h); epi(g + 8, n, c[u][nt][2], h); epi(g + 8, n + 1, c[u][nt][3], h);
-        }
-    }
-  }
-}
-
-// Register-tile GEMM against a weight tile that is ALREADY resident in shared memory (no staging, no barriers):
-// acc[i][j] += sum_k A[r0+i][k] * Bs[k*ldb + col(j)], columns col(j) = (j/4)*gstride + c0 + (j%4).
-template <int TM, int TN, int UNROLL = 2>
-__device__ __forceinline__ void gemm_resident(const float* __restrict__ arow, const int lda, const float* __restrict__ Bs,
-                                              const int ldb, const int c0, const int gstride, const int K,
-                                              float (&acc)[TM][TN]) {
-  constexpr int NG = TN / 4;
-#pragma unroll UNROLL
-  for (int kk = 0; kk < K; kk += 4) {
-    float4 a[TM];
-#pragma unroll
-    for (int i = 0; i < TM; ++i) a[i] = *reinterpret_cast<const float4*>(arow + i * lda + kk);
-#pragma unroll
-    for (int k4 = 0; k4 < 4; ++k4) {
-      float b[TN];
-#pragma unroll
-      for (int g = 0; g < NG; ++g) {
-        const float4 bv = *reinterpret_cast<const float4*>(Bs + (kk + k4) * ldb + g * gstride + c0);
-        b[g * 4 + 0] = bv.x; b[g * 4 + 1] = bv.y; b[g * 4 + 2] = bv.z; b[g * 4 + 3] = bv.w;
-      }
-#pragma unroll
-      for (int i = 0; i < TM; ++i) {
-        const float av = k4 == 0 ? a[i].x : (k4 == 1 ? a[i].y : (k4 == 2 ? a[i].z : a[i].w));
-#pragma unroll
-        for (int j = 0; j < TN; j += 2) fma2_s(acc[i][j], acc[i][j + 1], av, b[j], b[j + 1]);
-      }
-    }
-  }
-}
-
 }  // namespace nlb

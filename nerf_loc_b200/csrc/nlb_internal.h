@@ -52,17 +52,10 @@ struct RenderW {
   const float *w1a, *b1;        // [224][128] support-feature part of base_mlp.0 (+bias) -> per-frame precompute
   const float *rd1, *rd1_b;     // [16][4] natural, [16]
   const float *rd2, *rd2_b;     // [27][16] natural, [27]
-  const float *w1b;             // [96][128]: rows 0..62 PE, 63..89 ray_diff_fc
-  const float *w2, *b2, *w3, *b3;  // [128][128], [128]
-  const float *wq, *wk, *wv, *wfc; // wq^T, wk natural ([h*32+j][c]), wv^T, wfc^T; all [128][128]
+  const float *b2, *b3;         // [128] biases of base_mlp.2 / .4 (the matrices only exist as tensor-core tiles, below)
   const float *ln_g, *ln_b;     // [128]
-  // tensor-core (3xTF32) copies of the three 128-row base_mlp layers: per K-tile of 16, [hi | lo] canonical K-major tiles
-  const float *tc_w1b, *tc_w2, *tc_w3;
   // ray stage
   UnetLayer u[7];               // conv1, conv2, conv3, trans_conv3, trans_conv2, trans_conv1, conv_out
-  const float* tcu[7][3];       // tensor-core operands of the RayUnet layers (see pack.cu)
-  const float* tcu_x2[3];       // conv_out, x2 part (K = 32)
-  const float *tc_bl1a, *tc_ft1;
   // bf16x3 copies for the pair kernel (render_ray2.cu): per layer and TAP (0, 1, 2) the [Cout x Cin] operand as K-tiles of
   // [hi | lo] weight tiles (tc_bf16.cuh); conv_out keeps its 160 input channels in one block (K-tiles 0-3: x, 4: x2)
   const float* tb_u[7][3];

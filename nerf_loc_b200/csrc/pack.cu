@@ -55,12 +55,9 @@ static RenderW layout(const float* base, int S, size_t* total) {
   w.w1a = a.take(224 * 128); w.b1 = a.take(128);
   w.rd1 = a.take(64); w.rd1_b = a.take(16);
   w.rd2 = a.take(27 * 16); w.rd2_b = a.take(27);
-  w.w1b = a.take(96 * 128);
-  w.w2 = a.take(128 * 128); w.b2 = a.take(128);
-  w.w3 = a.take(128 * 128); w.b3 = a.take(128);
-  w.wq = a.take(128 * 128); w.wk = a.take(128 * 128); w.wv = a.take(128 * 128); w.wfc = a.take(128 * 128);
+  w.b2 = a.take(128);
+  w.b3 = a.take(128);
   w.ln_g = a.take(128); w.ln_b = a.take(128);
-  w.tc_w1b = a.take(2 * 128 * 96); w.tc_w2 = a.take(2 * 128 * 128); w.tc_w3 = a.take(2 * 128 * 128);
   for (int l = 0; l < 7; ++l) {
     const int sl = S > 0 ? S / UN_SDIV[l] : 0;
     w.u[l].w = a.take((size_t)3 * UN_CIN[l] * UN_COUT[l]);
@@ -68,15 +65,6 @@ static RenderW layout(const float* base, int S, size_t* total) {
     w.u[l].g = a.take((size_t)sl * UN_COUT[l]);
     w.u[l].be = a.take((size_t)sl * UN_COUT[l]);
   }
-  // tensor-core copies of the ray stage (3xTF32 hi|lo tiles): per RayUnet layer three GEMM operands [Cout x Cin]
-  // (conv: taps 0,1,2; transposed conv: taps 1,2,0), conv_out split into its x (K=128) and x2 (K=32) parts
-  for (int l = 0; l < 7; ++l)
-    for (int t = 0; t < 3; ++t) {
-      if (l == 6) { w.tcu[l][t] = a.take(2 * 128 * 128); w.tcu_x2[t] = a.take(2 * 128 * 32); }
-      else w.tcu[l][t] = a.take((size_t)2 * UN_COUT[l] * UN_CIN[l]);
-    }
-  w.tc_bl1a = a.take(2 * 32 * 128);
-  w.tc_ft1 = a.take(2 * 128 * 128);
   // bf16 hi | lo: 2 planes x 2 bytes = one float per weight
   for (int l = 0; l < 7; ++l)
     for (int t = 0; t < 3; ++t) w.tb_u[l][t] = a.take((size_t)UN_COUT[l] * UN_CIN[l]);
@@ -127,11 +115,9 @@ __global__ void pack_conv_kernel(float* dst, const float* __restrict__ src, int 
   dst[i] = transposed ? src[((size_t)ci * Cout + co) * 3 + t] : src[((size_t)co * Cin + ci) * 3 + t];
 }
 
-// tensor-core B operand: W [N][K] -> per K-tile of `ktile` = 2048 / N columns (a 16 KB tile): hi tile then lo tile, each the
-// canonical no-swizzle K-major layout (8-row core matrices of 16 bytes, 8-row groups ktile*32 bytes apart); 3xTF32 split.
-// perm == 1: K order of the neighbour MLP's per-pair layer-1 operand as neighbor_kernel writes it (two threads per row, each
-// storing 48 consecutive columns as float4s): [offset xyz, 0 | PE octaves 0-4 | ray_diff_fc 0-13] [PE octaves 5-9 |
-// ray_diff_fc 14-26 | 0 x 5]; the source order is [offset xyz | PE octaves 0-9 | ray_diff_fc 0-26].
+// K order of the neighbour MLP's per-pair layer-1 operand as neighbor2_kernel writes it (perm == 1; two threads per row, each
+// storing 48 consecutive columns): [offset xyz, 0 | PE octaves 0-4 | ray_diff_fc 0-13] [PE octaves 5-9 | ray_diff_fc 14-26 | 0 x 5];
+// the source order is [offset xyz | PE octaves 0-9 | ray_diff_fc 0-26].
 __device__ __forceinline__ int tcb_src_index(int k, int perm) {
   if (perm == 0) return k;
   if (perm == 2) {
@@ -152,22 +138,6 @@ __device__ __forceinline__ int tcb_src_index(int k, int perm) {
   if (k < 91) return k - 1;
   return -1;
 }
-__global__ void pack_tcb_kernel(float* dst, const float* __restrict__ src, int N, int Kp, int src_ld, int src_off, int Kv,
-                                int src_ks, int ktile, int perm) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N * Kp) return;
-  const int n = i / Kp, k = i % Kp;
-  const int ks = tcb_src_index(k, perm);
-  const float x = (ks >= 0 && ks < Kv) ? src[(size_t)n * src_ld + src_off + (size_t)ks * src_ks] : 0.f;
-  const float hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  const float lo = x - hi;
-  const int kt = k / ktile, kl = k % ktile;
-  const size_t base = (size_t)kt * (2 * N * ktile);
-  const size_t off = (size_t)(n / 8) * (ktile * 8) + (kl / 4) * 32 + (n % 8) * 4 + (kl % 4);
-  dst[base + off] = hi;
-  dst[base + (size_t)N * ktile + off] = lo;
-}
-
 // bf16x3 B operand (tc_bf16.cuh): W [N][K] -> per K-tile of `ktile` columns: hi tile then lo tile, each in the weight-tile
 // layout (8-row x 16-byte core matrices, adjacent in K contiguous, 8-row groups ktile*16 bytes apart); hi = bf16(x), lo = bf16(x - hi)
 // (n_off, N_total): the N rows packed by this call are rows n_off.. of a tile with N_total rows (several sources side by side)
@@ -202,12 +172,6 @@ struct Packer {
   }
   void c(const float* dst, int src, int n, int dst_off = 0) {
     pack_copy_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst) + dst_off, p[src], n);
-  }
-  // B[n][k] = src[n*src_ld + src_off + k*src_ks]
-  void tcb(const float* dst, int src, int N, int Kp, int src_ld, int src_off, int Kv, int src_ks = 1, int perm = 0) {
-    const int n = N * Kp;
-    pack_tcb_kernel<<<(n + 255) / 256, 256, 0, st>>>(const_cast<float*>(dst), p[src], N, Kp, src_ld, src_off, Kv, src_ks,
-                                                     2048 / N, perm);
   }
   void tcb16(const float* dst, int src, int N, int K, int src_ld, int src_off, int src_ks, int ktile, int Kv = -1, int perm = 0,
              int n_off = 0, int N_total = -1) {
@@ -255,19 +219,11 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
   k.c(w.bl3, BL4_W, 16);       k.c(w.bl3_b, BL4_B, 1);
   // --- neighbour MLP: input = [support feature 195 | PE 63 | ray_diff_fc 27] ---
   k.t(w.w1a, BM0_W, 224, 128, 285, 0, 195);  k.c(w.b1, BM0_B, 128);
-  k.t(w.w1b, BM0_W, 96, 128, 285, 195, 90);
   k.c(w.rd1, RD0_W, 64);  k.c(w.rd1_b, RD0_B, 16);
   k.c(w.rd2, RD2_W, 27 * 16);  k.c(w.rd2_b, RD2_B, 27);
-  k.t(w.w2, BM2_W, 128, 128, 128, 0, 128);  k.c(w.b2, BM2_B, 128);
-  k.t(w.w3, BM4_W, 128, 128, 128, 0, 128);  k.c(w.b3, BM4_B, 128);
-  k.t(w.wq, AT_Q, 128, 128, 128, 0, 128);
-  k.c(w.wk, AT_K, 128 * 128);
-  k.t(w.wv, AT_V, 128, 128, 128, 0, 128);
-  k.t(w.wfc, AT_FC, 128, 128, 128, 0, 128);
+  k.c(w.b2, BM2_B, 128);
+  k.c(w.b3, BM4_B, 128);
   k.c(w.ln_g, AT_LNG, 128);  k.c(w.ln_b, AT_LNB, 128);
-  k.tcb(w.tc_w1b, BM0_W, 128, 96, 285, 195, 90, 1, 1);
-  k.tcb(w.tc_w2, BM2_W, 128, 128, 128, 0, 128);
-  k.tcb(w.tc_w3, BM4_W, 128, 128, 128, 0, 128);
   // --- RayUnet ---
   if (S > 0) {
     for (int l = 0; l < 7; ++l) {
@@ -283,24 +239,6 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
       k.t(w.u[l].be, b + 3, sl, co, sl, 0, sl);
     }
   }
-  if (S > 0) {
-    for (int l = 0; l < 7; ++l) {
-      const int b = UNET + 4 * l, ci = UN_CIN[l], co = UN_COUT[l];
-      for (int t = 0; t < 3; ++t) {
-        if (UN_TR[l]) {                       // ConvTranspose1d weight [ci][co][3]: operands in the order tap 1, 2, 0
-          const int tap = t == 0 ? 1 : (t == 1 ? 2 : 0);
-          k.tcb(w.tcu[l][t], b, co, ci, 3, tap, ci, co * 3);
-        } else if (l == 6) {                  // conv_out [128][160][3]: x part then x2 part
-          k.tcb(w.tcu[l][t], b, 128, 128, 160 * 3, t, 128, 3);
-          k.tcb(w.tcu_x2[t], b, 128, 32, 160 * 3, 128 * 3 + t, 32, 3);
-        } else {                              // Conv1d weight [co][ci][3]
-          k.tcb(w.tcu[l][t], b, co, ci, ci * 3, t, ci, 3);
-        }
-      }
-    }
-  }
-  k.tcb(w.tc_bl1a, BL0_W, 32, 128, 328, 0, 128);
-  k.tcb(w.tc_ft1, FT0_W, 128, 128, 128, 0, 128);
   if (S > 0) {
     // K-tile extents as render_ray2.cu's GEMM list uses them (a tile is at most 16 KB and never straddles two source tiles)
     static const int KT16[7] = {64, 32, 32, 32, 64, 64, 32};

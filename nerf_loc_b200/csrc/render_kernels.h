@@ -33,8 +33,6 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
                      float* g_scratch, float* q_out, cudaStream_t st);
 int launch_fc_tail(const RenderW& w, const float* g, int64_t N, float* agg, float* q, cudaStream_t st);
 int launch_visibility(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, float* visdd, float* mvv, cudaStream_t st);
-int launch_neighbor(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
-                    const float* d2, const float* agg, float* fagg, float* feature, float* weights, cudaStream_t st);
 // second generation (neighbor2.cu): q projection, 32-sample super-tiles with the attention projections on tcgen05, fc + LayerNorm
 // tail; `scratch` holds neighbor2_scratch_floats(N) floats
 size_t neighbor2_scratch_floats(int64_t N);
@@ -48,10 +46,6 @@ int launch_blend_project(const float* feat, int64_t P, const float* bl1v, float*
 int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,
                   float* out, int ldo, cudaStream_t st);
 int launch_sup_geo(const float* xyz, const float* dir, const float* conf, int64_t M, float* out, cudaStream_t st);
-int launch_ray(const SceneDev& sc, const RenderW& w, const float* z_vals, int64_t zs, int64_t R, int S, int white_bkgd,
-               const float* fagg, const float* partial, const float* rgbvis, const unsigned char* nvalid, float* rgb,
-               float* depth, float* weights, unsigned char* mask, float* depth_unc, float* feat, float* sigma_dbg,
-               const FeatPeers& peers, cudaStream_t st);
 
 // pair kernel (render_ray2.cu): two rays per CTA, bf16x3 tcgen05; same contract as launch_ray
 // `xsplit`: feature_agg pre-split into bf16 hi | lo planes per ray, [R][2][16 chunks][S][8] (written by launch_neighbor2)

@@ -24,6 +24,8 @@
 namespace nlb {
 
 
+// phase timestamps of a mid-grid CTA (debug aid, read with nlb_debug_read_prof: slots 16..31)
+__device__ long long g_prof[32];
 #define AGG_STAMP(i) do { if (blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) g_prof[16 + i] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -911,6 +913,10 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   if (check_launch("aggregate_kernel")) return 1;
   prof_mark("aggregate");
   return 0;
+}
+
+int read_prof(long long* out, int n) {
+  return cudaMemcpyFromSymbol(out, g_prof, sizeof(long long) * (n < 32 ? n : 32)) == cudaSuccess ? 0 : set_error("read_prof failed");
 }
 
 int launch_blend_project(const float* feat, int64_t P, const float* bl1v, float* out, cudaStream_t st) {

@@ -1,14 +1,6 @@
-// tcgen05 (5th-generation tensor core) building blocks for sm_100a, written as inline PTX.
-//
-// MMA mode "3xTF32": the parity bar (1e-4) rules out single-pass tf32/bf16 operands, so every fp32 operand x is split
-// into hi = x with the low 13 mantissa bits cleared (exactly representable in tf32) and lo = x - hi (exact in fp32, the
-// hardware keeps its top 11 bits), and a product is evaluated as  Alo*Bhi + Ahi*Blo + Ahi*Bhi  with fp32 accumulation in
-// TMEM: three tcgen05.mma.kind::tf32 passes, ~2^-21 relative operand error.
-//
-// Operand layout in shared memory: the K-major, no-swizzle canonical layout of the UMMA shared-memory descriptor -
-// 8-row x 16-byte "core matrices" stored contiguously (128 B), core matrices adjacent in K `LBO` bytes apart, adjacent
-// 8-row groups `SBO` bytes apart.  Element (row r, col k) of a tile with KT columns lives at byte
-//     (r/8)*SBO + (k/4)*128 + (r%8)*16 + (k%4)*4,      LBO = 128, SBO = KT*32 (+ optional skew).
+// tcgen05 (5th-generation tensor core) building blocks for sm_100a, written as inline PTX: tensor-memory allocation, fences,
+// mbarriers, tcgen05.commit, tensor-memory loads / stores.  The MMA mode of this library (bf16x3: operands split into bf16
+// hi + lo, three tcgen05.mma.kind::f16 passes, fp32 accumulation in TMEM) and its operand layouts are in tc_bf16.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -66,39 +58,6 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// ---- descriptors --------------------------------------------------------------------------------------------------------
-// shared-memory matrix descriptor, K-major, no swizzle
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
-  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14);  // version 1 (Blackwell), base offset 0, SWIZZLE_NONE
-  return ((uint64_t)hi << 32) | lo;
-}
-// instruction descriptor: tf32 x tf32 -> f32, both operands K-major
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-// D[tmem] (+)= A[smem] * B[smem]^T, one K = 8 step; issued by ONE thread
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-// D[tmem] (+)= A[tmem] * B[smem]^T, one K = 8 step with the A operand read from tensor memory (lane = row, one 32-bit
-// column per k); issued by ONE thread
-__device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
 // ---- registers -> TMEM: this thread's row (TMEM lane), 8 consecutive 32-bit columns --------------------------------------
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
@@ -143,17 +102,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// ---- 3xTF32 operand split ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
-}
-
-// byte offset of element (r, k) in a canonical K-major tile whose 8-row groups are `sbo` bytes apart
-__device__ __forceinline__ uint32_t canon_off(int r, int k, uint32_t sbo) {
-  return (uint32_t)(r >> 3) * sbo + (uint32_t)(k >> 2) * 128u + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 3) * 4u;
 }
 
 }  // namespace tc

@@ -1,104 +1,10 @@
-// Self-test of the tcgen05 building blocks: C[128 x 128] = A[128 x K] * W[128 x K]^T for K <= 64 (one shot, no staging).
-// mode 0: single-pass tf32, mode 1: 3xTF32, mode 2: 3xTF32 with the A operand (hi and lo) in tensor memory; modes 4-6: bf16x3
-// (below).  Exposed as nlb_debug_tc_gemm for tests/test_gpu_tc.py.
+// Self-test of the tcgen05 building blocks (tc_bf16.cuh): C[128 x 128] = A[128 x K] * W[128 x K]^T, one shot, no staging.
+// Exposed as nlb_debug_tc_gemm for tests/test_gpu_tc.py.
 #include "nlb_internal.h"
 #include "tc_common.cuh"
 #include "tc_bf16.cuh"
 
 namespace nlb {
-
-__global__ void __launch_bounds__(256, 1)
-tc_test_kernel(const float* __restrict__ A, const float* __restrict__ W, const int K, const int mode, float* __restrict__ C) {
-  extern __shared__ __align__(128) unsigned char tsm[];
-  __shared__ uint64_t mbar;
-  __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t sbo = (uint32_t)K * 32u;          // bytes between 8-row groups
-  const uint32_t tile = 16u * sbo;                 // 128 rows
-  unsigned char* aHi = tsm;
-  unsigned char* aLo = aHi + tile;
-  unsigned char* bHi = aLo + tile;
-  unsigned char* bLo = bHi + tile;
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, 256);
-  if (tid == 32) tc::mbar_init(&mbar, 1);
-  for (int i = tid; i < 128 * K; i += 256) {
-    const int r = i / K, k = i - r * K;
-    float hi, lo;
-    tc::split_tf32(A[r * K + k], hi, lo);
-    *reinterpret_cast<float*>(aHi + tc::canon_off(r, k, sbo)) = mode ? hi : A[r * K + k];
-    *reinterpret_cast<float*>(aLo + tc::canon_off(r, k, sbo)) = lo;
-    tc::split_tf32(W[r * K + k], hi, lo);
-    *reinterpret_cast<float*>(bHi + tc::canon_off(r, k, sbo)) = mode ? hi : W[r * K + k];
-    *reinterpret_cast<float*>(bLo + tc::canon_off(r, k, sbo)) = lo;
-  }
-  tc::fence_async_smem();
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-  if (mode == 2) {
-    // A hi -> TMEM columns [128, 128+K), A lo -> [192, 192+K); warp w < 4 owns lanes 32w .. 32w+31
-    if (warp < 4) {
-      const int row = warp * 32 + lane;
-      const uint32_t base = tmem + ((uint32_t)(warp * 32) << 16);
-      for (int k0 = 0; k0 < K; k0 += 8) {
-        float hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) tc::split_tf32(A[row * K + k0 + j], hi[j], lo[j]);
-        tc::tmem_st8(base + 128u + (uint32_t)k0, hi);
-        tc::tmem_st8(base + 192u + (uint32_t)k0, lo);
-      }
-      tc::tmem_st_wait();
-    }
-    tc::fence_before_sync();
-    __syncthreads();
-    tc::fence_after_sync();
-    if (tid == 0) {
-      const uint32_t idesc = tc::idesc_tf32(128, 128);
-      uint32_t acc = 0;
-      for (int pass = 0; pass < 3; ++pass) {                       // lo*hi, hi*lo, hi*hi
-        const uint32_t a = tmem + (pass == 0 ? 192u : 128u);
-        const unsigned char* b = pass == 1 ? bLo : bHi;
-        for (int s = 0; s < K / 8; ++s) {
-          const uint64_t bd = tc::smem_desc(tc::smem_u32(b) + s * 256, 128, sbo);
-          tc::mma_tf32_ts(tmem, a + (uint32_t)(s * 8), bd, idesc, acc);
-          acc = 1;
-        }
-      }
-      tc::mma_commit(&mbar);
-    }
-  } else if (tid == 0) {
-    const uint32_t idesc = tc::idesc_tf32(128, 128);
-    uint32_t acc = 0;
-    const int npass = mode ? 3 : 1;
-    for (int pass = 0; pass < npass; ++pass) {
-      const unsigned char* a = (mode && pass == 0) ? aLo : aHi;   // lo*hi, hi*lo, hi*hi
-      const unsigned char* b = (mode && pass == 1) ? bLo : bHi;
-      for (int s = 0; s < K / 8; ++s) {
-        const uint64_t ad = tc::smem_desc(tc::smem_u32(a) + s * 256, 128, sbo);
-        const uint64_t bd = tc::smem_desc(tc::smem_u32(b) + s * 256, 128, sbo);
-        tc::mma_tf32(tmem, ad, bd, idesc, acc);
-        acc = 1;
-      }
-    }
-    tc::mma_commit(&mbar);
-  }
-  tc::mbar_wait(&mbar, 0);
-  tc::fence_after_sync();
-  {
-    const int row = (warp & 3) * 32 + lane;
-    const int c0 = (warp >> 2) * 64;
-    for (int cc = 0; cc < 64; cc += 32) {
-      float v[32];
-      tc::tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(c0 + cc), v);
-#pragma unroll
-      for (int j = 0; j < 32; ++j) C[row * 128 + c0 + cc + j] = v[j];
-    }
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 256);
-}
 
 // bf16x3 building blocks (tc_bf16.cuh): C[128 x 128] = A[128 x K] * W[128 x K]^T, K a multiple of 16, K <= 64.
 //   mode 4: A and B in the weight-tile layout (core matrices adjacent in K contiguous);
@@ -201,36 +107,14 @@ tc_test_bf16_kernel(const float* __restrict__ A, const float* __restrict__ W, co
   if (warp == 0) tc::tmem_dealloc(tmem, 256);
 }
 
-// mode 3: the warp-level path (rows16_mma: 3xTF32 on mma.sync.m16n8k8): C[16][128] = A[0:16][K] * Wt[K][128] (Wt is k-major here)
-template <int K>
-__global__ void __launch_bounds__(256) mma_sync_test_kernel(const float* __restrict__ A, const float* __restrict__ Wt, float* __restrict__ C) {
-  __shared__ float sA[16][K + 4];
-  for (int i = threadIdx.x; i < 16 * K; i += 256) sA[i / K][i % K] = A[i];
-  __syncthreads();
-  rows16_mma<128, K, 1>([&](int r, int, int) { return &sA[r][0]; }, Wt, 128, [&](int r, int c, float v, int) { C[r * 128 + c] = v; });
-}
-
 int launch_tc_test(const float* A, const float* W, int K, int mode, float* C, cudaStream_t st) {
-  if (mode == 3) {
-    if (K == 32) mma_sync_test_kernel<32><<<1, 256, 0, st>>>(A, W, C);
-    else if (K == 64) mma_sync_test_kernel<64><<<1, 256, 0, st>>>(A, W, C);
-    else return set_error("tc_test: mode 3 takes K = 32 or 64");
-    return check_launch("mma_sync_test_kernel");
-  }
-  if (mode >= 4 && mode <= 6) {
-    if (K % 16 != 0 || K < 16 || K > 64) return set_error("tc_test: bf16 modes take K = 16, 32, 48 or 64");
-    const size_t smem_b = (size_t)2 * (K / 8) * 130 * 16 + (size_t)4 * 128 * K * 2;
-    cudaError_t eb = cudaFuncSetAttribute(tc_test_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
-    if (eb != cudaSuccess) return set_error(cudaGetErrorString(eb));
-    tc_test_bf16_kernel<<<1, 256, smem_b, st>>>(A, W, K, mode, C);
-    return check_launch("tc_test_bf16_kernel");
-  }
-  if (K % 8 != 0 || K < 8 || K > 64) return set_error("tc_test: K must be a multiple of 8 in [8, 64]");
-  const size_t smem = (size_t)4 * 128 * K * 4;
-  cudaError_t e = cudaFuncSetAttribute(tc_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
-  tc_test_kernel<<<1, 256, smem, st>>>(A, W, K, mode, C);
-  return check_launch("tc_test_kernel");
+  if (mode < 4 || mode > 6) return set_error("tc_test: mode must be 4 (plain operands), 5 (shifted chunk-major A) or 6 (A in tensor memory)");
+  if (K % 16 != 0 || K < 16 || K > 64) return set_error("tc_test: K must be 16, 32, 48 or 64");
+  const size_t smem_b = (size_t)2 * (K / 8) * 130 * 16 + (size_t)4 * 128 * K * 2;
+  cudaError_t eb = cudaFuncSetAttribute(tc_test_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b);
+  if (eb != cudaSuccess) return set_error(cudaGetErrorString(eb));
+  tc_test_bf16_kernel<<<1, 256, smem_b, st>>>(A, W, K, mode, C);
+  return check_launch("tc_test_bf16_kernel");
 }
 
 }  // namespace nlb

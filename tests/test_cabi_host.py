@@ -32,5 +32,5 @@ def test_argument_validation_fails_loudly_without_touching_the_device():
     assert rc != 0 and b"scene is NULL" in L.nlb_last_error()
     rc = L.nlb_knn_query(nul, nul, 16, 8, nul, nul, nul)
     assert rc != 0 and b"NULL pointer" in L.nlb_last_error()
-    rc = L.nlb_debug_tc_gemm(nul, nul, 7, 1, nul, nul)
+    rc = L.nlb_debug_tc_gemm(nul, nul, 7, 4, nul, nul)
     assert rc != 0 and b"NULL pointer" in L.nlb_last_error()

@@ -20,14 +20,7 @@ torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 64)()
 _lib.load().nlb_debug_read_prof(buf, 64)
 v = list(buf)
-if os.environ.get("NLB_NB_V1"):
-    names = ["P0(t): PE, rd_fc, A1 -> TMEM", "A(t-1): scores, softmax, ctx", "wait L1", "E1(t)", "B(t-1): wv + fc GEMMs", "wait L2", "E2(t)",
-             "C1(t-1): LN, weights, out", "C2(t): q + q~ GEMMs", "wait L3", "E3(t): pf -> smem"]
-    for i in range(11):
-        print(f"{names[i]:36s} {v[i+1]-v[i]:8d} clk")
-    print("slot total", v[11] - v[0])
-    print("C1 detail: weights", v[12]-v[7], "LN", v[13]-v[12], "barrier", v[14]-v[13], "out", v[8]-v[14])
-else:
+if True:
     names = ["P0 (both sub-tiles) + q rows", "wait L1 (sub-tile 0)", "E1 (both)", "E2 (both, incl. waits)", "E3 (both, incl. waits)",
              "wait key projection", "scores + softmax (both)", "wait value projection", "context + weights (both)"]
     for i in range(9):
@@ -44,8 +37,6 @@ rn = ["load x (both rays)", "blend weights + wait blend GEMM", "blend MLP + soft
       "epi conv2", "wait conv3", "epi conv3", "wait tconv3", "epi tconv3", "wait tconv2", "epi tconv2", "wait tconv1",
       "epi tconv1 + reload x", "wait conv_out", "epi conv_out", "composite", "feat"]
 rv = v[32:]
-if os.environ.get("NLB_RAY_V1"):
-    rn = rn[:18]
 for i in range(len(rn)):
     print(f"ray {rn[i]:34s} {rv[i+1]-rv[i]:8d} clk")
-print("ray total (per pair of rays unless NLB_RAY_V1)", rv[len(rn)] - rv[0])
+print("ray total (per pair of rays)", rv[len(rn)] - rv[0])
