@@ -552,8 +552,11 @@ def knn_comparator(r):
                                             _lib.ptr(i32), _lib.ptr(d2b), _lib.stream()))
             torch.cuda.synchronize()
             out["ours_ms"] = (time.perf_counter() - t0) * 1e3
+        # the reference's CUDA kernel accumulates the squared distance with contracted FMAs, its CPU code (the definition this
+        # repo reproduces bit for bit, tests/test_gpu_render.py) does not: neighbours can swap at 1-ulp near-ties
         out.update({"queries": int(q.shape[0]), "support_points": int(sup.shape[0]),
-                    "indices_equal": bool(torch.equal(i32.long(), idx)), "distances_equal": bool(torch.equal(d2b, d2))})
+                    "index_agreement": float((i32.long() == idx).float().mean()),
+                    "max_rel_distance_diff": float(((d2b - d2).abs() / d2.clamp_min(1e-12)).max())})
         return out
     except Exception as e:
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}

@@ -80,6 +80,7 @@ struct Sync2 {
   uint64_t a_ready;
   uint64_t d_bar[N_DBAR];
   uint64_t x_full;           // the x tiles of both rays have landed (bulk copies of the pre-split feature_agg)
+  uint64_t bl2;              // a batch of colour-blend layer-2 MMAs (issued by a compute warp) has completed
   uint32_t tmem_slot;
   int nseg;
 };
@@ -366,6 +367,7 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
       for (int i = 0; i < NS; ++i) { tc::mbar_init(&sy.full[i], 1); tc::mbar_init(&sy.empty[i], 1); }
       tc::mbar_init(&sy.a_ready, NT);
       tc::mbar_init(&sy.x_full, 1);
+      tc::mbar_init(&sy.bl2, 1);
       for (int i = 0; i < N_DBAR; ++i) tc::mbar_init(&sy.d_bar[i], 1);
     }
   } else if (warp == 9 && lane == 0) {
@@ -551,12 +553,27 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
     // ---- colour blend (model.py:528-538), one ray after the other in the scratch of region Q -----------------------------
     float* sBl = reinterpret_cast<float*>(sm + Q_OFF);      // [S][36]
     float* sLogit = sBl + 128 * 36;                          // [S * V]
-    float* sW2 = sLogit + 2048;                              // [16][32] | b2[16] | w3[16] | b3
-    for (int i = tid; i < 512; i += NT) sW2[i] = __ldg(w.bl2 + i);
-    if (tid < 16) { sW2[512 + tid] = __ldg(w.bl2_b + tid); sW2[528 + tid] = __ldg(w.bl3 + tid); }
-    if (tid == 0) sW2[544] = __ldg(w.bl3_b);
+    float* sW2 = sLogit + 2048;                              // b2[16] | w3[16] | b3
+    unsigned char* sW2b = reinterpret_cast<unsigned char*>(sW2 + 64);   // layer 2 [16 x 32] as a bf16 hi | lo weight tile (1 KB | 1 KB)
+    if (tid < 16) { sW2[tid] = __ldg(w.bl2_b + tid); sW2[16 + tid] = __ldg(w.bl3 + tid); }
+    if (tid == 0) sW2[32] = __ldg(w.bl3_b);
+    {
+      const int n = tid >> 4, k = (tid & 15) * 2;           // 256 threads: one pair of the 16 x 32 weights each
+      uint32_t hi, lo;
+      tc::split_bf16x2(__ldg(w.bl2 + n * 32 + k), __ldg(w.bl2 + n * 32 + k + 1), hi, lo);
+      *reinterpret_cast<uint32_t*>(sW2b + tc::wt_off(n, k, 32)) = hi;
+      *reinterpret_cast<uint32_t*>(sW2b + 1024 + tc::wt_off(n, k, 32)) = lo;
+    }
+    tc::fence_async_smem();
     wait_d(D_BLEND);
     R2_STAMP(2);
+    // Layer 2 (32 -> 16) of the blend MLP runs on the tensor cores as well: the S * V (sample, view) items of a ray are rows of
+    // 128-row tiles; a thread builds layer-1 activations of its items (per-view half streamed from HBM + per-sample half from
+    // the blend GEMM), writes them as the A operand into free tensor-memory columns (128 ..), one compute warp issues the MMAs
+    // of a batch of four tiles, and the 16 outputs per item come back for the 16 -> 1 head.  (On FFMA2 this layer alone took
+    // 50 k of the 244 k clk per pair of rays: 2 x 1024 items x 512 FMAs on eight warps.)
+    constexpr uint32_t BL_TM = 128, BL_TILE = 48;            // per tile: A hi 16 | A lo 16 | D 16 columns
+    uint32_t bl_par = 0;
     for (int ray = 0; ray < 2; ++ray) {
       if (ray == 1 && !live1) break;   // uniform
       const int64_t s0 = sbase[ray];
@@ -567,64 +584,70 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
         for (int j = 0; j < 16; ++j) sBl[c.m * 36 + c.half * 16 + j] = v[j];
       }
       cta_sync();
-      // two (sample, view) items per thread and iteration; the rows of `partial` (streamed from HBM, written by aggregate_kernel
-      // a chunk ago) of the NEXT iteration are requested before the current one is evaluated
-      const int n_it = (S * V + 2 * NT - 1) / (2 * NT);
-      float4 pa[2][8], pn[2][8];
-      auto fetch = [&](int it, float4 (&dst)[2][8]) {
-        const int i0 = it * 2 * NT + tid, i1 = i0 + NT;
-        const int ib[2] = {i0 < S * V ? i0 : 0, i1 < S * V ? i1 : (i0 < S * V ? i0 : 0)};
+      const int n_items = S * V, n_tiles = (n_items + 127) / 128;
+      for (int t0 = 0; t0 < n_tiles; t0 += 4) {
+        float visf[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-          const float4* pp = reinterpret_cast<const float4*>(partial + (s0 * V + ib[u]) * 32);
+          const int tl = 2 * u + c.half, t = t0 + tl, i = t * 128 + c.m;
+          const bool on = t < n_tiles && i < n_items;
+          visf[u] = on ? __ldg(rgbvis + (s0 * V + i) * 4 + 3) : 0.f;
+          float4 pa[8];
+          const float4* pp = reinterpret_cast<const float4*>(partial + (s0 * V + (on ? i : 0)) * 32);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) dst[u][q] = __ldcs(pp + q);   // streamed once
-        }
-      };
-      fetch(0, pa);
-      for (int it = 0; it < n_it; ++it) {
-        const int i0 = it * 2 * NT + tid, i1 = i0 + NT;
-        const bool one = i0 < S * V, two = i1 < S * V;
-        const int ib[2] = {one ? i0 : 0, two ? i1 : (one ? i0 : 0)};
-        const float vis0 = one ? __ldg(rgbvis + (s0 * V + i0) * 4 + 3) : 0.f;
-        const float vis1 = two ? __ldg(rgbvis + (s0 * V + i1) * 4 + 3) : 0.f;
-        if (it + 1 < n_it) fetch(it + 1, pn);
-        float h1[2][32];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int s = ib[u] / V;
+          for (int q = 0; q < 8; ++q) pa[q] = on ? __ldcs(pp + q) : make_float4(0.f, 0.f, 0.f, 0.f);   // streamed once
+          const int s = (on ? i : 0) / V;
+          uint32_t hi[16], lo[16];
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            const float4 a = pa[u][q];
             const float4 bq = *reinterpret_cast<const float4*>(sBl + s * 36 + q * 4);
-            h1[u][q * 4 + 0] = leaky(a.x + bq.x); h1[u][q * 4 + 1] = leaky(a.y + bq.y);
-            h1[u][q * 4 + 2] = leaky(a.z + bq.z); h1[u][q * 4 + 3] = leaky(a.w + bq.w);
+            tc::split_bf16x2(leaky(pa[q].x + bq.x), leaky(pa[q].y + bq.y), hi[2 * q], lo[2 * q]);
+            tc::split_bf16x2(leaky(pa[q].z + bq.z), leaky(pa[q].w + bq.w), hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          if (t < n_tiles) {   // warp-uniform
+            tc::tmem_st16_u(c.trow + tmem + BL_TM + tl * BL_TILE, hi);
+            tc::tmem_st16_u(c.trow + tmem + BL_TM + tl * BL_TILE + 16, lo);
           }
         }
-        float logit0 = sW2[544], logit1 = logit0;
-#pragma unroll 2
-        for (int o = 0; o < 16; ++o) {
-          float a = sW2[512 + o], a1 = 0.f, cacc = a, c1 = 0.f;
+        tc::tmem_st_wait();
+        tc::fence_before_sync();
+        cta_sync();
+        if (warp == 0) {
+          tc::fence_after_sync();
+          if (tc::elect_one()) {
+            const uint32_t idesc = tc::idesc_bf16(128, 16);
+            const uint32_t wb = tc::smem_u32(sW2b), b_hi32 = tc::desc_hi(32u * 16u);
+            for (int tl = 0; tl < 4 && t0 + tl < n_tiles; ++tl) {
+              const uint32_t base = tmem + BL_TM + tl * BL_TILE;
 #pragma unroll
-          for (int k = 0; k < 32; k += 4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(sW2 + o * 32 + k);
-            fma2_v(a, a1, w4.x, w4.y, h1[0][k], h1[0][k + 1]);
-            fma2_v(cacc, c1, w4.x, w4.y, h1[1][k], h1[1][k + 1]);
-            fma2_v(a, a1, w4.z, w4.w, h1[0][k + 2], h1[0][k + 3]);
-            fma2_v(cacc, c1, w4.z, w4.w, h1[1][k + 2], h1[1][k + 3]);
+              for (int pass = 0; pass < 3; ++pass) {                  // lo*hi, hi*lo, hi*hi
+                const uint32_t a = base + (pass == 0 ? 16u : 0u);
+                const uint32_t bp = wb + (pass == 1 ? 1024u : 0u);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                  tc::mma_bf16_ts_w(base + 32u, a + (uint32_t)ks * 8u, tc::desc_lo(bp + (uint32_t)ks * 256u, 128u), b_hi32, idesc, pass > 0 || ks > 0);
+              }
+            }
+            tc::mma_commit(&sy.bl2);
           }
-          const float w3 = sW2[528 + o];
-          logit0 = fmaf(w3, leaky(a + a1), logit0);
-          logit1 = fmaf(w3, leaky(cacc + c1), logit1);
+          __syncwarp();
         }
-        if (one) sLogit[i0] = vis0 == 0.f ? -1e9f : logit0;
-        if (two) sLogit[i1] = vis1 == 0.f ? -1e9f : logit1;
-        if (it + 1 < n_it) {
+        tc::mbar_wait(&sy.bl2, bl_par);
+        bl_par ^= 1u;
+        tc::fence_after_sync();
 #pragma unroll
-          for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < 2; ++u) {
+          const int tl = 2 * u + c.half, t = t0 + tl, i = t * 128 + c.m;
+          if (t < n_tiles) {   // warp-uniform
+            float d[16];
+            tc::tmem_ld16(c.trow + tmem + BL_TM + tl * BL_TILE + 32, d);
+            float logit = sW2[32];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) pa[u][q] = pn[u][q];
+            for (int o = 0; o < 16; ++o) logit = fmaf(sW2[16 + o], leaky(d[o] + sW2[o]), logit);
+            if (i < n_items) sLogit[i] = visf[u] == 0.f ? -1e9f : logit;
+          }
         }
+        tc::fence_before_sync();   // the accumulator columns are rewritten by the next batch
       }
       cta_sync();
       if (tid < S) {

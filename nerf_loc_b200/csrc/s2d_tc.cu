@@ -228,22 +228,31 @@ s2d_tc_kernel(const PairMlp m, const float* __restrict__ w2_packed, const float*
 
 int launch_s2d_tc(const MatchW& w, const float* desc0, const float* desc1, int64_t N, int64_t M, float* score, cudaStream_t st) {
   const int64_t ntiles = (M + 127) / 128;
-  unsigned char* cells = nullptr;
-  // the split copy of the cell descriptors lives for the duration of this call (stream-ordered allocation)
-  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&cells), (size_t)ntiles * 6 * s2dtc::SLAB, st);
-  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  // the split copy of the cell descriptors (98 KB per 128 cells) lives in a buffer kept per host thread and device and grown on
+  // demand: nlb_s2d_scores has no scratch argument, and a stream-ordered allocation per call cost several milliseconds whenever
+  // the pool had been trimmed at a synchronisation
+  static thread_local unsigned char* cache[16] = {};
+  static thread_local size_t cache_bytes[16] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return set_error("s2d: unsupported device ordinal");
+  const size_t need = (size_t)ntiles * 6 * s2dtc::SLAB;
+  cudaError_t e = cudaSuccess;
+  if (cache_bytes[dev] < need) {
+    if (cache[dev]) { cudaStreamSynchronize(st); cudaFree(cache[dev]); cache[dev] = nullptr; cache_bytes[dev] = 0; }
+    e = cudaMalloc(reinterpret_cast<void**>(&cache[dev]), need);
+    if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+    cache_bytes[dev] = need;
+  }
+  unsigned char* cells = cache[dev];
   const int64_t nthreads = ntiles * 128 * 96;
   s2dtc::split_cells_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, st>>>(desc1, M, ntiles, cells);
   e = cudaFuncSetAttribute(s2dtc::s2d_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2dtc::SMEM_BYTES);
-  if (e != cudaSuccess) { cudaFreeAsync(cells, st); return set_error(cudaGetErrorString(e)); }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
+  if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
+  int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(N < sms ? N : sms);
   s2dtc::s2d_tc_kernel<<<grid, NT + 64, s2dtc::SMEM_BYTES, st>>>(w.coarse, w.tb_w2c, desc0, cells, N, M, score);
-  const int rc = check_launch("s2d_tc_kernel");
-  cudaFreeAsync(cells, st);
-  return rc;
+  return check_launch("s2d_tc_kernel");
 }
 
 }  // namespace nlb

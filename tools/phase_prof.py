@@ -8,7 +8,7 @@ from nerf_loc_b200.conditional_nerf import ConditionalNeRF
 from nerf_loc_b200.config import default_args
 sc, sd, ro, rd = bench.build_frame()
 dev = torch.device("cuda")
-model = ConditionalNeRF(default_args(bench.S)).eval(); model.load_state_dict(sd, strict=False); model = model.to(dev)
+model = ConditionalNeRF(default_args(128)).eval(); model.load_state_dict(sd, strict=False); model = model.to(dev)
 data = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in sc.items() if k != "vis_featmaps"}
 data["scene"], data["filename"] = "s", "f"
 model.support_neural_points = None

@@ -14,3 +14,4 @@ print('match', {k:v for k,v in d['match'].items() if k!='roofline'}); print(d['m
 print('pipeline', d.get('pipeline'))
 PY
 timeout 400 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/${T}_bench_ref.json 2>/dev/null; cut -c1-700 gpurun_out/${T}_bench_ref.json
+timeout 200 python tools/phase_prof.py > gpurun_out/${T}_phase.log 2>&1; grep -E "^ray|^nb2|^agg" gpurun_out/${T}_phase.log

@@ -1,0 +1,9 @@
+T=${1:-r2u}
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_tests.log 2>&1; tail -4 gpurun_out/${T}_tests.log | cut -c1-300
+timeout 200 python bench.py --steps 2 --warmup 2 --cpu-rays 0 --cpu-match-n3 0 2>gpurun_out/${T}_b1.err | python -c "
+import json,sys
+l=sys.stdin.readline()
+try:
+    d=json.loads(l); print('bench', d['value'], d['kernels_ms_per_step'])
+except Exception as e: print('FAILED', l[:200])"; tail -2 gpurun_out/${T}_b1.err
+timeout 200 python tools/phase_prof.py 2>&1 | grep "^ray"
