@@ -228,7 +228,7 @@ int nlb_confidence_head(const float* packed_weights, int S, const float* aggrega
 size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
   const size_t n = (size_t)(chunk_rays < 1 ? 1 : chunk_rays) * S;
   const size_t slabs = S > 128 ? align256((size_t)RL_MAX_GRID * ray_long_slab_floats(S) * 4) : 0;
-  return align256(n * KNN_K * 4) * 2 + align256(n * W_HID * 4) * 2 + align256(n * V * 32 * 4) + align256(n * V * 16) +
+  return align256(n * KNN_K * 4) * 2 + align256(n * W_HID * 4) * 2 + align256((n * V + 31) / 32 * 32 * 32 * 4) + align256(n * V * 16) +
          align256(n) + align256(neighbor2_scratch_floats((int64_t)n) * 4) + align256(n * V * 8) + align256(n * 416 * 4) + slabs + 2048;
 }
 
@@ -268,7 +268,7 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
   float* d2 = c.take<float>(n * KNN_K);
   float* agg = c.take<float>(n * W_HID);
   float* fagg = c.take<float>(n * W_HID);
-  float* partial = c.take<float>(n * V * 32);
+  float* partial = c.take<float>((n * V + 31) / 32 * 32 * 32);   // whole groups of 32 rows (partial_off)
   float* rgbvis = c.take<float>(n * V * 4);
   unsigned char* nvalid = c.take<unsigned char>(n);
   float* nb2 = c.take<float>(neighbor2_scratch_floats((int64_t)n));

@@ -148,23 +148,28 @@ fc_tail_kernel(const RenderW w, const float* __restrict__ G, const int64_t N, fl
     uint32_t d_par = 0, free_par = 0;
     int slab = 0;   // K-slabs written so far (over all tiles)
     auto wait_d = [&]() { tc::mbar_wait(&sy.d_ready, d_par); d_par ^= 1u; tc::fence_after_sync(); };
-    // this thread's part of a K-slab: row `row`, columns 16 half .. 16 half + 15 of the slab (two 8-column chunks)
-    auto fetch = [&](int64_t n, int kt, float4 (&dst)[4]) {
-      if (n < N) {
-        const float4* p = reinterpret_cast<const float4*>(G + n * G_LD + kt * 32 + half * 16);
+    // this thread's part of a K-slab: rows tid / 4 and 64 + tid / 4, the 8-column chunk tid % 4 (four lanes share a row's
+    // 128-byte run of the slab: coalesced, where one lane per row was 32 separate lines per load instruction)
+    const int64_t n_base = ((int64_t)blockIdx.x) * 128;
+    auto fetch = [&](int64_t nb, int kt, float4 (&dst)[4]) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = __ldcs(p + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 2; ++u) {
+        const int64_t nn = nb + u * 64 + (tid >> 2);
+        if (nn < N) {
+          const float4* p = reinterpret_cast<const float4*>(G + nn * G_LD + kt * 32 + (tid & 3) * 8);
+          dst[2 * u] = __ldcs(p); dst[2 * u + 1] = __ldcs(p + 1);
+        } else {
+          dst[2 * u] = make_float4(0.f, 0.f, 0.f, 0.f); dst[2 * u + 1] = dst[2 * u];
+        }
       }
     };
     for (int it = 0; it < nmy; ++it) {
-      const int64_t n = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 128 + row;
+      const int64_t nb = n_base + (int64_t)it * gridDim.x * 128;
+      const int64_t n = nb + row;
       float4 cur[4], nxt[4];
-      fetch(n, 0, cur);
+      fetch(nb, 0, cur);
       for (int kt = 0; kt < NKT1; ++kt, ++slab) {
-        if (kt + 1 < NKT1) fetch(n, kt + 1, nxt);
+        if (kt + 1 < NKT1) fetch(nb, kt + 1, nxt);
         const int buf = kt & 1;
         if (slab >= 2) {   // the MMAs that read this buffer two slabs ago have completed
           tc::mbar_wait(&sy.a_free[buf], (free_par >> buf) & 1u);
@@ -172,9 +177,9 @@ fc_tail_kernel(const RenderW w, const float* __restrict__ G, const int64_t N, fl
         }
         unsigned char* hi = sm + A_OFF + buf * 16384;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          const float v[8] = {cur[2 * c].x, cur[2 * c].y, cur[2 * c].z, cur[2 * c].w, cur[2 * c + 1].x, cur[2 * c + 1].y, cur[2 * c + 1].z, cur[2 * c + 1].w};
-          const uint32_t o = (uint32_t)(half * 2 + c) * 2048u + (uint32_t)row * 16u;
+        for (int u = 0; u < 2; ++u) {
+          const float v[8] = {cur[2 * u].x, cur[2 * u].y, cur[2 * u].z, cur[2 * u].w, cur[2 * u + 1].x, cur[2 * u + 1].y, cur[2 * u + 1].z, cur[2 * u + 1].w};
+          const uint32_t o = (uint32_t)(tid & 3) * 2048u + (uint32_t)(u * 64 + (tid >> 2)) * 16u;
           tc::split_store8(hi + o, hi + 8192 + o, v);
         }
         tc::fence_async_smem();

@@ -549,13 +549,14 @@ row_gemm128_kernel(const float* __restrict__ A, const float* __restrict__ wpacke
   uint32_t par = 0;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int64_t n0 = t * 128;
-    // A rows -> chunk-major bf16 hi | lo: lanes over rows of one 8-column chunk, 8 items in flight per thread
-#pragma unroll
-    for (int i0 = 0; i0 < 128 * 16; i0 += 8 * NT) {
+    // A rows -> chunk-major bf16 hi | lo.  Four lanes share a row (one 8-column chunk = 32 bytes each: a 128-byte run), eight
+    // rows per warp and instruction; 8 items in flight per thread.  (One lane per row, 512 bytes apart, was 32 separate lines
+    // per load instruction.)
+    {
       float4 a[8][2];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * NT + tid, r = i & 127, c = i >> 7;
+        const int r = (u >> 2) * 64 + (tid >> 2), c = (u & 3) * 4 + (tid & 3);
         a[u][0] = make_float4(0.f, 0.f, 0.f, 0.f); a[u][1] = a[u][0];
         if (n0 + r < N) {
           const float4* pp = reinterpret_cast<const float4*>(A + (n0 + r) * W_HID + c * 8);
@@ -564,7 +565,7 @@ row_gemm128_kernel(const float* __restrict__ A, const float* __restrict__ wpacke
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const int i = i0 + u * NT + tid, r = i & 127, c = i >> 7;
+        const int r = (u >> 2) * 64 + (tid >> 2), c = (u & 3) * 4 + (tid & 3);
         const float v[8] = {a[u][0].x, a[u][0].y, a[u][0].z, a[u][0].w, a[u][1].x, a[u][1].y, a[u][1].z, a[u][1].w};
         const uint32_t o = (uint32_t)c * RG_RA * 16u + (uint32_t)r * 16u;
         tc::split_store8(aHi + o, aLo + o, v);

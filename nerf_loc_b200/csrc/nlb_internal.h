@@ -28,12 +28,24 @@ constexpr int W_HID = 128;    // model_3d_hidden_dim
 constexpr int C_VIS = 32;     // DepthFusionNet output channels
 constexpr int KNN_K = 8;
 
+// Layout of the per-(sample, view) blend partials [rows][32] between aggregate_kernel and the ray kernels: groups of 32 rows,
+// the eight 16-byte pieces of a row 512 bytes apart, so that 32 consecutive rows read (or written) one piece at a time by 32
+// lanes are one contiguous 512-byte run.  (Row-major, the thread-per-row loads of the ray kernel were 32 separate 128-byte
+// lines per instruction and stalled its load issue for 10 k clk per batch.)  Float offset of 4-float piece q of row r:
+__host__ __device__ __forceinline__ int64_t partial_off(int64_t r, int q) { return (r >> 5) * 1024 + (int64_t)q * 128 + (r & 31) * 4; }
+
 struct UnetLayer {
   const float* w;      // conv: [3*Cin][Cout]; transposed conv: even [Cin][Cout] followed by odd [2*Cin][Cout]
   const float* b;      // [Cout]
   const float* g;      // LayerNorm gain, transposed to [S_level][Cout]
   const float* be;     // LayerNorm bias,  transposed to [S_level][Cout]
+  const float* g2;     // the same two in the piece-major layout of ln_off (pair ray kernel: thread-per-row reads, coalesced)
+  const float* be2;
 };
+
+// LayerNorm affine [rows][C] for thread-per-row readers: groups of 32 rows, the 4-float pieces of a row 512 bytes apart (see
+// partial_off).  Float offset of element (r, c):
+__host__ __device__ __forceinline__ int64_t ln_off(int r, int c, int C) { return (int64_t)(r >> 5) * (32 * C) + (c >> 2) * 128 + (r & 31) * 4 + (c & 3); }
 
 struct RenderW {
   int S;  // samples per ray the RayUnet LayerNorms were built for (0: no RayUnet packed)

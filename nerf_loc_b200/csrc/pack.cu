@@ -64,6 +64,8 @@ static RenderW layout(const float* base, int S, size_t* total) {
     w.u[l].b = a.take(UN_COUT[l]);
     w.u[l].g = a.take((size_t)sl * UN_COUT[l]);
     w.u[l].be = a.take((size_t)sl * UN_COUT[l]);
+    w.u[l].g2 = a.take((size_t)((sl + 31) / 32 * 32) * UN_COUT[l]);
+    w.u[l].be2 = a.take((size_t)((sl + 31) / 32 * 32) * UN_COUT[l]);
   }
   // bf16 hi | lo: 2 planes x 2 bytes = one float per weight
   for (int l = 0; l < 7; ++l)
@@ -100,6 +102,13 @@ __global__ void pack_t_kernel(float* dst, const float* __restrict__ src, int Kp,
   if (i >= Kp * N) return;
   const int k = i / N, n = i % N;
   dst[(size_t)k * dst_ld + n] = k < Kv ? src[(size_t)n * src_ld + src_off + k] : 0.f;
+}
+// LayerNorm affine [C][S] (reference layout) -> ln_off layout over [S][C]
+__global__ void pack_ln_kernel(float* dst, const float* __restrict__ src, int S, int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= S * C) return;
+  const int s = i / C, c = i % C;
+  dst[ln_off(s, c, C)] = src[(size_t)c * S + s];
 }
 __global__ void pack_copy_kernel(float* dst, const float* __restrict__ src, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -237,6 +246,8 @@ int render_weights_pack(const float* const* params, int n_params, int S, float* 
       k.c(w.u[l].b, b + 1, co);
       k.t(w.u[l].g, b + 2, sl, co, sl, 0, sl);   // [C][S] -> [S][C]
       k.t(w.u[l].be, b + 3, sl, co, sl, 0, sl);
+      pack_ln_kernel<<<(sl * co + 255) / 256, 256, 0, st>>>(const_cast<float*>(w.u[l].g2), params[b + 2], sl, co);
+      pack_ln_kernel<<<(sl * co + 255) / 256, 256, 0, st>>>(const_cast<float*>(w.u[l].be2), params[b + 3], sl, co);
     }
   }
   if (S > 0) {

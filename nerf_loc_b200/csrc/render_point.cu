@@ -599,7 +599,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
               a = fmaf(c.x, wb[0], a); a = fmaf(c.y, wb[1], a); a = fmaf(c.z, wb[2], a);
               a = fmaf(ri[RI_VIS], wb[3], a);
               a = fmaf(ri[RI_RD0], wb[4], a); a = fmaf(ri[RI_RD1], wb[5], a); a = fmaf(ri[RI_RD2], wb[6], a); a = fmaf(ri[RI_RD3], wb[7], a);
-              __stcs(partial_out + (nidx(p) * V + v) * 32 + lane, a + bias);
+              __stcs(partial_out + partial_off(nidx(p) * V + v, lane >> 2) + (lane & 3), a + bias);
             }
             if (mvf_out) {
               float* mo = mvf_out + (nidx(p) * V + v) * C_RGBF;
@@ -753,7 +753,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
             a = fmaf(ri[RI_RD0], wb[4], a); a = fmaf(ri[RI_RD1], wb[5], a); a = fmaf(ri[RI_RD2], wb[6], a); a = fmaf(ri[RI_RD3], wb[7], a);
             // per-chunk intermediates are written once and read once by the next kernel: streaming stores keep them from
             // evicting the reference feature maps (118 MB, gathered by every sample) out of the 126 MB L2
-            __stcs(partial_out + (nidx(p) * V + v) * 32 + lane, a + bias);
+            __stcs(partial_out + partial_off(nidx(p) * V + v, lane >> 2) + (lane & 3), a + bias);
           }
         }
       }

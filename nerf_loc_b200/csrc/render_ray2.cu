@@ -174,8 +174,8 @@ __device__ __forceinline__ void epi_conv1(const Ctx& c, const uint32_t tmem, con
     float g[16], be[16];
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(U.g + srow * 64 + c0 + cc + j));
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(U.be + srow * 64 + c0 + cc + j));
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(U.g2 + ln_off(srow, c0 + cc + j, 64)));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(U.be2 + ln_off(srow, c0 + cc + j, 64)));
       g[j] = g4.x; g[j + 1] = g4.y; g[j + 2] = g4.z; g[j + 3] = g4.w;
       be[j] = b4.x; be[j + 1] = b4.y; be[j + 2] = b4.z; be[j + 3] = b4.w;
     }
@@ -243,8 +243,8 @@ __device__ __forceinline__ void epi_enc_pair(const Ctx& c, const uint32_t tmem, 
     tld16(c.trow + tmem + c0 + cc, v);
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(U.g + srow * 128 + c0 + cc + j));
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(U.be + srow * 128 + c0 + cc + j));
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(U.g2 + ln_off(srow, c0 + cc + j, 128)));
+      const float4 b4 = __ldg(reinterpret_cast<const float4*>(U.be2 + ln_off(srow, c0 + cc + j, 128)));
       const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -312,8 +312,8 @@ __device__ __forceinline__ void epi_dec(const Ctx& c, const uint32_t tmem, const
       tld16(c.trow + tmem + par * N + c0 + cc, v);
 #pragma unroll
       for (int u = 0; u < 16; u += 4) {
-        const float4 g4 = __ldg(reinterpret_cast<const float4*>(U.g + so * N + c0 + cc + u));
-        const float4 b4 = __ldg(reinterpret_cast<const float4*>(U.be + so * N + c0 + cc + u));
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(U.g2 + ln_off(so, c0 + cc + u, N)));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(U.be2 + ln_off(so, c0 + cc + u, N)));
         const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int t = 0; t < 4; ++t) v[u + t] = elu(((v[u + t] + __ldg(U.b + c0 + cc + u + t)) - mean) * rstd * gg[t] + bb[t]);
@@ -546,6 +546,26 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
       const int ray = tid >> 7, s = tid & 127;
       if (s < S) sV[ray * 512 + 384 + s] = (ray == 0 || live1) ? z_vals[(ray0 + ray) * zs + s] : 0.f;
     }
+    // colour blend: the (sample, view) items of a ray are rows of 128-row tiles, processed in batches of four tiles; this
+    // thread's two items of the first batch are requested before anything else is waited for
+    const int bl_items = S * V, bl_tiles = (bl_items + 127) / 128, bl_nb = (bl_tiles + 3) / 4;
+    const int bl_steps = (live1 ? 2 : 1) * bl_nb;
+    float4 pa[2][8];
+    float visf[2];
+    auto bl_fetch = [&](int step) {
+      const int ray = step / bl_nb, t0 = (step - ray * bl_nb) * 4;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int t = t0 + 2 * u + (warp >> 2), i = t * 128 + (warp & 3) * 32 + lane;
+        const bool on = t < bl_tiles && i < bl_items;
+        visf[u] = on ? __ldg(rgbvis + (sbase[ray] * V + i) * 4 + 3) : 0.f;
+        const int64_t r = sbase[ray] * V + (on ? i : 0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)   // streamed once; 32 lanes x one piece = 512 contiguous bytes (partial_off)
+          pa[u][q] = on ? __ldcs(reinterpret_cast<const float4*>(partial + partial_off(r, q))) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    bl_fetch(0);
     tc::mbar_wait(&sy.x_full, 0);
     a_ready();                                                             // a#0: x of both rays
     R2_STAMP(1);
@@ -574,101 +594,110 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
     // 50 k of the 244 k clk per pair of rays: 2 x 1024 items x 512 FMAs on eight warps.)
     constexpr uint32_t BL_TM = 128, BL_TILE = 48;            // per tile: A hi 16 | A lo 16 | D 16 columns
     uint32_t bl_par = 0;
-    for (int ray = 0; ray < 2; ++ray) {
-      if (ray == 1 && !live1) break;   // uniform
+    for (int step = 0; step < bl_steps; ++step) {
+      const int ray = step / bl_nb, t0 = (step - ray * bl_nb) * 4;
       const int64_t s0 = sbase[ray];
-      {
+      if (t0 == 0) {
         float v[16];
         tc::tmem_ld16(c.trow + tmem + 448 + 32 * ray + c.half * 16, v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) sBl[c.m * 36 + c.half * 16 + j] = v[j];
-      }
-      cta_sync();
-      const int n_items = S * V, n_tiles = (n_items + 127) / 128;
-      for (int t0 = 0; t0 < n_tiles; t0 += 4) {
-        float visf[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int tl = 2 * u + c.half, t = t0 + tl, i = t * 128 + c.m;
-          const bool on = t < n_tiles && i < n_items;
-          visf[u] = on ? __ldg(rgbvis + (s0 * V + i) * 4 + 3) : 0.f;
-          float4 pa[8];
-          const float4* pp = reinterpret_cast<const float4*>(partial + (s0 * V + (on ? i : 0)) * 32);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) pa[q] = on ? __ldcs(pp + q) : make_float4(0.f, 0.f, 0.f, 0.f);   // streamed once
-          const int s = (on ? i : 0) / V;
-          uint32_t hi[16], lo[16];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 bq = *reinterpret_cast<const float4*>(sBl + s * 36 + q * 4);
-            tc::split_bf16x2(leaky(pa[q].x + bq.x), leaky(pa[q].y + bq.y), hi[2 * q], lo[2 * q]);
-            tc::split_bf16x2(leaky(pa[q].z + bq.z), leaky(pa[q].w + bq.w), hi[2 * q + 1], lo[2 * q + 1]);
-          }
-          if (t < n_tiles) {   // warp-uniform
-            tc::tmem_st16_u(c.trow + tmem + BL_TM + tl * BL_TILE, hi);
-            tc::tmem_st16_u(c.trow + tmem + BL_TM + tl * BL_TILE + 16, lo);
-          }
-        }
-        tc::tmem_st_wait();
-        tc::fence_before_sync();
         cta_sync();
-        if (warp == 0) {
-          tc::fence_after_sync();
-          if (tc::elect_one()) {
-            const uint32_t idesc = tc::idesc_bf16(128, 16);
-            const uint32_t wb = tc::smem_u32(sW2b), b_hi32 = tc::desc_hi(32u * 16u);
-            for (int tl = 0; tl < 4 && t0 + tl < n_tiles; ++tl) {
-              const uint32_t base = tmem + BL_TM + tl * BL_TILE;
-#pragma unroll
-              for (int pass = 0; pass < 3; ++pass) {                  // lo*hi, hi*lo, hi*hi
-                const uint32_t a = base + (pass == 0 ? 16u : 0u);
-                const uint32_t bp = wb + (pass == 1 ? 1024u : 0u);
-#pragma unroll
-                for (int ks = 0; ks < 2; ++ks)
-                  tc::mma_bf16_ts_w(base + 32u, a + (uint32_t)ks * 8u, tc::desc_lo(bp + (uint32_t)ks * 256u, 128u), b_hi32, idesc, pass > 0 || ks > 0);
-              }
-            }
-            tc::mma_commit(&sy.bl2);
-          }
-          __syncwarp();
-        }
-        tc::mbar_wait(&sy.bl2, bl_par);
-        bl_par ^= 1u;
-        tc::fence_after_sync();
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int tl = 2 * u + c.half, t = t0 + tl, i = t * 128 + c.m;
-          if (t < n_tiles) {   // warp-uniform
-            float d[16];
-            tc::tmem_ld16(c.trow + tmem + BL_TM + tl * BL_TILE + 32, d);
-            float logit = sW2[32];
-#pragma unroll
-            for (int o = 0; o < 16; ++o) logit = fmaf(sW2[16 + o], leaky(d[o] + sW2[o]), logit);
-            if (i < n_items) sLogit[i] = visf[u] == 0.f ? -1e9f : logit;
-          }
-        }
-        tc::fence_before_sync();   // the accumulator columns are rewritten by the next batch
       }
-      cta_sync();
-      if (tid < S) {
-        // softmax over the views and the blended colour; the V colour rows are requested together, ahead of the exponentials
-        float4 cv[16];
+      if (step == 0) R2_STAMP(20);
+      float vis_cur[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int tl = 2 * u + c.half, t = t0 + tl, i = t * 128 + c.m;
+        const bool on = t < bl_tiles && i < bl_items;
+        vis_cur[u] = visf[u];
+        const int s = (on ? i : 0) / V;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bq = *reinterpret_cast<const float4*>(sBl + s * 36 + q * 4);
+          tc::split_bf16x2(leaky(pa[u][q].x + bq.x), leaky(pa[u][q].y + bq.y), hi[2 * q], lo[2 * q]);
+          tc::split_bf16x2(leaky(pa[u][q].z + bq.z), leaky(pa[u][q].w + bq.w), hi[2 * q + 1], lo[2 * q + 1]);
+        }
+        if (t < bl_tiles) {   // warp-uniform
+          tc::tmem_st16_u(c.trow + tmem + BL_TM + tl * BL_TILE, hi);
+          tc::tmem_st16_u(c.trow + tmem + BL_TM + tl * BL_TILE + 16, lo);
+        }
+      }
+      if (step == 0) R2_STAMP(25);
+      // the per-view halves of the NEXT batch (HBM, written by aggregate_kernel a chunk ago: ~7 k clk when waited for in place)
+      // and, at a ray's last batch, its colour rows are requested now and land underneath the MMAs and the 16 -> 1 head
+      if (step + 1 < bl_steps) bl_fetch(step + 1);
+      const bool last_of_ray = t0 + 4 >= bl_tiles;
+      float4 cv[16];
+      if (last_of_ray && tid < S) {
 #pragma unroll
         for (int v = 0; v < 16; ++v)
           cv[v] = v < V ? __ldg(reinterpret_cast<const float4*>(rgbvis + ((s0 + tid) * V + v) * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float mx = -FLT_MAX;
-        for (int v = 0; v < V; ++v) mx = fmaxf(mx, sLogit[tid * V + v]);
-        float den = 0.f, r = 0.f, g = 0.f, bl = 0.f;
-#pragma unroll
-        for (int v = 0; v < 16; ++v) {
-          if (v < V) {
-            const float e = expf(sLogit[tid * V + v] - mx);
-            den += e; r += cv[v].x * e; g += cv[v].y * e; bl += cv[v].z * e;
-          }
-        }
-        sRGB[ray * 512 + tid * 4] = r / den; sRGB[ray * 512 + tid * 4 + 1] = g / den; sRGB[ray * 512 + tid * 4 + 2] = bl / den;
       }
+      if (step == 0) R2_STAMP(26);
+      tc::tmem_st_wait();
+      if (step == 0) R2_STAMP(27);
+      tc::fence_before_sync();
       cta_sync();
+      if (step == 0) R2_STAMP(21);
+      if (warp == 0) {
+        tc::fence_after_sync();
+        if (tc::elect_one()) {
+          const uint32_t idesc = tc::idesc_bf16(128, 16);
+          const uint32_t wb = tc::smem_u32(sW2b), b_hi32 = tc::desc_hi(32u * 16u);
+          for (int tl = 0; tl < 4 && t0 + tl < bl_tiles; ++tl) {
+            const uint32_t base = tmem + BL_TM + tl * BL_TILE;
+#pragma unroll
+            for (int pass = 0; pass < 3; ++pass) {                  // lo*hi, hi*lo, hi*hi
+              const uint32_t a = base + (pass == 0 ? 16u : 0u);
+              const uint32_t bp = wb + (pass == 1 ? 1024u : 0u);
+#pragma unroll
+              for (int ks = 0; ks < 2; ++ks)
+                tc::mma_bf16_ts_w(base + 32u, a + (uint32_t)ks * 8u, tc::desc_lo(bp + (uint32_t)ks * 256u, 128u), b_hi32, idesc, pass > 0 || ks > 0);
+            }
+          }
+          tc::mma_commit(&sy.bl2);
+        }
+        __syncwarp();
+      }
+      tc::mbar_wait(&sy.bl2, bl_par);
+      bl_par ^= 1u;
+      tc::fence_after_sync();
+      if (step == 0) R2_STAMP(22);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int tl = 2 * u + c.half, t = t0 + tl, i = t * 128 + c.m;
+        if (t < bl_tiles) {   // warp-uniform
+          float d[16];
+          tc::tmem_ld16(c.trow + tmem + BL_TM + tl * BL_TILE + 32, d);
+          float logit = sW2[32];
+#pragma unroll
+          for (int o = 0; o < 16; ++o) logit = fmaf(sW2[16 + o], leaky(d[o] + sW2[o]), logit);
+          if (i < bl_items) sLogit[i] = vis_cur[u] == 0.f ? -1e9f : logit;
+        }
+      }
+      tc::fence_before_sync();   // the accumulator columns are rewritten by the next batch
+      if (last_of_ray) {
+        cta_sync();
+        if (ray == 0) R2_STAMP(23);
+        if (tid < S) {
+          // softmax over the views and the blended colour
+          float mx = -FLT_MAX;
+          for (int v = 0; v < V; ++v) mx = fmaxf(mx, sLogit[tid * V + v]);
+          float den = 0.f, r = 0.f, g = 0.f, bl = 0.f;
+#pragma unroll
+          for (int v = 0; v < 16; ++v) {
+            if (v < V) {
+              const float e = expf(sLogit[tid * V + v] - mx);
+              den += e; r += cv[v].x * e; g += cv[v].y * e; bl += cv[v].z * e;
+            }
+          }
+          sRGB[ray * 512 + tid * 4] = r / den; sRGB[ray * 512 + tid * 4 + 1] = g / den; sRGB[ray * 512 + tid * 4 + 2] = bl / den;
+        }
+        if (ray == 0) R2_STAMP(24);
+        cta_sync();   // sLogit / sBl are rewritten for the next ray
+      }
     }
     R2_STAMP(3);
 
@@ -746,8 +775,8 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
         float g[16], be[16], sw[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          const float4 g4 = __ldg(reinterpret_cast<const float4*>(U.g + srow * 128 + c0 + cc + j));
-          const float4 b4 = __ldg(reinterpret_cast<const float4*>(U.be + srow * 128 + c0 + cc + j));
+          const float4 g4 = __ldg(reinterpret_cast<const float4*>(U.g2 + ln_off(srow, c0 + cc + j, 128)));
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(U.be2 + ln_off(srow, c0 + cc + j, 128)));
           const float4 s4 = __ldg(reinterpret_cast<const float4*>(w.sig_w + c0 + cc + j));
           g[j] = g4.x; g[j + 1] = g4.y; g[j + 2] = g4.z; g[j + 3] = g4.w;
           be[j] = b4.x; be[j + 1] = b4.y; be[j + 2] = b4.z; be[j + 3] = b4.w;

@@ -145,11 +145,10 @@ ray_long_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_
     cta_sync();
     for (int i = tid; i < S * V; i += NT) {
       const int s = i / V;
-      const float4* pp = reinterpret_cast<const float4*>(partial + (s0 * V + i) * 32);
       float h1[32];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const float4 a = __ldg(pp + q);
+        const float4 a = __ldg(reinterpret_cast<const float4*>(partial + partial_off(s0 * V + i, q)));
         const float4 b = *reinterpret_cast<const float4*>(sBl + s * 36 + q * 4);
         h1[q * 4 + 0] = leaky(a.x + b.x); h1[q * 4 + 1] = leaky(a.y + b.y);
         h1[q * 4 + 2] = leaky(a.z + b.z); h1[q * 4 + 3] = leaky(a.w + b.w);

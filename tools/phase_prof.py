@@ -40,3 +40,5 @@ rv = v[32:]
 for i in range(len(rn)):
     print(f"ray {rn[i]:34s} {rv[i+1]-rv[i]:8d} clk")
 print("ray total (per pair of rays)", rv[len(rn)] - rv[0])
+print("ray blend build detail: math+st", rv[25]-rv[20], "fetch issue", rv[26]-rv[25], "st wait", rv[27]-rv[26], "sync", rv[21]-rv[27])
+print("ray blend detail (ray 0): sBl", rv[20]-rv[2], "batch0 build A", rv[21]-rv[20], "batch0 MMA wait", rv[22]-rv[21], "rest of batches", rv[23]-rv[22], "softmax", rv[24]-rv[23])

@@ -6,4 +6,4 @@ l=sys.stdin.readline()
 try:
     d=json.loads(l); print('bench', d['value'], d['kernels_ms_per_step'])
 except Exception as e: print('FAILED', l[:200])"; tail -2 gpurun_out/${T}_b1.err
-timeout 200 python tools/phase_prof.py 2>&1 | grep "^ray"
+timeout 200 python tools/phase_prof.py > gpurun_out/${T}_phase.log 2>&1; grep -E "^ray" gpurun_out/${T}_phase.log
