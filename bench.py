@@ -27,6 +27,8 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"          # no "NCCL version ..." banner on stdout: rank 0 prints JSON lines only
 
 CONFIGS = {
     # name: (H, W, V, S, workload)

@@ -470,11 +470,13 @@ class ConditionalNeRF(nn.Module):
         dbg_fa = torch.empty(R * S, 128, device=dev) if _debug else None
         dbg_sig = torch.empty(R * S, device=dev) if _debug else None
         # equal chunks (a multiple of the SM count) instead of full chunks plus a small remainder
-        n_chunks = max(1, -(-R // self.chunk_rays))
-        chunk = min(self.chunk_rays, max(1, -(-(-(-R // n_chunks)) // 148) * 148))
+        cap = max(1, self.chunk_rays * 128 // max(S, 128))       # the scratch of a chunk scales with rays x samples
+        n_chunks = max(1, -(-R // cap))
+        chunk = min(cap, max(1, -(-(-(-R // n_chunks)) // 148) * 148))
         nb = L.nlb_render_scratch_bytes(chunk, S, maps.V)
-        key = ("scratch", nb)
-        if key not in self._frame:
+        key = "scratch"
+        if key not in self._frame or self._frame[key].numel() < nb:
+            self._frame.pop(key, None)                            # one scratch buffer per model: release before growing
             self._frame[key] = torch.empty(nb, dtype=torch.uint8, device=dev)
         white = 1 if data.get('white_bkgd', self.args.render.white_bkgd) else 0
         if _feat_peers is not None:
