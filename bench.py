@@ -610,10 +610,16 @@ def run_b200(args):
                                         "sample": f"{args.cpu_rays} evenly spaced rays of the frame x {S} samples in chunks of 2048 rays "
                                                   f"(oracle/ render_rays, exact KNN on all host threads)",
                                         "faithful_knn": faithful_knn_probe(r.sc, sup, r.ro_all, r.rd_all, S)}
-                # parity of the benchmarked frame on that sample (checker only).  Both paths get the SAME per-frame inputs:
-                # the support points are injected from the CPU setup, because a 1-ulp difference between a GPU and a CPU
-                # back-projection flips near-tied nearest neighbours (the reference itself is discontinuous there).
-                r.model.support_neural_points = {"fine": {k: v.to(dev) for k, v in sup.items()}, "coarse": None}
+                # parity of the benchmarked frame on that sample (checker only).  The device frame setup is the model's own:
+                # its back-projection reproduces the host operators bit for bit (nlb_backproject_points), so the KNN sees
+                # the same support points as the CPU path.  (A cuBLAS back-projection differs by an ulp in places and flips
+                # near-tied neighbours - the reference itself is discontinuous there; if the clouds ever differ, the CPU
+                # ones are injected and the line says so.)
+                own = r.model.support_neural_points["fine"]
+                same = all(torch.equal(own[k].cpu(), sup[k]) for k in ("xyz", "feature", "direction"))
+                line["support_points_bit_identical"] = bool(same)
+                if not same:
+                    r.model.support_neural_points = {"fine": {k: v.to(dev) for k, v in sup.items()}, "coarse": None}
                 out = r.step_device()
                 line["parity_on_sample"] = {k: float((out[k][idx.to(dev)].cpu() - ref[k]).abs().max() / ref[k].abs().max())
                                             for k in ("rgb", "depth", "feat", "weights")}

@@ -100,6 +100,15 @@ int nlb_descriptor_head(const float* packed_weights, int S, int level, const flo
 int nlb_confidence_head(const float* packed_weights, int S, const float* aggregated, int64_t N, float* conf,
                         float* scratch, void* stream);
 
+/* Back-projection of one reference view's depth pixels (model.py:203-265, the matmul / get_rays arithmetic at :236-247 and
+ * conditional_nerf/utils.py:56-70) with the rounding of the reference's HOST operators (ascending fma chains of MKL sgemm on a
+ * reduction of 3 / 4, single roundings elsewhere), so that xyz / xyz_ndc / direction are bit-identical with the reference run
+ * on the CPU.  mats_host: 37 floats in HOST memory computed with the reference's own host ops - inverse(K)[9], c2w[:3,:3][9],
+ * c2w[:3,3][3], rows 0..2 of inverse(c2w_ref) @ c2w [12], fx, fy, cx, cy of the stride-scaled K.  uu, vv [M] int64 pixel
+ * coordinates (torch.nonzero order), zz [M] depths.  Outputs: world [M,3], ref [M,3], dir [M,4] = (unit ray direction, depth). */
+int nlb_backproject_points(const float* mats_host, const int64_t* uu, const int64_t* vv, const float* zz, int64_t M, float* world,
+                           float* ref, float* dir, void* stream);
+
 /* ---- ConditionalNeRF.render_rays (conditional_nerf/model.py:472-600) ---------------------------------------------------
  * rays_o, rays_d [R,3] (unit directions, as conditional_nerf/utils.py:56-70 produces them); z_vals [S] with z_stride = 0
  * (sample_depths, model.py:451-458, shared by all rays) or [R,S] with z_stride = S (per-ray depths from

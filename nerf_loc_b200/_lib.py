@@ -43,6 +43,7 @@ SIGNATURES = {
                                      c_void_p, c_void_p]),
     "nlb_descriptor_head": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "nlb_confidence_head": (c_int, [c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "nlb_backproject_points": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "nlb_render_scratch_bytes": (c_size_t, [c_int64, c_int, c_int]),
     "nlb_render_rays": (c_int, [ctypes.POINTER(NlbScene), c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64,
                                 c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

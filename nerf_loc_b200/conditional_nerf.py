@@ -309,7 +309,45 @@ class ConditionalNeRF(nn.Module):
 
     def backproject_support_frame(self, imgs, feats, depths, Ks, c2ws, stride=1):
         """model.py:203-265: depth pixels of every reference view -> (feature [M,3+C], xyz_world, xyz_ref, direction [M,4]).
-        Point order (view-major, then row-major nonzero order) defines the KNN indices."""
+        Point order (view-major, then row-major nonzero order) defines the KNN indices.
+
+        On the device the per-point arithmetic runs in `nlb_backproject_points`, which reproduces the rounding of the
+        reference's host operators: xyz / xyz_ndc / direction are bit-identical with the reference run on the CPU (a
+        cuBLAS product differs by an ulp in places, which flips near-tied nearest neighbours).  The 3x3 / 4x4 matrices
+        come from the reference's own host ops."""
+        if not imgs.is_cuda:
+            return self._backproject_support_frame_host(imgs, feats, depths, Ks, c2ws, stride)
+        L = _lib.load()
+        Ks_h, c2ws_h = Ks.detach().float().cpu(), c2ws.detach().float().cpu()
+        w2c_ref = torch.inverse(c2ws_h[0])
+        outs = ([], [], [], [])
+        for v, (img, feat, depth) in enumerate(zip(imgs, feats, depths)):
+            H, W = int(img.shape[-2] / stride), int(img.shape[-1] / stride)
+            K = Ks_h[v].clone()
+            K[:2] /= stride
+            c2w = c2ws_h[v]
+            mats = torch.cat([torch.inverse(K).reshape(-1), c2w[:3, :3].reshape(-1), c2w[:3, 3],
+                              torch.matmul(w2c_ref, c2w)[:3].reshape(-1),
+                              torch.stack([K[0, 0], K[1, 1], K[0, 2], K[1, 2]])]).contiguous()
+            dm = F.interpolate(depth[None, None], size=(H, W)).squeeze()
+            im = F.interpolate(img[None], size=(H, W)).squeeze().permute(1, 2, 0)
+            vv, uu = torch.nonzero(dm > 0, as_tuple=True)
+            zz = dm[vv, uu].float().contiguous()
+            M = zz.shape[0]
+            world = torch.empty(M, 3, device=zz.device)
+            ref = torch.empty(M, 3, device=zz.device)
+            direction = torch.empty(M, 4, device=zz.device)
+            _lib.check(L.nlb_backproject_points(mats.data_ptr(), _lib.ptr(uu.contiguous()), _lib.ptr(vv.contiguous()),
+                                                _lib.ptr(zz), M, _lib.ptr(world), _lib.ptr(ref), _lib.ptr(direction),
+                                                _lib.stream()))
+            outs[0].append(torch.cat([im[vv, uu], feat[vv, uu]], 1))
+            outs[1].append(world)
+            outs[2].append(ref)
+            outs[3].append(direction)
+        return tuple(torch.cat(o) for o in outs)
+
+    def _backproject_support_frame_host(self, imgs, feats, depths, Ks, c2ws, stride=1):
+        """The same function on host tensors with the reference's own operators (what the device kernel is pinned to)."""
         outs = ([], [], [], [])
         w2c_ref = torch.inverse(c2ws[0])
         for img, feat, depth, K, c2w in zip(imgs, feats, depths, Ks, c2ws):

@@ -115,6 +115,8 @@ struct Carver {
 
 }  // namespace nlb
 
+namespace nlb { int launch_backproject(const float* mats_host, const long long* uu, const long long* vv, const float* zz, long long M,
+                                      float* world, float* ref, float* dir, cudaStream_t st); }
 namespace nlb { int launch_tc_test(const float* A, const float* W, int K, int mode, float* C, cudaStream_t st); }
 namespace nlb { int read_prof(long long* out, int n); int read_prof_ray2(long long* out, int n); int read_prof_nb2(long long* out, int n); }
 using namespace nlb;
@@ -223,6 +225,14 @@ int nlb_confidence_head(const float* packed_weights, int S, const float* aggrega
   const RenderW w = render_weights_view(packed_weights, S);
   if (launch_linear(aggregated, N, W_HID, W_HID, w.cf1, w.cf1_b, 64, 1, scratch, 64, (cudaStream_t)stream)) return 1;
   return launch_rowdot_sigmoid(scratch, N, 64, w.cf2, w.cf2_b, conf, (cudaStream_t)stream);
+}
+
+int nlb_backproject_points(const float* mats_host, const int64_t* uu, const int64_t* vv, const float* zz, int64_t M, float* world,
+                           float* ref, float* dir, void* stream) {
+  if (!mats_host) return set_error("nlb_backproject_points: NULL matrices");
+  if (M > 0 && (!uu || !vv || !zz || !world || !ref || !dir)) return set_error("nlb_backproject_points: NULL pointer");
+  if (M < 0) return set_error("nlb_backproject_points: negative point count");
+  return launch_backproject(mats_host, (const long long*)uu, (const long long*)vv, zz, M, world, ref, dir, (cudaStream_t)stream);
 }
 
 size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {

@@ -156,6 +156,25 @@ def test_render_rays_vs_golden(name):
     assert torch.equal(out["mask"].cpu(), g["mask"])
 
 
+@pytest.mark.parametrize("H,W,V,stride", [(64, 96, 3, 4), (64, 96, 3, 8), (480, 640, 8, 4)])
+def test_backprojection_bit_identical_with_host_ops(H, W, V, stride):
+    """model.py:203-265 on the device (nlb_backproject_points) against the reference's operators on the host: support
+    features, xyz, xyz_ndc and directions bit for bit - the KNN input must not depend on where the frame was set up."""
+    from nerf_loc_b200.conditional_nerf import ConditionalNeRF
+    from nerf_loc_b200.config import default_args
+    sc = syn.make_scene(H, W, V, seed=21)
+    m = ConditionalNeRF(default_args(16))
+    feats = sc["feat_fine_src"] if stride == 4 else sc["feat_coarse_src"]
+    with torch.no_grad():
+        host = O.backproject_support_frame(sc["topk_images"], feats, sc["topk_depths"], sc["topk_Ks"], sc["topk_poses"], stride)
+        dev = m.backproject_support_frame(sc["topk_images"].cuda(), feats.cuda(), sc["topk_depths"].cuda(),
+                                          sc["topk_Ks"].cuda(), sc["topk_poses"].cuda(), stride=stride)
+    assert host[1].shape[0] > 0
+    for name, a, b in zip(("feature", "xyz", "xyz_ndc", "direction"), host, dev):
+        assert a.shape == b.shape, name
+        assert torch.equal(a, b.cpu()), "%s: %d values differ" % (name, int((a != b.cpu()).sum()))
+
+
 def test_render_v8_s128_multi_chunk_vs_oracle():
     """The metric's shape (8 views: the fused view-weight path of the aggregator; 128 samples: a full 128-row tensor-core tile
     per ray) over several chunks of the internal chunk loop, with a ragged last chunk, against the oracle."""

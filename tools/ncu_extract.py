@@ -34,7 +34,10 @@ WANT = {
 
 
 def main(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    # a .csv is the raw page already exported on the GPU box (`ncu -i rep --page raw --csv`): reports with many launches
+    # are too large to bring back
+    raw = open(path).read() if path.endswith(".csv") else subprocess.run(
+        ["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     out = {}

@@ -21,14 +21,17 @@ def to_bytes(v, unit):
 
 
 def main(path, rays, tag):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    # a .csv is the raw page already exported on the GPU box (`ncu -i rep --page raw --csv`): reports with many launches
+    # are too large to bring back
+    raw = open(path).read() if path.endswith(".csv") else subprocess.run(
+        ["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
     out, detail = {}, {}
     for r in rows[2:]:
         for pat, name in NAMES:
-            if pat in r[ik] and name not in out:
+            if pat in r[ik]:                              # the last launch of a kernel wins (steady state, not setup)
                 rd, wr = to_bytes(r[ir], units[ir]), to_bytes(r[iw], units[iw])
                 out[name] = (rd + wr) / rays
                 detail[name] = {"dram_read_bytes": rd, "dram_write_bytes": wr}
