@@ -43,6 +43,7 @@ __device__ __forceinline__ void fast_sincos2(float x, float& s, float& c) {
 constexpr int NS = 10;                       // weight stages: a layer's tiles stay until both sub-tiles used them, 6 more run ahead
 constexpr uint32_t STG_BYTES = 16384;        // one [128 x 32] hi | lo tile
 constexpr int TP = 16;                       // samples per sub-tile
+constexpr int NTC = 512;                     // compute threads: one group of 8 warps per sub-tile
 constexpr int LDQ = 132;
 // tensor-memory map of sub-tile u (columns): accumulator | A hi | A lo (two bf16 per column)
 constexpr uint32_t TM_SUB = 256, TM_D = 0, TM_AHI = 128, TM_ALO = 192;
@@ -68,7 +69,9 @@ static_assert(sizeof(Sync) <= 256, "nb2::Sync");
 constexpr int N_LAYERS = 5;                  // base_mlp 0, 2, 4; key projection; value projection
 __device__ __forceinline__ int layer_tiles(int l) { return l == 0 ? 3 : 4; }
 
-__global__ void __launch_bounds__(NT + 128, 1)
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory"); }
+
+__global__ void __launch_bounds__(NTC + 128, 1)
 neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int K,
                  const int* __restrict__ knn_idx, const float* __restrict__ knn_d2, const float* __restrict__ q_in,
                  float* __restrict__ o_out, float* __restrict__ wsum_out, float* __restrict__ weights_out) {
@@ -82,11 +85,11 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   Sync& sy = *reinterpret_cast<Sync*>(smraw + SYNC_OFF);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (warp == 8) {
+  if (warp == NTC / 32) {
     tc::tmem_alloc(&sy.tmem_slot, 512);
     if (lane == 0) {
       for (int i = 0; i < NS; ++i) { tc::mbar_init(&sy.full[i], 1); tc::mbar_init(&sy.empty[i], 1); }
-      for (int u = 0; u < 2; ++u) { tc::mbar_init(&sy.a_ready[u], NT); tc::mbar_init(&sy.d_ready[u], 1); }
+      for (int u = 0; u < 2; ++u) { tc::mbar_init(&sy.a_ready[u], NTC / 2); tc::mbar_init(&sy.d_ready[u], 1); }
     }
   }
   tc::fence_before_sync();
@@ -96,10 +99,10 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   const int64_t nst = (N + 2 * TP - 1) / (2 * TP);                              // super-tiles
   const int nmy = (int)((nst - blockIdx.x + gridDim.x - 1) / gridDim.x);        // of this CTA (grid <= nst)
 
-  if (warp >= 8) {
-   // service warpgroup (warps 10, 11 are only there so that the register hand-over is warpgroup-aligned)
+  if (warp >= NTC / 32) {
+   // service warpgroup (its last two warps are only there so that the register hand-over is warpgroup-aligned)
    tc::reg_dec<56>();
-   if (warp == 9) {
+   if (warp == NTC / 32 + 1) {
     // ------------------------------------------------ weight producer: 19 tiles of 16 KB per super-tile ------------------------
     uint32_t empty_par = 0;
     int i = 0;
@@ -122,7 +125,7 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         }
       }
     }
-   } else if (warp == 8) {
+   } else if (warp == NTC / 32) {
     // ------------------------------------------------ MMA issuer: bf16x3, A from tensor memory --------------------------------
     // layer l of sub-tile 0 on the layer's tiles (kept in the ring), then the same tiles for sub-tile 1 (released one by one)
     uint32_t full_par = 0, a_par = 0;
@@ -169,22 +172,25 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
    }
   } else {
     // ------------------------------------------------ compute warps ------------------------------------------------------
-    tc::reg_inc<224>();
+    // Two groups of 8 warps, group u owns sub-tile u from its geometry to its context: the epilogues of the two sub-tiles run
+    // side by side (four warps per scheduler instead of two) while the issuer alternates between their accumulators.
+    tc::reg_inc<104>();
     const float range = sc.far_ - sc.near_;
-    const int row = (warp & 3) * 32 + lane;            // TMEM lane == (sample, neighbour) row of a sub-tile
-    const int half = warp >> 2;                         // column half owned in the epilogues
+    const int u = warp >> 3, gtid = tid & 255;
+    const int row = (warp & 3) * 32 + lane;            // TMEM lane == (sample, neighbour) row of the sub-tile
+    const int half = (warp >> 2) & 1;                   // column half owned in the epilogues
     const int p = row >> 3, k = row & 7;
-    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)u * TM_SUB;
     uint32_t d_par = 0;
-    for (int i = tid; i < 64 + 16 + 432 + 27; i += NT)
+    for (int i = tid; i < 64 + 16 + 432 + 27; i += NTC)
       sW[i] = i < 64 ? __ldg(w.rd1 + i) : (i < 80 ? __ldg(w.rd1_b + i - 64) : (i < 512 ? __ldg(w.rd2 + i - 80) : __ldg(w.rd2_b + i - 512)));
-    cta_sync();
-    auto wait_d = [&](int u) {
-      tc::mbar_wait(&sy.d_ready[u], (d_par >> u) & 1u);
-      d_par ^= 1u << u;
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+    auto wait_d = [&]() {
+      tc::mbar_wait(&sy.d_ready[u], d_par);
+      d_par ^= 1u;
       tc::fence_after_sync();
     };
-    auto a_ready = [&](int u) { tc::fence_before_sync(); tc::mbar_arrive(&sy.a_ready[u]); };
+    auto a_ready = [&]() { tc::fence_before_sync(); tc::mbar_arrive(&sy.a_ready[u]); };
 
     // The (sample, neighbour) records of the NEXT super-tile are staged in shared memory by the half-0 threads in two steps, so
     // that neither the index -> geometry dependency nor the records themselves cost registers or stalls in the phases between:
@@ -220,7 +226,7 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
       return q;
     };
-    auto stage_rows = [&](const int u, const RowPre& q, const int64_t n0t) {
+    auto stage_rows = [&](const RowPre& q, const int64_t n0t) {
       float* rr = sRow + (u * 128 + row) * ROW_LD;
       *reinterpret_cast<float4*>(rr + 8) = make_float4(q.x, q.y, q.z, q.dx);
       *reinterpret_cast<float4*>(rr + 12) = make_float4(q.dy, q.dz, 1.f, __int_as_float(q.id));
@@ -237,17 +243,16 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
 
     // ---- P0: per (sample, neighbour) geometry -> A operand of layer 1 (PE 63 | ray_diff_fc 27 | 0 x 6, permuted) in tensor memory.
     // Two threads per row, each with half of the work: positional-encoding octaves 0-4 / 5-9 and ray_diff_fc outputs 0-13 / 14-26
-    // (K order: pack.cu::tcb_src_index); 48 values = 24 packed columns per plane and thread.
-    auto phase0 = [&](const int u) {
+    // (K order: pack.cu::tcb_src_index); 48 values = 24 packed columns per plane and thread, written 16 values at a time.
+    auto phase0 = [&]() {
       const float* rrow = sRow + (u * 128 + row) * ROW_LD;
       const float4 g0 = *reinterpret_cast<const float4*>(rrow), g1 = *reinterpret_cast<const float4*>(rrow + 4);
       const float4 r2 = *reinterpret_cast<const float4*>(rrow + 8), r3 = *reinterpret_cast<const float4*>(rrow + 12);
       const int rid = __float_as_int(r3.w);
       const bool live = rid >= 0;
-      struct { float x, y, z, dx, dy, dz; } rr = {r2.x, r2.y, r2.z, r2.w, r3.x, r3.y};
       float vals[48];
-      const float off[3] = {live ? __fdiv_rn(__fsub_rn(rr.x, g0.x), range) : 0.f, live ? __fdiv_rn(__fsub_rn(rr.y, g0.y), range) : 0.f,
-                            live ? __fdiv_rn(__fsub_rn(rr.z, g0.z), range) : 0.f};
+      const float off[3] = {live ? __fdiv_rn(__fsub_rn(r2.x, g0.x), range) : 0.f, live ? __fdiv_rn(__fsub_rn(r2.y, g0.y), range) : 0.f,
+                            live ? __fdiv_rn(__fsub_rn(r2.z, g0.z), range) : 0.f};
       if (half == 0) {
         sD[u * 256 + row] = live ? r3.z : 1.f;
         sD[u * 256 + 128 + row] = live ? g1.z : 0.f;   // confidence
@@ -259,7 +264,7 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
       // octaves 5 * half + {0, 2, 4} by range-reduced sincos, {1, 3} from their predecessors by the double-angle identities
       // (absolute error doubles: 4e-7 -> 8e-7, two orders below what the 1e-4 parity bar needs)
-      float f = half ? 32.f : 1.f;
+      const float f = half ? 32.f : 1.f;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         float sn[5], co[5];
@@ -282,9 +287,9 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       {
         // ray difference (model.py:396-399) and ray_diff_fc (4 -> 16 -> 27, LeakyReLU)
         const float nx = g0.w, ny = g1.x, nz = g1.y;
-        const float rx = rr.dx - nx, ry = rr.dy - ny, rz = rr.dz - nz;
+        const float rx = r2.w - nx, ry = r3.x - ny, rz = r3.y - nz;
         const float rn = sqrtf(rx * rx + ry * ry + rz * rz) + 1e-8f;
-        const float rd[4] = {rx / rn, ry / rn, rz / rn, rr.dx * nx + rr.dy * ny + rr.dz * nz};
+        const float rd[4] = {rx / rn, ry / rn, rz / rn, r2.w * nx + r3.x * ny + r3.y * nz};
         float h1[16];
 #pragma unroll
         for (int o = 0; o < 16; ++o) {
@@ -311,70 +316,65 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) tc::split_bf16x2(vals[c8 * 16 + 2 * j], vals[c8 * 16 + 2 * j + 1], hi[j], lo[j]);
-        tc::tmem_st8_u(trow + u * TM_SUB + TM_AHI + (uint32_t)(half * 24 + c8 * 8), hi);
-        tc::tmem_st8_u(trow + u * TM_SUB + TM_ALO + (uint32_t)(half * 24 + c8 * 8), lo);
+        tc::tmem_st8_u(trow + TM_AHI + (uint32_t)(half * 24 + c8 * 8), hi);
+        tc::tmem_st8_u(trow + TM_ALO + (uint32_t)(half * 24 + c8 * 8), lo);
       }
       tc::tmem_st_wait();
     };
 
     // ---- epilogue of a base_mlp layer: accumulator (+ per-frame support part or bias) -> LeakyReLU -> A operand of the next layer
-    // MODE 0: layer 1 (adds the gathered sup_pre row), 1: layer 2 (bias b2), 2: layer 3 (bias b3)
-    auto mlp_epilogue = [&](const int u, const int mode) {
+    // MODE 0: layer 1 (adds the gathered sup_pre row), 1: layer 2 (bias b2), 2: layer 3 (bias b3).  16 columns at a time; the
+    // addend of the first 32 columns is requested before the accumulator is waited for (layer 1: an L2 round trip underneath the
+    // MMA), each quarter's registers are refilled with the addend 32 columns further as soon as they are consumed.
+    auto mlp_epilogue = [&](const int mode) {
       const int c0 = half * 64;
       const int id = sIdx[u * 128 + row];
       const float* add = mode == 0 ? (id >= 0 ? sc.sup_pre + (size_t)id * W_HID : nullptr) : (mode == 1 ? w.b2 : w.b3);
-      // the whole 64-column addend of the row (layer 1: the gathered per-frame support part) is requested before the accumulator
-      // is waited for: one L2 round trip per sub-tile, underneath the MMA
-      float4 a4[8], b4n[8];
+      float4 a4[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) a4[j] = add ? __ldg(reinterpret_cast<const float4*>(add + c0 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      wait_d(u);
+      wait_d();
 #pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        float v[32];
-        tc::tmem_ld32(trow + u * TM_SUB + TM_D + (uint32_t)(c0 + cc), v);
-        if (cc == 0) {   // second half of the row: requested before the first half is consumed
+      for (int cc = 0; cc < 64; cc += 16) {
+        float v[16];
+        tc::tmem_ld16(trow + TM_D + (uint32_t)(c0 + cc), v);
+        uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) b4n[j] = add ? __ldg(reinterpret_cast<const float4*>(add + c0 + 32 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 b4 = a4[j];
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = a4[(cc & 16) / 4 + j];
           tc::split_bf16x2(leaky(v[4 * j] + b4.x), leaky(v[4 * j + 1] + b4.y), hi[2 * j], lo[2 * j]);
           tc::split_bf16x2(leaky(v[4 * j + 2] + b4.z), leaky(v[4 * j + 3] + b4.w), hi[2 * j + 1], lo[2 * j + 1]);
         }
-        if (cc == 0) {
+        if (cc < 32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) a4[j] = b4n[j];
+          for (int j = 0; j < 4; ++j)
+            a4[(cc & 16) / 4 + j] = add ? __ldg(reinterpret_cast<const float4*>(add + c0 + cc + 32 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        tc::tmem_st16_u(trow + u * TM_SUB + TM_AHI + (uint32_t)((c0 + cc) / 2), hi);
-        tc::tmem_st16_u(trow + u * TM_SUB + TM_ALO + (uint32_t)((c0 + cc) / 2), lo);
+        tc::tmem_st8_u(trow + TM_AHI + (uint32_t)((c0 + cc) / 2), hi);
+        tc::tmem_st8_u(trow + TM_ALO + (uint32_t)((c0 + cc) / 2), lo);
       }
       tc::tmem_st_wait();
     };
 
-    float prob[2][2];   // [sub-tile][head of this thread's column half]
+    float prob[2];   // per head of this thread's column half
     // ---- scores q_h . k_h / sqrt(d_k), softmax over the K neighbours (8 consecutive lanes) --------------------------------------
-    auto scores = [&](const int u) {
+    auto scores = [&]() {
       const float* qrow = sQ + (u * TP + p) * LDQ + half * 64;
-      float sdot[2] = {0.f, 0.f};
-#pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        float v[32];
-        tc::tmem_ld32(trow + u * TM_SUB + TM_D + (uint32_t)(half * 64 + cc), v);
-        float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const float4 q4 = *reinterpret_cast<const float4*>(qrow + cc + j);
-          fma2_v(a0, a1, q4.x, q4.y, v[j], v[j + 1]);
-          fma2_v(a0, a1, q4.z, q4.w, v[j + 2], v[j + 3]);
-        }
-        sdot[cc >> 5] = a0 + a1;
-      }
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        float a = k < K ? sdot[h] * 0.17677669529663687f : -FLT_MAX;   // 1 / sqrt(d_k = 32)
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 32; cc += 16) {
+          float v[16];
+          tc::tmem_ld16(trow + TM_D + (uint32_t)(half * 64 + h * 32 + cc), v);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 q4 = *reinterpret_cast<const float4*>(qrow + h * 32 + cc + j);
+            fma2_v(a0, a1, q4.x, q4.y, v[j], v[j + 1]);
+            fma2_v(a0, a1, q4.z, q4.w, v[j + 2], v[j + 3]);
+          }
+        }
+        const float a = k < K ? (a0 + a1) * 0.17677669529663687f : -FLT_MAX;   // 1 / sqrt(d_k = 32)
         float m = a;
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
@@ -384,38 +384,34 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 1);
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 2);
         ssum += __shfl_xor_sync(0xffffffffu, ssum, 4);
-        prob[u][h] = e / ssum;
+        prob[h] = e / ssum;
       }
     };
 
-    // ---- context o = sum_k a_hk v_k (reduce-scatter over the 8 lanes of a sample), neighbour weights ----------------------------
-    auto context = [&](const int u, const int64_t n0t) {
-      float v[64];
-#pragma unroll
-      for (int cc = 0; cc < 64; cc += 32) {
-        float t[32];
-        tc::tmem_ld32(trow + u * TM_SUB + TM_D + (uint32_t)(half * 64 + cc), t);
-        const float a = prob[u][cc >> 5];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[cc + j] = t[j] * a;
-      }
-      // of its 2 w values a lane keeps [0, w) if bit (w / 8) of k is clear, [w, 2 w) otherwise, and adds what the partner lane
-      // (which keeps the other half) sends for the same positions: lane k ends with columns 8 k .. 8 k + 7
-#pragma unroll
-      for (int w2 = 32; w2 >= 8; w2 >>= 1) {
-        const bool up = (k & (w2 >> 3)) != 0;
-#pragma unroll
-        for (int j = 0; j < w2; ++j) {
-          const float send = up ? v[j] : v[j + w2];
-          const float keep = up ? v[j + w2] : v[j];
-          v[j] = keep + __shfl_xor_sync(0xffffffffu, send, w2 >> 3);
-        }
-      }
+    // ---- context o = sum_k a_hk v_k, one head (32 columns) at a time: reduce-scatter over the 8 lanes of a sample, lane k ends
+    // with columns 4 k .. 4 k + 3 of the head; neighbour weights ---------------------------------------------------------------------
+    auto context = [&](const int64_t n0t) {
       const int64_t n = n0t + p;
-      if (n < N) {
-        float4* dst = reinterpret_cast<float4*>(o_out + n * W_HID + half * 64 + k * 8);
-        __stcs(dst, make_float4(v[0], v[1], v[2], v[3]));
-        __stcs(dst + 1, make_float4(v[4], v[5], v[6], v[7]));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[32];
+        tc::tmem_ld32(trow + TM_D + (uint32_t)(half * 64 + h * 32), v);
+        const float a = prob[h];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] *= a;
+        // of its 2 w values a lane keeps [0, w) if bit (w / 4) of k is clear, [w, 2 w) otherwise, and adds what the partner lane
+        // (which keeps the other half) sends for the same positions
+#pragma unroll
+        for (int w2 = 16; w2 >= 4; w2 >>= 1) {
+          const bool up = (k & (w2 >> 2)) != 0;
+#pragma unroll
+          for (int j = 0; j < w2; ++j) {
+            const float send = up ? v[j] : v[j + w2];
+            const float keep = up ? v[j + w2] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, w2 >> 2);
+          }
+        }
+        if (n < N) __stcs(reinterpret_cast<float4*>(o_out + n * W_HID + half * 64 + h * 32 + k * 4), make_float4(v[0], v[1], v[2], v[3]));
       }
       if (half == 0) {
         // weights = (1/clamp(dist)) * softmax_K(corr) * conf, normalised (model.py:415-426); the rows of `feature` are identical
@@ -442,71 +438,57 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       }
     };
 
-    if (half == 0) {
-      const int64_t n00 = (int64_t)blockIdx.x * 2 * TP;
-      const RowPre a = fetch_ids(n00), b = fetch_ids(n00 + TP);
-      stage_rows(0, a, n00);
-      stage_rows(1, b, n00 + TP);
-    }
+    if (half == 0) stage_rows(fetch_ids((int64_t)blockIdx.x * 2 * TP + u * TP), (int64_t)blockIdx.x * 2 * TP + u * TP);
     cp_async_commit();
     cp_async_wait<0>();
-    cta_sync();
+    group_sync(u);
     for (int it = 0; it < nmy; ++it) {
       const bool stamp = it == 1 && blockIdx.x == gridDim.x / 2 && tid == 0;
-      const int64_t n0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 2 * TP;
+      const int64_t n0 = ((int64_t)blockIdx.x + (int64_t)it * gridDim.x) * 2 * TP + u * TP;   // first sample of this group's sub-tile
       NB2_STAMP(0);
-      // q rows of the 32 samples (written by qproj_kernel): asynchronous copy, consumed by the score phase
-      for (int i = tid; i < 2 * TP * 32; i += NT) {
+      // q rows of the group's 16 samples (written by fc_tail / qproj): asynchronous copy, consumed by the score phase
+      for (int i = gtid; i < TP * 32; i += 256) {
         const int pp = i >> 5, c4 = i & 31;
-        if (n0 + pp < N) cp_async16(sQ + pp * LDQ + c4 * 4, q_in + (n0 + pp) * W_HID + c4 * 4);
-        else *reinterpret_cast<float4*>(sQ + pp * LDQ + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n0 + pp < N) cp_async16(sQ + (u * TP + pp) * LDQ + c4 * 4, q_in + (n0 + pp) * W_HID + c4 * 4);
+        else *reinterpret_cast<float4*>(sQ + (u * TP + pp) * LDQ + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       cp_async_commit();
-      phase0(0);
-      a_ready(0);
-      phase0(1);
-      a_ready(1);
+      phase0();
+      a_ready();
       NB2_STAMP(1);
-      cta_sync();   // sIdx / sD of this super-tile visible; sRow consumed
+      group_sync(u);   // sIdx / sD of this sub-tile visible; sRow consumed
       const bool more = it + 1 < nmy;
-      const int64_t n0n = ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * 2 * TP;
-      RowPre pre0, pre1;
-      if (more && half == 0) { pre0 = fetch_ids(n0n); pre1 = fetch_ids(n0n + TP); }
+      const int64_t n0n = ((int64_t)blockIdx.x + (int64_t)(it + 1) * gridDim.x) * 2 * TP + u * TP;
+      RowPre pre;
+      if (more && half == 0) pre = fetch_ids(n0n);
       NB2_STAMP(2);
 #pragma unroll 1
       for (int l = 0; l < 3; ++l) {
-        mlp_epilogue(0, l);   // (waits for the accumulator of sub-tile 0 itself)
-        a_ready(0);
-        mlp_epilogue(1, l);
-        a_ready(1);
+        mlp_epilogue(l);   // (waits for the accumulator itself)
+        a_ready();
         if (l == 0) {
-          if (more && half == 0) { stage_rows(0, pre0, n0n); stage_rows(1, pre1, n0n + TP); }
+          if (more && half == 0) stage_rows(pre, n0n);
           cp_async_commit();
         }
         NB2_STAMP(3 + l);
       }
       cp_async_wait<0>();
-      cta_sync();   // q rows landed
-      wait_d(0);
+      group_sync(u);   // q rows and the next records landed
+      wait_d();
       NB2_STAMP(6);
-      scores(0);
-      a_ready(0);   // the key accumulator of sub-tile 0 may be overwritten by its value projection
-      wait_d(1);
-      scores(1);
-      a_ready(1);
+      scores();
+      a_ready();   // the key accumulator may be overwritten by the value projection
       NB2_STAMP(7);
-      wait_d(0);
+      wait_d();
       NB2_STAMP(8);
-      context(0, n0);
-      wait_d(1);
-      context(1, n0 + TP);
+      context(n0);
       NB2_STAMP(9);
-      cta_sync();   // sIdx / sD / sQ are rewritten by the next super-tile
+      group_sync(u);   // sIdx / sD / sQ are rewritten by the next super-tile
     }
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == NTC / 32) {
     tc::fence_after_sync();
     tc::tmem_dealloc(tmem, 512);
   }
@@ -710,7 +692,7 @@ int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   }
   const int64_t nst = (N + 2 * nb2::TP - 1) / (2 * nb2::TP);
   const unsigned grid = (unsigned)(nst < sms ? nst : sms);   // persistent: one CTA per SM
-  nb2::neighbor2_kernel<<<grid, NT + 128, nb2::SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, q, o, wsum, weights);
+  nb2::neighbor2_kernel<<<grid, nb2::NTC + 128, nb2::SMEM_BYTES, st>>>(sc, w, ps, N, K, idx, d2, q, o, wsum, weights);
   if (check_launch("neighbor2_kernel")) return 1;
   prof_mark("neighbor2");
   nb2::row_gemm128_kernel<1><<<g128, NT, nb2::RG_SMEM, st>>>(o, w.tb_wfc, N, agg, w.ln_g, w.ln_b, wsum, fagg, feature, fagg_split,
