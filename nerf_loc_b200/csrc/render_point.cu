@@ -17,6 +17,7 @@
 //       projections are folded onto the query / context side and `feature` has one distinct row per sample.
 #include <float.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "nlb_common.cuh"
 #include "nlb_internal.h"
 #include "render_kernels.h"
@@ -77,8 +78,8 @@ __device__ __forceinline__ Taps make_taps(float ix, float iy, int w, int h, bool
 // row info slots
 // per map a bilinear footprint is stored ready to use: 4 pixel indices (y * width + x, clamped into the map; as int bits) and
 // 4 weights (0 for taps that do not contribute) - computed once per row in phase 1 instead of once per lane in every gather
-enum { RI_TF = 0, RI_TI = 8, RI_TV = 16, RI_DEPTH = 24, RI_VALID, RI_MASK, RI_VIS, RI_DD, RI_W,
-       RI_RD0, RI_RD1, RI_RD2, RI_RD3, RI_V, RI_P, RI_N = 36 };   // RI_V / RI_P: view and sample index of the row (int bits)
+enum { RI_TF = 0, RI_TI = 8, RI_TV = 16, RI_DEPTH = 24, RI_VALID, RI_MASK, RI_DD, RI_VIS /* 28: float4 VIS W RD0 RD1 */, RI_W,
+       RI_RD0, RI_RD1, RI_RD2 /* 32: RD2 RD3 */, RI_RD3, RI_V, RI_P, RI_N = 36 };   // RI_V / RI_P: view and sample index of the row (int bits)
 
 __device__ __forceinline__ void store_taps(float* slot, const Taps& t, int w, int h) {
   const int x0 = min(max(t.x0, 0), w - 1), x1 = min(max(t.x0 + 1, 0), w - 1);
@@ -180,6 +181,9 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   const float near_ = sc.near_, far_ = sc.far_;
 
   AGG_STAMP(0);
+  // visibility | depth difference of this thread's (sample, view) row: requested now, consumed after the projections
+  float2 vd_pre = make_float2(0.f, 0.f);
+  if (EXT && tid < rows) vd_pre = __ldcs(visdd_in + nidx(tid / V) * V + (tid - (tid / V) * V));   // written once by visibility_kernel
   // decoder weights (32 KB) go into the staging ring, which is idle until phase 7: dec1 as [32][128] (the four heads side by
   // side), dec2 as 4 x [32][32].  Both are read as mma.sync B fragments (thread (g, t) reads rows t / t + 4 resp. 2t / 2t + 1,
   // column g), so 8-column groups are XOR-swizzled with the row to keep those reads bank-conflict free without padding:
@@ -424,10 +428,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     const bool live = tid < rows;
     float vis = 0.f, dd = 0.f;
     if (EXT) {
-      if (live) {
-        const float2 vd = __ldcs(visdd_in + nidx(tid / V) * V + (tid - (tid / V) * V));   // written once by visibility_kernel
-        vis = vd.x; dd = vd.y;
-      }
+      if (live) { vis = vd_pre.x; dd = vd_pre.y; }
     } else {
       const float m0 = sO1[tid * 6], m1 = sO1[tid * 6 + 1], v0 = sO1[tid * 6 + 2], v1 = sO1[tid * 6 + 3];
       const float aw = sO1[tid * 6 + 4], vs = sO1[tid * 6 + 5];
@@ -521,110 +522,139 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       for (int i = 0; i < 5; ++i) wb[3 + i] = __ldg(w.bl1v + (195 + i) * 32 + lane);
       bias = __ldg(w.bl1_b + lane);
     }
-    for (int p = warp; p < np; p += NT / 32) {
-      float2 f[8][3];
-      float rgbv[8], wvv[8];
-#pragma unroll
-      for (int v0 = 0; v0 < 8; v0 += 2) {
-        float2 q[2][4][3];
-        float wt[2][4], bq[2][4];
-        float4 cq[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int v = v0 + u;
-          cq[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* fb0 = sc.feat + lane * 2;
+    const float* bb0 = sc.featb + lane;
+    const unsigned hw = (unsigned)(sc.h * sc.w);
+    // FULL (V == 8, the rendering configuration): no per-view guards, no zero-filled buffers
+    auto gather_sample = [&](const int p, auto full_c) {
+      constexpr bool FULL = decltype(full_c)::value;
+      // Software pipeline over the views, two register buffers: while view v is interpolated the loads of view v + 1 are in flight
+      // and those of view v + 2 are issued into the buffer v just left.  The statistics are accumulated in one pass about the first
+      // view's value K (d = x - K, exactly 0 for view 0): mean = K sw + sum w d, var = sum w (d - c)^2 = sum w d^2 - 2 c sum w d +
+      // c^2 sw with c = mean - K - so the views' channels need not stay in registers for a second pass.
+      const float* ri0 = sRI + p * V * RI_N;
+      float2 q[2][4][3];
+      float wt[2][4], bq[2][4];
+      float2 kk[3], sx[3], sxx[3];
+      float rk = 0.f, rsx = 0.f, rsxx = 0.f, sw = 0.f;   // the same for the lane's colour channel
+      // colour: lane (v, t) = (lane / 4, lane % 4) fetches tap t of view v, the taps are summed over the 4 lanes of a view
+      float4 crgb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (FULL || (lane >> 2) < V) {
+        const float* ri = ri0 + (lane >> 2) * RI_N;
+        const float wi = ri[RI_TI + 4 + (lane & 3)];
+        if (wi != 0.f) {
+          const int pix = __float_as_int(ri[RI_TI + (lane & 3)]);
+          const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc.images + ((size_t)(lane >> 2) * sc.H * sc.W + pix) * 4));
+          crgb = make_float4(c4.x * wi, c4.y * wi, c4.z * wi, 0.f);
+        }
+      }
+      auto issue = [&](const int b, const int v) {
+        if (!FULL) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
-            wt[u][t] = 0.f; bq[u][t] = 0.f;
+            wt[b][t] = 0.f; bq[b][t] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) q[u][t][j] = make_float2(0.f, 0.f);
-          }
-          if (v < V) {
-            const float* ri = sRI + (p * V + v) * RI_N;
-            const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TF);
-            const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TF + 4);
-            const float* fb = sc.feat + ((size_t)v * sc.h * sc.w) * C_FEAT + lane * 2;
-            const float* tp[4] = {fb + (size_t)ti.x * C_FEAT, fb + (size_t)ti.y * C_FEAT, fb + (size_t)ti.z * C_FEAT, fb + (size_t)ti.w * C_FEAT};
-            const float twv[4] = {tw.x, tw.y, tw.z, tw.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              wt[u][t] = twv[t];
-#pragma unroll
-              for (int j = 0; j < 3; ++j) q[u][t][j] = __ldg(reinterpret_cast<const float2*>(tp[t] + j * 64));
-            }
-            if (lane < 4) {
-              const float wi = ri[RI_TI + 4 + lane];
-              if (wi != 0.f) {
-                const int pix = __float_as_int(ri[RI_TI + lane]);
-                const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc.images + ((size_t)v * sc.H * sc.W + pix) * 4));
-                cq[u] = make_float4(c4.x * wi, c4.y * wi, c4.z * wi, 0.f);
-              }
-            }
-            if (with_blend) {
-              const float* bb = sc.featb + ((size_t)v * sc.h * sc.w) * 32 + lane;
-              bq[u][0] = __ldg(bb + (size_t)ti.x * 32);
-              bq[u][1] = __ldg(bb + (size_t)ti.y * 32);
-              bq[u][2] = __ldg(bb + (size_t)ti.z * 32);
-              bq[u][3] = __ldg(bb + (size_t)ti.w * 32);
-            }
+            for (int j = 0; j < 3; ++j) q[b][t][j] = make_float2(0.f, 0.f);
           }
         }
+        if (FULL || v < V) {
+          const float* ri = ri0 + v * RI_N;
+          const int4 ti = *reinterpret_cast<const int4*>(ri + RI_TF);
+          const float4 tw = *reinterpret_cast<const float4*>(ri + RI_TF + 4);
+          const unsigned vb = (unsigned)v * hw;
+          const unsigned pg[4] = {vb + (unsigned)ti.x, vb + (unsigned)ti.y, vb + (unsigned)ti.z, vb + (unsigned)ti.w};
+          const float twv[4] = {tw.x, tw.y, tw.z, tw.w};
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int v = v0 + u;
+          for (int t = 0; t < 4; ++t) {
+            wt[b][t] = twv[t];
+            const float* tp = fb0 + (size_t)pg[t] * C_FEAT;
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            float2 acc = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              acc.x = fmaf(q[u][t][j].x, wt[u][t], acc.x);
-              acc.y = fmaf(q[u][t][j].y, wt[u][t], acc.y);
-            }
-            f[v][j] = acc;
+            for (int j = 0; j < 3; ++j) q[b][t][j] = __ldg(reinterpret_cast<const float2*>(tp + j * 64));
           }
-          rgbv[v] = 0.f; wvv[v] = 0.f;
-          if (v < V) {   // warp-uniform
-            float4 c = cq[u];
-            c.x += __shfl_xor_sync(0xffffffffu, c.x, 1); c.y += __shfl_xor_sync(0xffffffffu, c.y, 1); c.z += __shfl_xor_sync(0xffffffffu, c.z, 1);
-            c.x += __shfl_xor_sync(0xffffffffu, c.x, 2); c.y += __shfl_xor_sync(0xffffffffu, c.y, 2); c.z += __shfl_xor_sync(0xffffffffu, c.z, 2);
-            c.x = __shfl_sync(0xffffffffu, c.x, 0); c.y = __shfl_sync(0xffffffffu, c.y, 0); c.z = __shfl_sync(0xffffffffu, c.z, 0);
-            const float* ri = sRI + (p * V + v) * RI_N;
-            rgbv[v] = lane == 0 ? c.x : (lane == 1 ? c.y : c.z);
-            wvv[v] = ri[RI_W];
-            if (lane == 0 && rgbvis_out) __stcs(reinterpret_cast<float4*>(rgbvis_out + (nidx(p) * V + v) * 4), make_float4(c.x, c.y, c.z, ri[RI_VIS]));
-            if (with_blend) {
-              float a = 0.f;
+          if (with_blend) {
 #pragma unroll
-              for (int t = 0; t < 4; ++t) a = fmaf(bq[u][t], wt[u][t], a);
-              a = fmaf(c.x, wb[0], a); a = fmaf(c.y, wb[1], a); a = fmaf(c.z, wb[2], a);
-              a = fmaf(ri[RI_VIS], wb[3], a);
-              a = fmaf(ri[RI_RD0], wb[4], a); a = fmaf(ri[RI_RD1], wb[5], a); a = fmaf(ri[RI_RD2], wb[6], a); a = fmaf(ri[RI_RD3], wb[7], a);
-              __stcs(partial_out + partial_off(nidx(p) * V + v, lane >> 2) + (lane & 3), a + bias);
-            }
-            if (mvf_out) {
-              float* mo = mvf_out + (nidx(p) * V + v) * C_RGBF;
-              if (lane < 3) mo[lane] = rgbv[v];
+            for (int t = 0; t < 4; ++t) bq[b][t] = __ldg(bb0 + (size_t)pg[t] * 32);
+          }
+        }
+      };
+      issue(0, 0);
+      issue(1, 1);
+      crgb.x += __shfl_xor_sync(0xffffffffu, crgb.x, 1); crgb.y += __shfl_xor_sync(0xffffffffu, crgb.y, 1); crgb.z += __shfl_xor_sync(0xffffffffu, crgb.z, 1);
+      crgb.x += __shfl_xor_sync(0xffffffffu, crgb.x, 2); crgb.y += __shfl_xor_sync(0xffffffffu, crgb.y, 2); crgb.z += __shfl_xor_sync(0xffffffffu, crgb.z, 2);
 #pragma unroll
-              for (int j = 0; j < 3; ++j) { mo[3 + j * 64 + lane * 2] = f[v][j].x; mo[3 + j * 64 + lane * 2 + 1] = f[v][j].y; }
-            }
+      for (int v = 0; v < 8; ++v) {
+        const int b = v & 1;
+        float2 f[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            acc.x = fmaf(q[b][t][j].x, wt[b][t], acc.x);
+            acc.y = fmaf(q[b][t][j].y, wt[b][t], acc.y);
+          }
+          f[j] = acc;
+        }
+        float bacc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) bacc = fmaf(bq[b][t], wt[b][t], bacc);
+        float rgbl = 0.f, wv = 0.f;
+        if (FULL || v < V) {   // warp-uniform
+          const float cx = __shfl_sync(0xffffffffu, crgb.x, 4 * v), cy = __shfl_sync(0xffffffffu, crgb.y, 4 * v),
+                      cz = __shfl_sync(0xffffffffu, crgb.z, 4 * v);
+          const float4 r0 = *reinterpret_cast<const float4*>(ri0 + v * RI_N + RI_VIS);   // vis | w | rd0 | rd1
+          const float2 r1 = *reinterpret_cast<const float2*>(ri0 + v * RI_N + RI_RD2);   // rd2 | rd3
+          rgbl = lane == 0 ? cx : (lane == 1 ? cy : cz);
+          wv = r0.y;
+          if (lane == 0 && rgbvis_out) __stcs(reinterpret_cast<float4*>(rgbvis_out + (nidx(p) * V + v) * 4), make_float4(cx, cy, cz, r0.x));
+          if (with_blend) {
+            float a = bacc;
+            a = fmaf(cx, wb[0], a); a = fmaf(cy, wb[1], a); a = fmaf(cz, wb[2], a);
+            a = fmaf(r0.x, wb[3], a);
+            a = fmaf(r0.z, wb[4], a); a = fmaf(r0.w, wb[5], a); a = fmaf(r1.x, wb[6], a); a = fmaf(r1.y, wb[7], a);
+            __stcs(partial_out + partial_off(nidx(p) * V + v, lane >> 2) + (lane & 3), a + bias);
+          }
+          if (mvf_out) {
+            float* mo = mvf_out + (nidx(p) * V + v) * C_RGBF;
+            if (lane < 3) mo[lane] = rgbl;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { mo[3 + j * 64 + lane * 2] = f[j].x; mo[3 + j * 64 + lane * 2 + 1] = f[j].y; }
+          }
+        }
+        if (v + 2 < 8) issue(b, v + 2);   // the buffer is free: request the view after next
+        sw += wv;
+        if (v == 0) {
+          rk = rgbl;
+        } else {
+          const float d = rgbl - rk, wd = wv * d;
+          rsx += wd;
+          rsxx = fmaf(wd, d, rsxx);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          if (v == 0) {
+            kk[j] = f[j];
+            sx[j] = make_float2(0.f, 0.f);
+            sxx[j] = make_float2(0.f, 0.f);
+          } else {
+            const float dx = f[j].x - kk[j].x, dy = f[j].y - kk[j].y;
+            const float wdx = wv * dx, wdy = wv * dy;
+            sx[j].x += wdx; sx[j].y += wdy;
+            sxx[j].x = fmaf(wdx, dx, sxx[j].x); sxx[j].y = fmaf(wdy, dy, sxx[j].y);
           }
         }
       }
-      // visibility-weighted mean / variance over the views, same summation order as mean_var_rows
+      // visibility-weighted mean / variance over the views (ibrnet.py:8-12)
       float* g = sG + p * LDG;
+      const int64_t n = nidx(p);
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        float mx = 0.f, my = 0.f;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) { mx += f[v][j].x * wvv[v]; my += f[v][j].y * wvv[v]; }
-        float vx = 0.f, vy = 0.f;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-          const float dx = f[v][j].x - mx, dy = f[v][j].y - my;
-          vx += wvv[v] * (dx * dx); vy += wvv[v] * (dy * dy);
-        }
+        const float mx = fmaf(kk[j].x, sw, sx[j].x), my = fmaf(kk[j].y, sw, sx[j].y);
+        const float cx = mx - kk[j].x, cy = my - kk[j].y;
+        const float vx = fmaxf(fmaf(cx * cx, sw, fmaf(-2.f * cx, sx[j].x, sxx[j].x)), 0.f);
+        const float vy = fmaxf(fmaf(cy * cy, sw, fmaf(-2.f * cy, sx[j].y, sxx[j].y)), 0.f);
         if (GOUT) {
-          float* go = g_out + nidx(p) * 416 + j * 64 + lane * 2;
+          float* go = g_out + n * 416 + j * 64 + lane * 2;
           __stcs(reinterpret_cast<float2*>(go), make_float2(mx, my));
           __stcs(reinterpret_cast<float2*>(go + 192), make_float2(vx, vy));
         } else {
@@ -634,21 +664,21 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         }
       }
       if (lane < 3) {
-        float m = 0.f;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) m += rgbv[v] * wvv[v];
-        float var = 0.f;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) { const float d = rgbv[v] - m; var += wvv[v] * (d * d); }
+        const float m = fmaf(rk, sw, rsx), cm = m - rk;
+        const float var = fmaxf(fmaf(cm * cm, sw, fmaf(-2.f * cm, rsx, rsxx)), 0.f);
         if (GOUT) {
-          g_out[nidx(p) * 416 + 384 + lane] = m;
-          g_out[nidx(p) * 416 + 387 + lane] = var;
+          g_out[n * 416 + 384 + lane] = m;
+          g_out[n * 416 + 387 + lane] = var;
         } else {
           g[lane] = m;
           g[C_RGBF + lane] = var;
         }
       }
-      if (GOUT && lane < 26) g_out[nidx(p) * 416 + 390 + lane] = lane < 3 ? g[390 + lane] : 0.f;   // extras (phase 4), zero padding up to 416
+      if (GOUT && lane < 26) g_out[n * 416 + 390 + lane] = lane < 3 ? g[390 + lane] : 0.f;   // extras (phase 4), zero padding up to 416
+    };
+    for (int p = warp; p < np; p += NT / 32) {
+      if (V == 8) gather_sample(p, std::true_type{});
+      else gather_sample(p, std::false_type{});
     }
   } else {
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
