@@ -95,14 +95,19 @@ constexpr int LDG = 420;   // 393 -> 416 (+4)
 #ifndef AGG_ROWS
 #define AGG_ROWS 64
 #endif
+#ifndef AGG_PERSIST
+#define AGG_PERSIST 0   // 1: persistent CTAs with next-tile prefetch for the render variant (measured slower: 160 vs 152 ms, the
+#endif                  // two CTAs of an SM fall into lockstep and their latency-bound phases stop covering each other)
 
 // ROWS = (sample, view) rows per CTA.  128 rows fill the SM with one CTA; 64 rows fit two CTAs per SM (about 110 KB each), which
 // doubles the resident warps for the latency-bound gather phases.
 // FUSED (V <= 8): the gather of phase 5 feeds the mean / variance of phase 6 through registers, so the [ROWS][LDF] tile of
 // interpolated features does not exist and the arena only holds the decoder input; the 50 KB it saves per CTA go to the L1.
-template <int ROWS, bool FUSED>
+// SLIM (the persistent render variant: decoder and out_fc live in their own kernels): no weight staging ring, no row tile
+template <int ROWS, bool FUSED, bool SLIM = false>
 constexpr int agg_smem_floats() {
-  return STAGE_FLOATS + ROWS * (FUSED ? LDX : LDF) + (ROWS / 8) * LDG + (ROWS / 8) * 68 + ROWS * RI_N + (ROWS / 8) * 4;
+  return (SLIM ? 0 : STAGE_FLOATS + ROWS * (FUSED ? LDX : LDF)) + (ROWS / 8) * LDG + (ROWS / 8) * 68 + ROWS * RI_N + (ROWS / 8) * 4 +
+         2 * (ROWS / 8) * 8 + 2 * ROWS * 2;   // + the next tile's point data and visibility rows (persistent GOUT variant)
 }
 
 // visibility-weighted mean / variance over the views of one sample (ibrnet.py:8-12): one warp, lanes over channels
@@ -141,26 +146,37 @@ __device__ __forceinline__ void mean_var_rows(const float* __restrict__ f0, cons
   }
 }
 
+// packed fp32 pairs (one issue slot for two FMAs): the gather keeps channel pairs in 64-bit registers end to end
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float2 up2(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f32x2 fma2p(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2p(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2p(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
 // EXT: visibility and depth difference per (sample, view) come from visibility_kernel (`visdd_in`, [N][V] float2) - the NeuRay
 // projection, the visibility-feature gather and the decoder are compiled out.
 // GOUT (with FUSED and EXT): the per-sample statistics vector (mean | variance | 3 extras, the input of out_fc) goes to global
 // memory (`g_out`, [N][416]: map-channel means 0..191, variances 192..383, rgb mean / variance 384..389, extras 390..392, zeros)
 // and out_fc + the attention query projection run as 128-sample tensor-core GEMMs in fc_tail_kernel.
 template <int ROWS, bool FUSED, bool EXT, bool GOUT = false>
-__global__ void __launch_bounds__(NT, 128 / ROWS)
+__global__ void __launch_bounds__(NT, (FUSED && EXT && GOUT) ? 2 : 128 / ROWS)
 aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const int64_t N, const int with_blend,
                  const float2* __restrict__ visdd_in, float* __restrict__ g_out,
                  float* __restrict__ agg_out, float* __restrict__ partial_out, float* __restrict__ rgbvis_out,
                  unsigned char* __restrict__ nvalid_out, float* __restrict__ mvf_out, float* __restrict__ mvv_out) {
   extern __shared__ __align__(16) float smem[];
   float* sB = smem;
-  float* arena = sB + STAGE_FLOATS;
+  constexpr bool SLIM = FUSED && EXT && GOUT;
+  float* arena = sB + (SLIM ? 0 : STAGE_FLOATS);
   constexpr int TP_MAX = ROWS / 8;
   constexpr int PARTS = NT / ROWS;  // threads per row in the per-row scalar phases
-  float* sG = arena + ROWS * (FUSED ? LDX : LDF);
+  float* sG = arena + (SLIM ? 0 : ROWS * (FUSED ? LDX : LDF));
   float* sO1 = sG + TP_MAX * LDG;
   float* sRI = sO1 + TP_MAX * 68;
   float* sPt = sRI + ROWS * RI_N;
+  float* sPre = sPt + TP_MAX * 4;        // [2][TP_MAX][8]: o | d | z (or xyz) of the samples of this / the next tile
+  float* sVd = sPre + 2 * TP_MAX * 8;    // [2][ROWS] float2: visibility | depth difference rows of this / the next tile
   float* sX = arena;                // [ROWS][LDX]
   float* sF = arena;                // [ROWS][LDF] (after the decoder is done)
 
@@ -172,18 +188,55 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   // quarter of a feature-map pixel apart for adjacent query pixels), consecutive samples of one ray do not (more than a pixel
   // apart along the epipolar line), and the bilinear gathers of a tile are what this kernel waits for.
   const bool by_ray = ps.xyz == nullptr;
-  const int64_t tile_g = by_ray ? (int64_t)blockIdx.x / ps.S : (int64_t)blockIdx.x;
-  const int tile_s = by_ray ? (int)((int64_t)blockIdx.x - tile_g * ps.S) : 0;
   const int64_t n_items = by_ray ? N / ps.S : N;                     // rays or points
+  const int64_t n_tiles = by_ray ? ((n_items + TP - 1) / TP) * ps.S : (n_items + TP - 1) / TP;
+  const float near_ = sc.near_, far_ = sc.far_;
+  // GOUT (the render path): persistent CTAs.  The point data and the visibility rows of a CTA's NEXT tile are copied into shared
+  // memory (cp.async) while the current tile is gathered, so a tile starts with its projections instead of with a round trip to
+  // global memory, and the launch cost of a CTA is paid once per 16 k tiles.  The other variants run one tile per CTA.
+  auto prefetch = [&](const int64_t t, const int buf) {
+    const int64_t tg = by_ray ? t / ps.S : t;
+    const int ts = by_ray ? (int)(t - tg * ps.S) : 0;
+    const int npn = (int)min((int64_t)TP, n_items - tg * TP);
+    if (tid < npn * 8) {
+      const int pp = tid >> 3, f = tid & 7;
+      const int64_t item = tg * TP + pp;
+      const float* src = nullptr;
+      if (by_ray) src = f < 3 ? ps.rays_o + item * 3 + f : (f < 6 ? ps.rays_d + item * 3 + (f - 3) : (f == 6 ? ps.z + item * ps.zs + ts : nullptr));
+      else src = f < 3 ? ps.xyz + item * 3 + f : nullptr;
+      if (src) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(sPre + (buf * TP_MAX + pp) * 8 + f);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src));
+      }
+    }
+    if (tid >= 64 && tid < 64 + npn * V) {
+      const int r = tid - 64, pp = r / V;
+      const int64_t n = by_ray ? (tg * TP + pp) * ps.S + ts : tg * TP + pp;
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(sVd + (buf * ROWS + r) * 2);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(visdd_in + n * V + (r - pp * V)));
+    }
+    cp_async_commit();
+  };
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+  const int64_t tile_g = by_ray ? tile / ps.S : tile;
+  const int tile_s = by_ray ? (int)(tile - tile_g * ps.S) : 0;
   const int np = (int)min((int64_t)TP, n_items - tile_g * TP);
   auto nidx = [&](int p) -> int64_t { return by_ray ? (tile_g * TP + p) * ps.S + tile_s : tile_g * TP + p; };
   const int rows = np * V;
-  const float near_ = sc.near_, far_ = sc.far_;
+  const int pbuf = it & 1;
 
   AGG_STAMP(0);
-  // visibility | depth difference of this thread's (sample, view) row: requested now, consumed after the projections
   float2 vd_pre = make_float2(0.f, 0.f);
-  if (EXT && tid < rows) vd_pre = __ldcs(visdd_in + nidx(tid / V) * V + (tid - (tid / V) * V));   // written once by visibility_kernel
+  if (GOUT && AGG_PERSIST) {
+    if (it == 0) prefetch(tile, 0);
+    cp_async_wait<0>();
+    cta_sync();   // this tile's point data and visibility rows landed; the previous tile is done with sRI / sG
+    if (tile + gridDim.x < n_tiles) prefetch(tile + gridDim.x, pbuf ^ 1);
+  } else if (EXT && tid < rows) {
+    // visibility | depth difference of this thread's (sample, view) row: requested now, consumed after the projections
+    vd_pre = __ldcs(visdd_in + nidx(tid / V) * V + (tid - (tid / V) * V));   // written once by visibility_kernel
+  }
   // decoder weights (32 KB) go into the staging ring, which is idle until phase 7: dec1 as [32][128] (the four heads side by
   // side), dec2 as 4 x [32][32].  Both are read as mma.sync B fragments (thread (g, t) reads rows t / t + 4 resp. 2t / 2t + 1,
   // column g), so 8-column groups are XOR-swizzled with the row to keep those reads bank-conflict free without padding:
@@ -207,9 +260,22 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     if (r < rows) {
       const int p = r / V, v = r - p * V;
       float x, y, z;
-      load_point(ps, nidx(p), x, y, z);
+      if (GOUT && AGG_PERSIST) {
+        const float* pr = sPre + (pbuf * TP_MAX + p) * 8;
+        if (by_ray) {   // xyz = rays_o + rays_d * z, one rounding per op (model.py:498)
+          x = __fadd_rn(pr[0], __fmul_rn(pr[3], pr[6]));
+          y = __fadd_rn(pr[1], __fmul_rn(pr[4], pr[6]));
+          z = __fadd_rn(pr[2], __fmul_rn(pr[5], pr[6]));
+        } else {
+          x = pr[0]; y = pr[1]; z = pr[2];
+        }
+      } else {
+        load_point(ps, nidx(p), x, y, z);
+      }
       const float* cam = sc.cams + v * 32;
-      for (int job = part; job < 3; job += PARTS) {
+      // (EXT: the NeuRay projection, job 1, lives in visibility_kernel; the two remaining jobs go to different threads of the row)
+      for (int jj = part; jj < (EXT ? 2 : 3); jj += PARTS) {
+        const int job = EXT ? jj * 2 : jj;
         if (job == 0) {
           // the (sample, view) split of the row index is taken once here: a runtime division per row in each of the later
           // per-row loops was 11 % of the kernel's instructions
@@ -229,7 +295,6 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           store_taps(ri + RI_TI, make_taps(((gx + 1.f) / 2.f) * (float)(sc.W - 1), ((gy + 1.f) / 2.f) * (float)(sc.H - 1), sc.W, sc.H, true), sc.W, sc.H);
           store_taps(ri + RI_TF, make_taps(((gx + 1.f) / 2.f) * (float)(sc.w - 1), ((gy + 1.f) / 2.f) * (float)(sc.h - 1), sc.w, sc.h, true), sc.w, sc.h);
         } else if (job == 1) {
-          if (EXT) continue;
           // NeuRay convention
           const float* kr = cam + 12;
           const float c0 = fmaf(kr[2], z, fmaf(kr[1], y, kr[0] * x)) + kr[3];
@@ -428,7 +493,10 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     const bool live = tid < rows;
     float vis = 0.f, dd = 0.f;
     if (EXT) {
-      if (live) { vis = vd_pre.x; dd = vd_pre.y; }
+      if (live) {
+        if (GOUT && AGG_PERSIST) vd_pre = *reinterpret_cast<const float2*>(sVd + (pbuf * ROWS + tid) * 2);
+        vis = vd_pre.x; dd = vd_pre.y;
+      }
     } else {
       const float m0 = sO1[tid * 6], m1 = sO1[tid * 6 + 1], v0 = sO1[tid * 6 + 2], v1 = sO1[tid * 6 + 3];
       const float aw = sO1[tid * 6 + 4], vs = sO1[tid * 6 + 5];
@@ -533,9 +601,13 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       // view's value K (d = x - K, exactly 0 for view 0): mean = K sw + sum w d, var = sum w (d - c)^2 = sum w d^2 - 2 c sum w d +
       // c^2 sw with c = mean - K - so the views' channels need not stay in registers for a second pass.
       const float* ri0 = sRI + p * V * RI_N;
-      float2 q[2][4][3];
+      // output addresses once per sample; per view they differ by compile-time offsets (8 views: rows 8 n .. 8 n + 7 of partial_off)
+      const int64_t n = nidx(p);
+      float* rv_ptr = rgbvis_out ? rgbvis_out + n * V * 4 : nullptr;
+      float* pp_ptr = partial_out + (FULL ? (n >> 2) * 1024 + (lane >> 2) * 128 + (n & 3) * 32 + (lane & 3) : 0);
+      f32x2 q[2][4][3];
       float wt[2][4], bq[2][4];
-      float2 kk[3], sx[3], sxx[3];
+      f32x2 nkk[3], sx[3], sxx[3];   // -K | sum w d | sum w d^2, channel pairs
       float rk = 0.f, rsx = 0.f, rsxx = 0.f, sw = 0.f;   // the same for the lane's colour channel
       // colour: lane (v, t) = (lane / 4, lane % 4) fetches tap t of view v, the taps are summed over the 4 lanes of a view
       float4 crgb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -554,7 +626,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           for (int t = 0; t < 4; ++t) {
             wt[b][t] = 0.f; bq[b][t] = 0.f;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) q[b][t][j] = make_float2(0.f, 0.f);
+            for (int j = 0; j < 3; ++j) q[b][t][j] = 0ull;
           }
         }
         if (FULL || v < V) {
@@ -569,7 +641,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
             wt[b][t] = twv[t];
             const float* tp = fb0 + (size_t)pg[t] * C_FEAT;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) q[b][t][j] = __ldg(reinterpret_cast<const float2*>(tp + j * 64));
+            for (int j = 0; j < 3; ++j) q[b][t][j] = __ldg(reinterpret_cast<const f32x2*>(tp + j * 64));
           }
           if (with_blend) {
 #pragma unroll
@@ -584,16 +656,17 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
 #pragma unroll
       for (int v = 0; v < 8; ++v) {
         const int b = v & 1;
-        float2 f[3];
+        // d = sum_t q_t w_t - K: the interpolation starts from -K (0 for view 0, whose value becomes K)
+        f32x2 d[3];
+        {
+          const f32x2 w2[4] = {pk2(wt[b][0], wt[b][0]), pk2(wt[b][1], wt[b][1]), pk2(wt[b][2], wt[b][2]), pk2(wt[b][3], wt[b][3])};
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          float2 acc = make_float2(0.f, 0.f);
+          for (int j = 0; j < 3; ++j) {
+            f32x2 acc = v == 0 ? 0ull : nkk[j];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) {
-            acc.x = fmaf(q[b][t][j].x, wt[b][t], acc.x);
-            acc.y = fmaf(q[b][t][j].y, wt[b][t], acc.y);
+            for (int t = 0; t < 4; ++t) acc = fma2p(q[b][t][j], w2[t], acc);
+            d[j] = acc;
           }
-          f[j] = acc;
         }
         float bacc = 0.f;
 #pragma unroll
@@ -606,19 +679,24 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           const float2 r1 = *reinterpret_cast<const float2*>(ri0 + v * RI_N + RI_RD2);   // rd2 | rd3
           rgbl = lane == 0 ? cx : (lane == 1 ? cy : cz);
           wv = r0.y;
-          if (lane == 0 && rgbvis_out) __stcs(reinterpret_cast<float4*>(rgbvis_out + (nidx(p) * V + v) * 4), make_float4(cx, cy, cz, r0.x));
+          if (lane == 0 && rv_ptr) __stcs(reinterpret_cast<float4*>(rv_ptr + v * 4), make_float4(cx, cy, cz, r0.x));
           if (with_blend) {
             float a = bacc;
             a = fmaf(cx, wb[0], a); a = fmaf(cy, wb[1], a); a = fmaf(cz, wb[2], a);
             a = fmaf(r0.x, wb[3], a);
             a = fmaf(r0.z, wb[4], a); a = fmaf(r0.w, wb[5], a); a = fmaf(r1.x, wb[6], a); a = fmaf(r1.y, wb[7], a);
-            __stcs(partial_out + partial_off(nidx(p) * V + v, lane >> 2) + (lane & 3), a + bias);
+            if (FULL) __stcs(pp_ptr + v * 4, a + bias);
+            else __stcs(partial_out + partial_off(n * V + v, lane >> 2) + (lane & 3), a + bias);
           }
           if (mvf_out) {
-            float* mo = mvf_out + (nidx(p) * V + v) * C_RGBF;
+            float* mo = mvf_out + (n * V + v) * C_RGBF;
             if (lane < 3) mo[lane] = rgbl;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) { mo[3 + j * 64 + lane * 2] = f[j].x; mo[3 + j * 64 + lane * 2 + 1] = f[j].y; }
+            for (int j = 0; j < 3; ++j) {
+              float2 f = up2(d[j]);
+              if (v != 0) { const float2 k2 = up2(nkk[j]); f.x -= k2.x; f.y -= k2.y; }
+              mo[3 + j * 64 + lane * 2] = f.x; mo[3 + j * 64 + lane * 2 + 1] = f.y;
+            }
           }
         }
         if (v + 2 < 8) issue(b, v + 2);   // the buffer is free: request the view after next
@@ -626,33 +704,37 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         if (v == 0) {
           rk = rgbl;
         } else {
-          const float d = rgbl - rk, wd = wv * d;
+          const float dr = rgbl - rk, wd = wv * dr;
           rsx += wd;
-          rsxx = fmaf(wd, d, rsxx);
+          rsxx = fmaf(wd, dr, rsxx);
         }
+        if (v == 0) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          if (v == 0) {
-            kk[j] = f[j];
-            sx[j] = make_float2(0.f, 0.f);
-            sxx[j] = make_float2(0.f, 0.f);
-          } else {
-            const float dx = f[j].x - kk[j].x, dy = f[j].y - kk[j].y;
-            const float wdx = wv * dx, wdy = wv * dy;
-            sx[j].x += wdx; sx[j].y += wdy;
-            sxx[j].x = fmaf(wdx, dx, sxx[j].x); sxx[j].y = fmaf(wdy, dy, sxx[j].y);
+          for (int j = 0; j < 3; ++j) {
+            const float2 k2 = up2(d[j]);
+            nkk[j] = pk2(-k2.x, -k2.y);
+            sx[j] = 0ull;
+            sxx[j] = 0ull;
+          }
+        } else {
+          const f32x2 wv2 = pk2(wv, wv);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const f32x2 wd = mul2p(wv2, d[j]);
+            sx[j] = add2p(sx[j], wd);
+            sxx[j] = fma2p(wd, d[j], sxx[j]);
           }
         }
       }
       // visibility-weighted mean / variance over the views (ibrnet.py:8-12)
       float* g = sG + p * LDG;
-      const int64_t n = nidx(p);
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        const float mx = fmaf(kk[j].x, sw, sx[j].x), my = fmaf(kk[j].y, sw, sx[j].y);
-        const float cx = mx - kk[j].x, cy = my - kk[j].y;
-        const float vx = fmaxf(fmaf(cx * cx, sw, fmaf(-2.f * cx, sx[j].x, sxx[j].x)), 0.f);
-        const float vy = fmaxf(fmaf(cy * cy, sw, fmaf(-2.f * cy, sx[j].y, sxx[j].y)), 0.f);
+        const float2 nk = up2(nkk[j]), s1 = up2(sx[j]), s2 = up2(sxx[j]);
+        const float mx = fmaf(-nk.x, sw, s1.x), my = fmaf(-nk.y, sw, s1.y);
+        const float cx = mx + nk.x, cy = my + nk.y;
+        const float vx = fmaxf(fmaf(cx * cx, sw, fmaf(-2.f * cx, s1.x, s2.x)), 0.f);
+        const float vy = fmaxf(fmaf(cy * cy, sw, fmaf(-2.f * cy, s1.y, s2.y)), 0.f);
         if (GOUT) {
           float* go = g_out + n * 416 + j * 64 + lane * 2;
           __stcs(reinterpret_cast<float2*>(go), make_float2(mx, my));
@@ -678,7 +760,11 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     };
     for (int p = warp; p < np; p += NT / 32) {
       if (V == 8) gather_sample(p, std::true_type{});
+#ifdef AGG_FULL_ONLY
+      else __trap();
+#else
       else gather_sample(p, std::false_type{});
+#endif
     }
   } else {
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
@@ -808,7 +894,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   for (int i = tid; i < (TP_MAX - np) * LDG; i += NT) sG[np * LDG + i] = 0.f;
 
   AGG_STAMP(7);
-  if (GOUT) return;
+  if (GOUT) { if (AGG_PERSIST) continue; else return; }   // (persistent: the next tile starts with a CTA-wide barrier)
   // ---- phase 7: out_fc 393 -> 64 -> 128 (ELU) --------------------------------------------------------------------
   cta_sync();  // sG complete
   rows16_gemm<64, TP_MAX, 416, 8>([&](int r, int) { return sG + r * LDG; }, w.fc1, 64, sB,
@@ -819,6 +905,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   });
 
   AGG_STAMP(8);
+  }
 }
 
 // Per-frame pre-projection of the reference feature maps through the map-feature rows of the colour-blend first layer
@@ -916,8 +1003,18 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   if (sc.V <= 8 && !unfused) {
     const size_t smem = agg_smem_floats<ROWS, true>() * sizeof(float);
     if (ext && g_scratch && q_out && !fc_inside) {
-      if (set_smem(aggregate_kernel<ROWS, true, true, true>, smem)) return 1;
-      aggregate_kernel<ROWS, true, true, true><<<grid, NT, smem, st>>>(sc, w, ps, N, with_blend, vd, g_scratch, agg, partial, rgbvis, nvalid, mvf, mvv);
+      // render variant: 16 samples (the same sample index of 16 adjacent rays) per tile - the serial per-tile phases (projection,
+      // view weights, barriers) cost the same for 128 rows as for 64 - in 45 KB of shared memory, two CTAs per SM
+      constexpr int ROWS_G = 128;
+      const int TPG = ROWS_G / 8 < ROWS_G / sc.V ? ROWS_G / 8 : ROWS_G / sc.V;
+      const int64_t tiles_g = ps.xyz ? (N + TPG - 1) / TPG : ((N / ps.S + TPG - 1) / TPG) * ps.S;
+      const size_t smem_p = agg_smem_floats<ROWS_G, true, true>() * sizeof(float);
+      if (set_smem(aggregate_kernel<ROWS_G, true, true, true>, smem_p)) return 1;
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      const unsigned pgrid = AGG_PERSIST ? (unsigned)(tiles_g < 2 * (int64_t)sms ? tiles_g : 2 * (int64_t)sms) : (unsigned)tiles_g;
+      aggregate_kernel<ROWS_G, true, true, true><<<pgrid, NT, smem_p, st>>>(sc, w, ps, N, with_blend, vd, g_scratch, agg, partial, rgbvis, nvalid, mvf, mvv);
       if (check_launch("aggregate_kernel")) return 1;
       prof_mark("aggregate");
       if (launch_fc_tail(w, g_scratch, N, agg, q_out, st)) return 1;
