@@ -106,7 +106,7 @@ constexpr int LDG = 420;   // 393 -> 416 (+4)
 // SLIM (the persistent render variant: decoder and out_fc live in their own kernels): no weight staging ring, no row tile
 template <int ROWS, bool FUSED, bool SLIM = false>
 constexpr int agg_smem_floats() {
-  return (SLIM ? 0 : STAGE_FLOATS + ROWS * (FUSED ? LDX : LDF)) + (ROWS / 8) * LDG + (ROWS / 8) * 68 + ROWS * RI_N + (ROWS / 8) * 4 +
+  return (SLIM ? 0 : STAGE_FLOATS + ROWS * (FUSED ? LDX : LDF)) + (ROWS / 8) * (SLIM ? 32 : LDG) + (ROWS / 8) * 68 + ROWS * RI_N + (ROWS / 8) * 4 +
          2 * (ROWS / 8) * 8 + 2 * ROWS * 2;   // + the next tile's point data and visibility rows (persistent GOUT variant)
 }
 
@@ -172,7 +172,9 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
   constexpr int TP_MAX = ROWS / 8;
   constexpr int PARTS = NT / ROWS;  // threads per row in the per-row scalar phases
   float* sG = arena + (SLIM ? 0 : ROWS * (FUSED ? LDX : LDF));
-  float* sO1 = sG + TP_MAX * LDG;
+  // SLIM: of a sample's statistics vector only the three extras 390..392 (+ zero padding) pass through shared memory
+  constexpr int LDGS = SLIM ? 32 : LDG, G0 = SLIM ? 390 : 0;
+  float* sO1 = sG + TP_MAX * LDGS;
   float* sRI = sO1 + TP_MAX * 68;
   float* sPt = sRI + ROWS * RI_N;
   float* sPre = sPt + TP_MAX * 4;        // [2][TP_MAX][8]: o | d | z (or xyz) of the samples of this / the next tile
@@ -535,7 +537,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       const float ddv = sum8(wv * (d * d));
       if (live) {
         ri[RI_W] = wv;
-        float* g = sG + p * LDG;
+        float* g = sG + p * LDGS - G0;
         if (v == 0) {
           g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
           if (nvalid_out) nvalid_out[nidx(p)] = (unsigned char)nval;
@@ -562,7 +564,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       const unsigned nval = __popc(__ballot_sync(0xffffffffu, on && ri[RI_MASK] != 0.f));
       const float d = dd - ddm;
       const float ddv = warp_sum(wv * (d * d));
-      float* g = sG + p * LDG;
+      float* g = sG + p * LDGS - G0;
       if (lane == 0) {
         g[390] = ddm; g[391] = ddv; g[392] = wsum / (float)V;
         if (nvalid_out) nvalid_out[nidx(p)] = (unsigned char)nval;
@@ -727,7 +729,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         }
       }
       // visibility-weighted mean / variance over the views (ibrnet.py:8-12)
-      float* g = sG + p * LDG;
+      float* g = sG + p * LDGS - G0;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         const float2 nk = up2(nkk[j]), s1 = up2(sx[j]), s2 = up2(sxx[j]);
@@ -891,7 +893,7 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     else mean_var_rows<16>(sF + (p * V) * LDF, sRI + (p * V) * RI_N, V, lane, sG + p * LDG);
   }
   }
-  for (int i = tid; i < (TP_MAX - np) * LDG; i += NT) sG[np * LDG + i] = 0.f;
+  for (int i = tid; i < (TP_MAX - np) * LDGS; i += NT) sG[np * LDGS + i] = 0.f;
 
   AGG_STAMP(7);
   if (GOUT) { if (AGG_PERSIST) continue; else return; }   // (persistent: the next tile starts with a CTA-wide barrier)
@@ -1003,9 +1005,9 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   if (sc.V <= 8 && !unfused) {
     const size_t smem = agg_smem_floats<ROWS, true>() * sizeof(float);
     if (ext && g_scratch && q_out && !fc_inside) {
-      // render variant: 16 samples (the same sample index of 16 adjacent rays) per tile - the serial per-tile phases (projection,
-      // view weights, barriers) cost the same for 128 rows as for 64 - in 45 KB of shared memory, two CTAs per SM
-      constexpr int ROWS_G = 128;
+      // render variant: 32 samples (the same sample index of 32 adjacent rays) per tile - the serial per-tile phases (projection,
+      // view weights, barriers) cost little more for 256 rows than for 64 - in 40 KB of shared memory, two CTAs per SM
+      constexpr int ROWS_G = 256;
       const int TPG = ROWS_G / 8 < ROWS_G / sc.V ? ROWS_G / 8 : ROWS_G / sc.V;
       const int64_t tiles_g = ps.xyz ? (N + TPG - 1) / TPG : ((N / ps.S + TPG - 1) / TPG) * ps.S;
       const size_t smem_p = agg_smem_floats<ROWS_G, true, true>() * sizeof(float);
