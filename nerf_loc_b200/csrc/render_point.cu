@@ -596,33 +596,18 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
     const float* bb0 = sc.featb + lane;
     const unsigned hw = (unsigned)(sc.h * sc.w);
     // FULL (V == 8, the rendering configuration): no per-view guards, no zero-filled buffers
-    auto gather_sample = [&](const int p, auto full_c) {
+    auto gather_samples = [&](auto full_c) {
       constexpr bool FULL = decltype(full_c)::value;
+      // (the pipeline does not drain between the samples of a warp: views 0 and 1 of the next sample are requested while views 6
+      // and 7 of this one are consumed, its colour taps one sample ahead)
       // Software pipeline over the views, two register buffers: while view v is interpolated the loads of view v + 1 are in flight
       // and those of view v + 2 are issued into the buffer v just left.  The statistics are accumulated in one pass about the first
       // view's value K (d = x - K, exactly 0 for view 0): mean = K sw + sum w d, var = sum w (d - c)^2 = sum w d^2 - 2 c sum w d +
       // c^2 sw with c = mean - K - so the views' channels need not stay in registers for a second pass.
-      const float* ri0 = sRI + p * V * RI_N;
-      // output addresses once per sample; per view they differ by compile-time offsets (8 views: rows 8 n .. 8 n + 7 of partial_off)
-      const int64_t n = nidx(p);
-      float* rv_ptr = rgbvis_out ? rgbvis_out + n * V * 4 : nullptr;
-      float* pp_ptr = partial_out + (FULL ? (n >> 2) * 1024 + (lane >> 2) * 128 + (n & 3) * 32 + (lane & 3) : 0);
       f32x2 q[2][4][3];
       float wt[2][4], bq[2][4];
-      f32x2 nkk[3], sx[3], sxx[3];   // -K | sum w d | sum w d^2, channel pairs
-      float rk = 0.f, rsx = 0.f, rsxx = 0.f, sw = 0.f;   // the same for the lane's colour channel
-      // colour: lane (v, t) = (lane / 4, lane % 4) fetches tap t of view v, the taps are summed over the 4 lanes of a view
-      float4 crgb = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (FULL || (lane >> 2) < V) {
-        const float* ri = ri0 + (lane >> 2) * RI_N;
-        const float wi = ri[RI_TI + 4 + (lane & 3)];
-        if (wi != 0.f) {
-          const int pix = __float_as_int(ri[RI_TI + (lane & 3)]);
-          const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc.images + ((size_t)(lane >> 2) * sc.H * sc.W + pix) * 4));
-          crgb = make_float4(c4.x * wi, c4.y * wi, c4.z * wi, 0.f);
-        }
-      }
-      auto issue = [&](const int b, const int v) {
+      auto issue = [&](const int b, const int ps_, const int v) {
+        const float* ri0 = sRI + ps_ * V * RI_N;
         if (!FULL) {
 #pragma unroll
           for (int t = 0; t < 4; ++t) {
@@ -651,8 +636,37 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
           }
         }
       };
-      issue(0, 0);
-      issue(1, 1);
+      auto colour = [&](const int ps_) {
+        // colour: lane (v, t) = (lane / 4, lane % 4) fetches tap t of view v, the taps are summed over the 4 lanes of a view
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (FULL || (lane >> 2) < V) {
+          const float* ri = sRI + (ps_ * V + (lane >> 2)) * RI_N;
+          const float wi = ri[RI_TI + 4 + (lane & 3)];
+          if (wi != 0.f) {
+            const int pix = __float_as_int(ri[RI_TI + (lane & 3)]);
+            const float4 c4 = __ldg(reinterpret_cast<const float4*>(sc.images + ((size_t)(lane >> 2) * sc.H * sc.W + pix) * 4));
+            c = make_float4(c4.x * wi, c4.y * wi, c4.z * wi, 0.f);
+          }
+        }
+        return c;
+      };
+      float4 crgb_next = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (warp < np) {
+        crgb_next = colour(warp);
+        issue(0, warp, 0);
+        issue(1, warp, 1);
+      }
+      for (int p = warp; p < np; p += NT / 32) {
+      const bool has_next = p + NT / 32 < np;
+      const float* ri0 = sRI + p * V * RI_N;
+      // output addresses once per sample; per view they differ by compile-time offsets (8 views: rows 8 n .. 8 n + 7 of partial_off)
+      const int64_t n = nidx(p);
+      float* rv_ptr = rgbvis_out ? rgbvis_out + n * V * 4 : nullptr;
+      float* pp_ptr = partial_out + (FULL ? (n >> 2) * 1024 + (lane >> 2) * 128 + (n & 3) * 32 + (lane & 3) : 0);
+      f32x2 nkk[3], sx[3], sxx[3];   // -K | sum w d | sum w d^2, channel pairs
+      float rk = 0.f, rsx = 0.f, rsxx = 0.f, sw = 0.f;   // the same for the lane's colour channel
+      float4 crgb = crgb_next;
+      if (has_next) crgb_next = colour(p + NT / 32);
       crgb.x += __shfl_xor_sync(0xffffffffu, crgb.x, 1); crgb.y += __shfl_xor_sync(0xffffffffu, crgb.y, 1); crgb.z += __shfl_xor_sync(0xffffffffu, crgb.z, 1);
       crgb.x += __shfl_xor_sync(0xffffffffu, crgb.x, 2); crgb.y += __shfl_xor_sync(0xffffffffu, crgb.y, 2); crgb.z += __shfl_xor_sync(0xffffffffu, crgb.z, 2);
 #pragma unroll
@@ -701,7 +715,8 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
             }
           }
         }
-        if (v + 2 < 8) issue(b, v + 2);   // the buffer is free: request the view after next
+        if (v + 2 < 8) issue(b, p, v + 2);   // the buffer is free: request the view after next
+        else if (has_next) issue(b, p + NT / 32, v + 2 - 8);
         sw += wv;
         if (v == 0) {
           rk = rgbl;
@@ -759,15 +774,10 @@ aggregate_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         }
       }
       if (GOUT && lane < 26) g_out[n * 416 + 390 + lane] = lane < 3 ? g[390 + lane] : 0.f;   // extras (phase 4), zero padding up to 416
+      }
     };
-    for (int p = warp; p < np; p += NT / 32) {
-      if (V == 8) gather_sample(p, std::true_type{});
-#ifdef AGG_FULL_ONLY
-      else __trap();
-#else
-      else gather_sample(p, std::false_type{});
-#endif
-    }
+    if (V == 8) gather_samples(std::true_type{});
+    else gather_samples(std::false_type{});
   } else {
   // ---- phase 5: rgb + 192-channel feature gather (zeros padding, align_corners=True), one warp per row ----------
   // A warp handles two rows per iteration and requests everything they need before it consumes any of it: 2 x 4 taps x 3
