@@ -378,11 +378,21 @@ __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy,
   for (int n = t.level_count[top] - 1; n >= 0; --n) {
     if (sp < STACK) { stk_node[sp] = ((unsigned)top << 28) | (unsigned)n; stk_d[sp] = node_d2(qx, qy, qz, t.boxes + t.level_off[top] + NODE_F4 * n); ++sp; }
   }
-  while (sp > 0) {
-    --sp;
-    const float nd = stk_d[sp];
+  // The nearest child of a node is visited next without a round trip through the stack (which lives in local memory): `cur`
+  // holds it; the visiting order is the one of a stack that had it on top.
+  unsigned cur = 0;
+  float cur_d = 0.f;
+  bool have_cur = false;
+  while (have_cur || sp > 0) {
+    float nd;
+    unsigned code;
+    if (have_cur) {
+      nd = cur_d; code = cur; have_cur = false;
+    } else {
+      --sp;
+      nd = stk_d[sp]; code = stk_node[sp];
+    }
     if (nd > fminf(best.worst(), bound)) continue;  // strict: equal distance may still hide a smaller index
-    const unsigned code = stk_node[sp];
     const int lvl = code >> 28;
     const int node = code & 0x0fffffffu;
     if (lvl == 0) {
@@ -417,8 +427,8 @@ __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy,
           stk_node[sp] = ((unsigned)cl << 28) | (unsigned)(c0 + k); stk_d[sp] = cd[k]; ++sp;
         }
       }
-      if (nearest >= 0 && nearest_d <= w && sp < STACK) {
-        stk_node[sp] = ((unsigned)cl << 28) | (unsigned)(c0 + nearest); stk_d[sp] = nearest_d; ++sp;
+      if (nearest >= 0 && nearest_d <= w) {
+        cur = ((unsigned)cl << 28) | (unsigned)(c0 + nearest); cur_d = nearest_d; have_cur = true;
       }
     }
   }
@@ -498,11 +508,23 @@ __global__ void __launch_bounds__(128) knn_query_rays_kernel(const void* __restr
     knn_search<K>(tree, qx, qy, qz, best, bound);
     const int64_t i = r * S + s;
     have_prev = best.id[K - 1] != 0x7fffffff;
+    int oi[K];
+    float od[K];
 #pragma unroll
     for (int k = 0; k < K; ++k) {
       const bool ok = best.id[k] != 0x7fffffff;
-      __stcs(idx32 + i * K + k, ok ? best.id[k] : 0);
-      __stcs(dist2 + i * K + k, ok ? best.d[k] : 0.f);
+      oi[k] = ok ? best.id[k] : 0;
+      od[k] = ok ? best.d[k] : 0.f;
+    }
+    if (K % 4 == 0) {   // (rows of K * 4 bytes: 16-byte aligned)
+#pragma unroll
+      for (int k = 0; k < K; k += 4) {
+        __stcs(reinterpret_cast<int4*>(idx32 + i * K + k), make_int4(oi[k], oi[k + 1], oi[k + 2], oi[k + 3]));
+        __stcs(reinterpret_cast<float4*>(dist2 + i * K + k), make_float4(od[k], od[k + 1], od[k + 2], od[k + 3]));
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) { __stcs(idx32 + i * K + k, oi[k]); __stcs(dist2 + i * K + k, od[k]); }
     }
   }
 }
