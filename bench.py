@@ -649,7 +649,7 @@ def main():
                     help="1: the metric's frame (default; its line also carries configs[2]); 3: Cambridge shape; sweep: configs[4]")
     ap.add_argument("--sweep-max", type=int, default=22, help="largest exponent of the ray-count sweep")
     ap.add_argument("--rays", type=int, default=0, help="debug: render only the first N rays of the frame")
-    ap.add_argument("--chunk", type=int, default=75776, help="rays per kernel wave (148 SMs x 512)")
+    ap.add_argument("--chunk", type=int, default=76960, help="cap on the rays per kernel wave (148 SMs x 520: a 640x480 frame is four equal waves)")
     ap.add_argument("--cpu-match-n3", type=int, default=256, help="3D points in the CPU matcher sample (0 = skip)")
     ap.add_argument("--cpu-rays", type=int, default=-1,
                     help="rays in the CPU sample: b200 arm default 4096 (about 15 s of host time), 0 = skip; reference arm default: "

@@ -184,7 +184,7 @@ class ConditionalNeRF(nn.Module):
         self._packed_key = None
         self._packed_src = None
         self._frame = {}
-        self.chunk_rays = 75776  # rays per kernel wave inside nlb_render_rays (148 SMs x 512; 5.0 KB of scratch per sample at V = 8)
+        self.chunk_rays = 76960  # cap on the rays per kernel wave inside nlb_render_rays (148 SMs x 520: a 640x480 frame is four equal waves; 5.0 KB of scratch per sample at V = 8)
 
     # ---- per-frame cache protocol -------------------------------------------------------------------------------------
     @property

@@ -27,11 +27,11 @@ if True:
         print(f"nb2 {names[i]:36s} {v[i+1]-v[i]:8d} clk")
     print("nb2 super-tile (32 samples) total", v[9] - v[0])
 
-an = ["proj", "vis gather", "decoder GEMMs+heads", "view weights", "rgb/feat gather", "blend partial", "mean/var", "out_fc"]
-for i in range(8):
-    print(f"agg {an[i]:28s} {v[17+i]-v[16+i]:8d} clk")
-print("agg total", v[24] - v[16])
-print("decoder detail: wait weights/sX", v[25]-v[18], "dec1", v[26]-v[25], "dec2", v[27]-v[26], "heads+vis", v[19]-v[27])
+# aggregate_kernel, render variant (stamps 16 + i: 0 start, 1 projections done, 4 view weights done, 7 gather + statistics done)
+print(f"agg projections (256 rows)            {v[17]-v[16]:8d} clk")
+print(f"agg visibility rows + view weights    {v[20]-v[17]:8d} clk")
+print(f"agg gather + statistics (4 samples per warp) {v[23]-v[20]:8d} clk")
+print("agg tile (32 samples) total", v[23] - v[16])
 
 rn = ["load x (both rays)", "blend weights + wait blend GEMM", "blend MLP + softmax (both rays)", "wait conv1", "epi conv1", "wait conv2",
       "epi conv2", "wait conv3", "epi conv3", "wait tconv3", "epi tconv3", "wait tconv2", "epi tconv2", "wait tconv1",
