@@ -238,7 +238,7 @@ int nlb_backproject_points(const float* mats_host, const int64_t* uu, const int6
 size_t nlb_render_scratch_bytes(int64_t chunk_rays, int S, int V) {
   const size_t n = (size_t)(chunk_rays < 1 ? 1 : chunk_rays) * S;
   const size_t slabs = S > 128 ? align256((size_t)RL_MAX_GRID * ray_long_slab_floats(S) * 4) : 0;
-  return align256(n * KNN_K * 4) * 2 + align256(n * W_HID * 4) * 2 + align256((n * V + 31) / 32 * 32 * 32 * 4) + align256(n * V * 16) +
+  return align256(n * KNN_K * 4) * 2 + align256(pm128_floats((int64_t)n) * 4) + align256(n * W_HID * 4) + align256((n * V + 31) / 32 * 32 * 32 * 4) + align256(n * V * 16) +
          align256(n) + align256(neighbor2_scratch_floats((int64_t)n) * 4) + align256(n * V * 8) + align256(n * 416 * 4) + slabs + 2048;
 }
 
@@ -276,7 +276,7 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
   Carver c{(char*)scratch, scratch_bytes};
   int* idx = c.take<int>(n * KNN_K);
   float* d2 = c.take<float>(n * KNN_K);
-  float* agg = c.take<float>(n * W_HID);
+  float* agg = c.take<float>(pm128_floats((int64_t)n));   // piece-major (pm128_off), whole groups of 32 rows
   float* fagg = c.take<float>(n * W_HID);
   float* partial = c.take<float>((n * V + 31) / 32 * 32 * 32);   // whole groups of 32 rows (partial_off)
   float* rgbvis = c.take<float>(n * V * 4);
@@ -317,9 +317,10 @@ static int render_rays_impl(const nlb_scene* scene, const float* packed_weights,
     prof.mark(nullptr);
     if (knn_chunk(i, st)) { rc_err = 1; break; }
     prof.mark("knn_query_rays");
-    const int ar = launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, visdd, gvec, nb2, st);
+    const int ar = launch_aggregate(sc, w, ps, nc, 1, agg, partial, rgbvis, nvalid, nullptr, nullptr, visdd, gvec, nb2, st, true);
     if (ar == 1) { rc_err = 1; break; }
-    if (launch_neighbor2(sc, w, ps, nc, KNN_K, idx, d2, agg, fa32, fsplit, S, nullptr, nullptr, nb2, ar == 2, st)) { rc_err = 1; break; }
+    // (agg is piece-major only if fc_tail_kernel wrote it: ar == 2)
+    if (launch_neighbor2(sc, w, ps, nc, KNN_K, idx, d2, agg, fa32, fsplit, S, nullptr, nullptr, nb2, ar == 2, st, ar == 2)) { rc_err = 1; break; }
     if (split_x) {
       if (launch_ray2(sc, w, zc, z_stride, rc, S, white_bkgd, fsplit, partial, rgbvis, nvalid, rgb + r0 * 3, depth + r0,
                       weights + r0 * S, mask + r0, depth_uncertainty + r0, feat ? feat + r0 * C_FEAT : nullptr,

@@ -40,7 +40,8 @@ struct Sync {
 static_assert(sizeof(Sync) <= 128, "fct::Sync");
 
 __global__ void __launch_bounds__(NT + 64, 2)
-fc_tail_kernel(const RenderW w, const float* __restrict__ G, const int64_t N, float* __restrict__ agg_out, float* __restrict__ q_out) {
+fc_tail_kernel(const RenderW w, const float* __restrict__ G, const int64_t N, float* __restrict__ agg_out, float* __restrict__ q_out,
+               const bool agg_pm) {
   extern __shared__ __align__(1024) unsigned char sm[];
   Sync& sy = *reinterpret_cast<Sync*>(sm + SYNC_OFF);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -213,7 +214,8 @@ fc_tail_kernel(const RenderW w, const float* __restrict__ G, const int64_t N, fl
         for (int j = 0; j < 32; ++j) v[j] = elu(v[j] + __ldg(w.fc2_b + half * 64 + cc + j));
         if (n < N) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(agg_out + n * W_HID + half * 64 + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(agg_out + (agg_pm ? pm128_off(n, half * 64 + cc + j) : n * W_HID + half * 64 + cc + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
         uint32_t hi[16], lo[16];
 #pragma unroll
@@ -232,7 +234,7 @@ fc_tail_kernel(const RenderW w, const float* __restrict__ G, const int64_t N, fl
         tc::tmem_ld32(trow + TM_D + (uint32_t)(half * 64 + cc), v);
         if (n < N) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(q_out + n * W_HID + half * 64 + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(q_out + pm128_off(n, half * 64 + cc + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
       tc::fence_before_sync();
@@ -249,7 +251,7 @@ fc_tail_kernel(const RenderW w, const float* __restrict__ G, const int64_t N, fl
 
 }  // namespace fct
 
-int launch_fc_tail(const RenderW& w, const float* g, int64_t N, float* agg, float* q, cudaStream_t st) {
+int launch_fc_tail(const RenderW& w, const float* g, int64_t N, float* agg, float* q, bool agg_pm, cudaStream_t st) {
   if (N <= 0) return 0;
   cudaError_t e = cudaFuncSetAttribute(fct::fc_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fct::SMEM_BYTES);
   if (e != cudaSuccess) return set_error(cudaGetErrorString(e));
@@ -258,7 +260,7 @@ int launch_fc_tail(const RenderW& w, const float* g, int64_t N, float* agg, floa
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t tiles = (N + 127) / 128;
   const unsigned grid = (unsigned)(tiles < 2 * sms ? tiles : 2 * sms);
-  fct::fc_tail_kernel<<<grid, NT + 64, fct::SMEM_BYTES, st>>>(w, g, N, agg, q);
+  fct::fc_tail_kernel<<<grid, NT + 64, fct::SMEM_BYTES, st>>>(w, g, N, agg, q, agg_pm);
   return check_launch("fc_tail_kernel");
 }
 

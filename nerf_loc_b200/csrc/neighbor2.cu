@@ -449,7 +449,7 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       // q rows of the group's 16 samples (written by fc_tail / qproj): asynchronous copy, consumed by the score phase
       for (int i = gtid; i < TP * 32; i += 256) {
         const int pp = i >> 5, c4 = i & 31;
-        if (n0 + pp < N) cp_async16(sQ + (u * TP + pp) * LDQ + c4 * 4, q_in + (n0 + pp) * W_HID + c4 * 4);
+        if (n0 + pp < N) cp_async16(sQ + (u * TP + pp) * LDQ + c4 * 4, q_in + pm128_off(n0 + pp, c4 * 4));
         else *reinterpret_cast<float4*>(sQ + (u * TP + pp) * LDQ + c4 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       cp_async_commit();
@@ -508,7 +508,8 @@ template <int MODE>
 __global__ void __launch_bounds__(NT, 1)
 row_gemm128_kernel(const float* __restrict__ A, const float* __restrict__ wpacked, const int64_t N, const float* __restrict__ resid,
                    const float* __restrict__ ln_g, const float* __restrict__ ln_b, const float* __restrict__ wsum,
-                   float* __restrict__ out, float* __restrict__ out_feature, unsigned char* __restrict__ out_split, const int S_split) {
+                   float* __restrict__ out, float* __restrict__ out_feature, unsigned char* __restrict__ out_split, const int S_split,
+                   const bool resid_pm) {
   extern __shared__ __align__(1024) unsigned char smraw[];
   unsigned char* sWt = smraw + RG_W_OFF;
   unsigned char* aHi = smraw + RG_A_OFF;
@@ -589,19 +590,22 @@ row_gemm128_kernel(const float* __restrict__ A, const float* __restrict__ wpacke
         tc::tmem_ld32(trow + (uint32_t)(c0 + cc), v);
         if (n < N) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + n * W_HID + c0 + cc + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(out + pm128_off(n, c0 + cc + j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         }
       }
     } else {
       float v[64];
       float sum = 0.f;
+      // residual row: 4-float pieces `rstep` floats apart (row-major: 4; piece-major, pm128_off: 128)
+      const float* rbase = resid + (resid_pm ? (n >> 5) * 4096 + (n & 31) * 4 : n * W_HID);
+      const int64_t rstep = resid_pm ? 128 : 4;
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 32) {
         float t32[32];
         tc::tmem_ld32(trow + (uint32_t)(c0 + cc), t32);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
-          const float4 r4 = n < N ? __ldcs(reinterpret_cast<const float4*>(resid + n * W_HID + c0 + cc + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 r4 = n < N ? __ldcs(reinterpret_cast<const float4*>(rbase + (int64_t)((c0 + cc + j) >> 2) * rstep)) : make_float4(0.f, 0.f, 0.f, 0.f);
           v[cc + j] = t32[j] + r4.x; v[cc + j + 1] = t32[j + 1] + r4.y; v[cc + j + 2] = t32[j + 2] + r4.z; v[cc + j + 3] = t32[j + 3] + r4.w;
           sum += (v[cc + j] + v[cc + j + 1]) + (v[cc + j + 2] + v[cc + j + 3]);
         }
@@ -663,17 +667,17 @@ int read_prof_nb2(long long* out, int n) {
   return cudaMemcpyFromSymbol(out, nb2::g_prof_nb2, sizeof(long long) * (n < 32 ? n : 32)) == cudaSuccess ? 0 : set_error("read_prof_nb2 failed");
 }
 
-size_t neighbor2_scratch_floats(int64_t N) { return (size_t)N * W_HID * 2 + (size_t)((N + 63) / 64 * 64); }
+size_t neighbor2_scratch_floats(int64_t N) { return pm128_floats(N) + (size_t)N * W_HID + (size_t)((N + 63) / 64 * 64); }
 
-// scratch: q [N][128] | o [N][128] | wsum [N]  (neighbor2_scratch_floats(N) floats)
+// scratch: q (piece-major, whole groups of 32 rows) | o [N][128] | wsum [N]  (neighbor2_scratch_floats(N) floats)
 int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
                      const float* d2, const float* agg, float* fagg, unsigned char* fagg_split, int S_split, float* feature,
-                     float* weights, float* scratch, bool q_ready, cudaStream_t st) {
+                     float* weights, float* scratch, bool q_ready, cudaStream_t st, bool agg_pm) {
   if (N <= 0) return 0;
   if (K < 1 || K > 8) return set_error("neighbor: K must be in 1..8");
   if (!scratch) return set_error("neighbor: scratch is NULL");
   float* q = scratch;
-  float* o = q + (size_t)N * W_HID;
+  float* o = q + pm128_floats(N);
   float* wsum = o + (size_t)N * W_HID;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -686,7 +690,7 @@ int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   const unsigned g128 = (unsigned)(t128 < sms ? t128 : sms);
   if (fagg_split && (S_split < 1 || N % S_split != 0)) return set_error("neighbor: the pre-split output needs whole rays");
   if (!q_ready) {
-    nb2::row_gemm128_kernel<0><<<g128, NT, nb2::RG_SMEM, st>>>(agg, w.tb_wq, N, nullptr, nullptr, nullptr, nullptr, q, nullptr, nullptr, 1);
+    nb2::row_gemm128_kernel<0><<<g128, NT, nb2::RG_SMEM, st>>>(agg, w.tb_wq, N, nullptr, nullptr, nullptr, nullptr, q, nullptr, nullptr, 1, false);
     if (check_launch("qproj_kernel")) return 1;
     prof_mark("qproj");
   }
@@ -696,7 +700,7 @@ int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
   if (check_launch("neighbor2_kernel")) return 1;
   prof_mark("neighbor2");
   nb2::row_gemm128_kernel<1><<<g128, NT, nb2::RG_SMEM, st>>>(o, w.tb_wfc, N, agg, w.ln_g, w.ln_b, wsum, fagg, feature, fagg_split,
-                                                             S_split < 1 ? 1 : S_split);
+                                                             S_split < 1 ? 1 : S_split, agg_pm);
   if (check_launch("attn_tail_kernel")) return 1;
   prof_mark("attn_tail");
   return 0;

@@ -43,6 +43,13 @@ struct UnetLayer {
   const float* be2;
 };
 
+// [N][128] fp32 matrices that are written and read by thread-per-row epilogues (aggregated, the attention query): the same
+// piece-major layout with 32 pieces per row - groups of 32 rows (4096 floats), piece q of row r at q * 128 + (r & 31) * 4.  A
+// row-major 16-byte access per lane touches 32 different 128-byte lines per instruction; here it is one 512-byte run.  Buffers
+// hold whole groups (N rounded up to 32 rows).
+__host__ __device__ __forceinline__ int64_t pm128_off(int64_t r, int c) { return (r >> 5) * 4096 + (int64_t)(c >> 2) * 128 + (r & 31) * 4 + (c & 3); }
+__host__ __device__ __forceinline__ size_t pm128_floats(int64_t N) { return (size_t)((N + 31) / 32) * 4096; }
+
 // LayerNorm affine [rows][C] for thread-per-row readers: groups of 32 rows, the 4-float pieces of a row 512 bytes apart (see
 // partial_off).  Float offset of element (r, c):
 __host__ __device__ __forceinline__ int64_t ln_off(int r, int c, int C) { return (int64_t)(r >> 5) * (32 * C) + (c >> 2) * 128 + (r & 31) * 4 + (c & 3); }

@@ -30,18 +30,19 @@ struct FeatPeers {
 // GEMMs (fc_tail_kernel) instead of inside aggregate_kernel.  Returns 0 (done), 2 (done, and `q_out` holds W_q aggregated) or 1.
 int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int with_blend, float* agg,
                      float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, float* visdd_scratch,
-                     float* g_scratch, float* q_out, cudaStream_t st);
-int launch_fc_tail(const RenderW& w, const float* g, int64_t N, float* agg, float* q, cudaStream_t st);
+                     float* g_scratch, float* q_out, cudaStream_t st, bool agg_pm = false);
+// `q` is written in the piece-major layout of pm128_off, `agg` too if `agg_pm` (both hold pm128_floats(N) floats then)
+int launch_fc_tail(const RenderW& w, const float* g, int64_t N, float* agg, float* q, bool agg_pm, cudaStream_t st);
 int launch_visibility(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, float* visdd, float* mvv, cudaStream_t st);
 // second generation (neighbor2.cu): q projection, 32-sample super-tiles with the attention projections on tcgen05, fc + LayerNorm
 // tail; `scratch` holds neighbor2_scratch_floats(N) floats
 size_t neighbor2_scratch_floats(int64_t N);
 // outputs: `fagg` fp32 [N][128] and / or `fagg_split` (the pair ray kernel's operand layout, samples grouped into rays of
 // `S_split`); either may be null
-// `q_ready`: scratch already holds q = W_q aggregated (fc_tail_kernel wrote it)
+// `q_ready`: scratch already holds q = W_q aggregated (fc_tail_kernel wrote it, piece-major: pm128_off)
 int launch_neighbor2(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int K, const int* idx,
                      const float* d2, const float* agg, float* fagg, unsigned char* fagg_split, int S_split, float* feature,
-                     float* weights, float* scratch, bool q_ready, cudaStream_t st);
+                     float* weights, float* scratch, bool q_ready, cudaStream_t st, bool agg_pm = false);   // agg_pm: `agg` is in the pm128_off layout
 int launch_blend_project(const float* feat, int64_t P, const float* bl1v, float* out, cudaStream_t st);
 int launch_linear(const float* A, int64_t N, int K, int lda, const float* Wt, const float* bias, int Nout, int act,
                   float* out, int ldo, cudaStream_t st);

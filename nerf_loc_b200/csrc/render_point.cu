@@ -993,7 +993,7 @@ static int set_smem(Kern k, size_t bytes) {
 
 int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, int64_t N, int with_blend, float* agg,
                      float* partial, float* rgbvis, unsigned char* nvalid, float* mvf, float* mvv, float* visdd_scratch,
-                     float* g_scratch, float* q_out, cudaStream_t st) {
+                     float* g_scratch, float* q_out, cudaStream_t st, bool agg_pm) {
   if (N <= 0) return 0;
   if (sc.V < 1 || sc.V > 16) return set_error("aggregate: number of reference views must be in 1..16");
   if (with_blend && !sc.featb) return set_error("aggregate: scene.featmaps_blend is NULL (call nlb_blend_prepare once per frame)");
@@ -1029,7 +1029,7 @@ int launch_aggregate(const SceneDev& sc, const RenderW& w, const PointSrc& ps, i
       aggregate_kernel<ROWS_G, true, true, true><<<pgrid, NT, smem_p, st>>>(sc, w, ps, N, with_blend, vd, g_scratch, agg, partial, rgbvis, nvalid, mvf, mvv);
       if (check_launch("aggregate_kernel")) return 1;
       prof_mark("aggregate");
-      if (launch_fc_tail(w, g_scratch, N, agg, q_out, st)) return 1;
+      if (launch_fc_tail(w, g_scratch, N, agg, q_out, agg_pm, st)) return 1;
       prof_mark("fc_tail");
       return 2;   // aggregated AND the attention query are done
     } else if (ext) {
