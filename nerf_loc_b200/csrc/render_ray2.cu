@@ -100,6 +100,14 @@ struct Ctx {
 };
 
 __device__ __forceinline__ void tld16(uint32_t addr, float (&v)[16]) { tc::tmem_ld16(addr, v); }
+// 16 consecutive bias values (64-byte aligned: packed arrays start on 256-byte boundaries) as four 16-byte loads
+__device__ __forceinline__ void ldb16(const float* __restrict__ p, float (&b)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+    b[4 * i] = t.x; b[4 * i + 1] = t.y; b[4 * i + 2] = t.z; b[4 * i + 3] = t.w;
+  }
+}
 
 // block-wide sums of two independent quantities (slot 0 / slot 1 of the ray pair); every thread gets both
 __device__ __forceinline__ float2 block_sum2(float a, float b, float* red) {
@@ -148,9 +156,11 @@ __device__ __forceinline__ void epi_conv1(const Ctx& c, const uint32_t tmem, con
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       float v[16];
+      float bv[16];
+      ldb16(U.b + c0 + cc, bv);
       tld16(c.trow + tmem + 64 * ray + c0 + cc, v);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) sum[ray] += v[j] + __ldg(U.b + c0 + cc + j);
+      for (int j = 0; j < 16; ++j) sum[ray] += v[j] + bv[j];
     }
   const float2 tot = block_sum2(valid ? sum[0] : 0.f, valid ? sum[1] : 0.f, c.red);
   const float mean[2] = {tot.x / n, tot.y / n};
@@ -160,9 +170,11 @@ __device__ __forceinline__ void epi_conv1(const Ctx& c, const uint32_t tmem, con
 #pragma unroll
     for (int cc = 0; cc < 32; cc += 16) {
       float v[16];
+      float bv[16];
+      ldb16(U.b + c0 + cc, bv);
       tld16(c.trow + tmem + 64 * ray + c0 + cc, v);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) { const float d = (v[j] + __ldg(U.b + c0 + cc + j)) - mean[ray]; q[ray] += d * d; }
+      for (int j = 0; j < 16; ++j) { const float d = (v[j] + bv[j]) - mean[ray]; q[ray] += d * d; }
     }
   const float2 qt = block_sum2(valid ? q[0] : 0.f, valid ? q[1] : 0.f, c.red);
   const float rstd[2] = {1.f / sqrtf(qt.x / n + 1e-5f), 1.f / sqrtf(qt.y / n + 1e-5f)};
@@ -182,10 +194,12 @@ __device__ __forceinline__ void epi_conv1(const Ctx& c, const uint32_t tmem, con
 #pragma unroll
     for (int ray = 0; ray < 2; ++ray) {
       float v[16];
+      float bv[16];
+      ldb16(U.b + c0 + cc, bv);
       tld16(c.trow + tmem + 64 * ray + c0 + cc, v);
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        const float y = elu(((v[j] + __ldg(U.b + c0 + cc + j)) - mean[ray]) * rstd[ray] * g[j] + be[j]);
+        const float y = elu(((v[j] + bv[j]) - mean[ray]) * rstd[ray] * g[j] + be[j]);
         v[j] = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, 1));     // MaxPool over the sample pair (2j, 2j + 1)
       }
       // both lanes of a pair hold the pooled row: the even lane stores ray 0's, the odd lane ray 1's
@@ -216,9 +230,11 @@ __device__ __forceinline__ void epi_enc_pair(const Ctx& c, const uint32_t tmem, 
 #pragma unroll
   for (int cc = 0; cc < 64; cc += 16) {
     float v[16];
+    float bv[16];
+    ldb16(U.b + c0 + cc, bv);
     tld16(c.trow + tmem + c0 + cc, v);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) sum += v[j] + __ldg(U.b + c0 + cc + j);
+    for (int j = 0; j < 16; ++j) sum += v[j] + bv[j];
   }
   if (!valid) sum = 0.f;
   const float2 tot = block_sum2(b == 0 ? sum : 0.f, b == 1 ? sum : 0.f, c.red);
@@ -227,9 +243,11 @@ __device__ __forceinline__ void epi_enc_pair(const Ctx& c, const uint32_t tmem, 
 #pragma unroll
   for (int cc = 0; cc < 64; cc += 16) {
     float v[16];
+    float bv[16];
+    ldb16(U.b + c0 + cc, bv);
     tld16(c.trow + tmem + c0 + cc, v);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { const float d = (v[j] + __ldg(U.b + c0 + cc + j)) - mean; q += d * d; }
+    for (int j = 0; j < 16; ++j) { const float d = (v[j] + bv[j]) - mean; q += d * d; }
   }
   if (!valid) q = 0.f;
   const float2 qt = block_sum2(b == 0 ? q : 0.f, b == 1 ? q : 0.f, c.red);
@@ -240,6 +258,8 @@ __device__ __forceinline__ void epi_enc_pair(const Ctx& c, const uint32_t tmem, 
 #pragma unroll
   for (int cc = 0; cc < 64; cc += 16) {
     float v[16];
+    float bv[16];
+    ldb16(U.b + c0 + cc, bv);
     tld16(c.trow + tmem + c0 + cc, v);
 #pragma unroll
     for (int j = 0; j < 16; j += 4) {
@@ -248,7 +268,7 @@ __device__ __forceinline__ void epi_enc_pair(const Ctx& c, const uint32_t tmem, 
       const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float y = elu(((v[j + u] + __ldg(U.b + c0 + cc + j + u)) - mean) * rstd * gg[u] + bb[u]);
+        const float y = elu(((v[j + u] + bv[j + u]) - mean) * rstd * gg[u] + bb[u]);
         v[j + u] = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, 2));   // partner row: same ray, sample s ^ 1
       }
     }
@@ -280,9 +300,11 @@ __device__ __forceinline__ void epi_dec(const Ctx& c, const uint32_t tmem, const
 #pragma unroll
     for (int cc = 0; cc < NC; cc += 16) {
       float v[16];
+      float bv[16];
+      ldb16(U.b + c0 + cc, bv);
       tld16(c.trow + tmem + par * N + c0 + cc, v);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) sum += v[u] + __ldg(U.b + c0 + cc + u);
+      for (int u = 0; u < 16; ++u) sum += v[u] + bv[u];
     }
   if (!valid) sum = 0.f;
   const float2 tot = block_sum2(b == 0 ? sum : 0.f, b == 1 ? sum : 0.f, c.red);
@@ -293,9 +315,11 @@ __device__ __forceinline__ void epi_dec(const Ctx& c, const uint32_t tmem, const
 #pragma unroll
     for (int cc = 0; cc < NC; cc += 16) {
       float v[16];
+      float bv[16];
+      ldb16(U.b + c0 + cc, bv);
       tld16(c.trow + tmem + par * N + c0 + cc, v);
 #pragma unroll
-      for (int u = 0; u < 16; ++u) { const float d = (v[u] + __ldg(U.b + c0 + cc + u)) - mean; q += d * d; }
+      for (int u = 0; u < 16; ++u) { const float d = (v[u] + bv[u]) - mean; q += d * d; }
     }
   if (!valid) q = 0.f;
   const float2 qt = block_sum2(b == 0 ? q : 0.f, b == 1 ? q : 0.f, c.red);
@@ -309,6 +333,8 @@ __device__ __forceinline__ void epi_dec(const Ctx& c, const uint32_t tmem, const
 #pragma unroll
     for (int cc = 0; cc < NC; cc += 16) {
       float v[16];
+      float bv[16];
+      ldb16(U.b + c0 + cc, bv);
       tld16(c.trow + tmem + par * N + c0 + cc, v);
 #pragma unroll
       for (int u = 0; u < 16; u += 4) {
@@ -316,7 +342,7 @@ __device__ __forceinline__ void epi_dec(const Ctx& c, const uint32_t tmem, const
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(U.be2 + ln_off(so, c0 + cc + u, N)));
         const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int t = 0; t < 4; ++t) v[u + t] = elu(((v[u + t] + __ldg(U.b + c0 + cc + u + t)) - mean) * rstd * gg[t] + bb[t]);
+        for (int t = 0; t < 4; ++t) v[u + t] = elu(((v[u + t] + bv[u + t]) - mean) * rstd * gg[t] + bb[t]);
       }
       if (valid) {
 #pragma unroll
@@ -750,9 +776,11 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
 #pragma unroll
         for (int cc = 0; cc < 64; cc += 16) {
           float v[16];
+          float bv[16];
+          ldb16(U.b + c0 + cc, bv);
           tld16(c.trow + tmem + 128 * ray + c0 + cc, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sum[ray] += v[j] + __ldg(U.b + c0 + cc + j);
+          for (int j = 0; j < 16; ++j) sum[ray] += v[j] + bv[j];
         }
       const float2 tot = block_sum2(valid ? sum[0] : 0.f, valid ? sum[1] : 0.f, red);
       const float mean[2] = {tot.x / n, tot.y / n};
@@ -762,9 +790,11 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
 #pragma unroll
         for (int cc = 0; cc < 64; cc += 16) {
           float v[16];
+          float bv[16];
+          ldb16(U.b + c0 + cc, bv);
           tld16(c.trow + tmem + 128 * ray + c0 + cc, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { const float d = (v[j] + __ldg(U.b + c0 + cc + j)) - mean[ray]; q[ray] += d * d; }
+          for (int j = 0; j < 16; ++j) { const float d = (v[j] + bv[j]) - mean[ray]; q[ray] += d * d; }
         }
       const float2 qt = block_sum2(valid ? q[0] : 0.f, valid ? q[1] : 0.f, red);
       const float rstd[2] = {1.f / sqrtf(qt.x / n + 1e-5f), 1.f / sqrtf(qt.y / n + 1e-5f)};
@@ -785,10 +815,12 @@ ray2_kernel(const SceneDev sc, const RenderW w, const float* __restrict__ z_vals
 #pragma unroll
         for (int ray = 0; ray < 2; ++ray) {
           float v[16];
+          float bv[16];
+          ldb16(U.b + c0 + cc, bv);
           tld16(c.trow + tmem + 128 * ray + c0 + cc, v);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            part[ray] = fmaf(elu(((v[j] + __ldg(U.b + c0 + cc + j)) - mean[ray]) * rstd[ray] * g[j] + be[j]), sw[j], part[ray]);
+            part[ray] = fmaf(elu(((v[j] + bv[j]) - mean[ray]) * rstd[ray] * g[j] + be[j]), sw[j], part[ray]);
         }
       }
       sSigP[0 * 256 + c.half * 128 + c.m] = part[0];
