@@ -330,9 +330,9 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
       const int c0 = half * 64;
       const int id = sIdx[u * 128 + row];
       const float* add = mode == 0 ? (id >= 0 ? sc.sup_pre + (size_t)id * W_HID : nullptr) : (mode == 1 ? w.b2 : w.b3);
-      float4 a4[8];
+      float4 a4[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a4[j] = add ? __ldg(reinterpret_cast<const float4*>(add + c0 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j = 0; j < 16; ++j) a4[j] = add ? __ldg(reinterpret_cast<const float4*>(add + c0 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       wait_d();
 #pragma unroll
       for (int cc = 0; cc < 64; cc += 16) {
@@ -341,14 +341,9 @@ neighbor2_kernel(const SceneDev sc, const RenderW w, const PointSrc ps, const in
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 b4 = a4[(cc & 16) / 4 + j];
+          const float4 b4 = a4[cc / 4 + j];
           tc::split_bf16x2(leaky(v[4 * j] + b4.x), leaky(v[4 * j + 1] + b4.y), hi[2 * j], lo[2 * j]);
           tc::split_bf16x2(leaky(v[4 * j + 2] + b4.z), leaky(v[4 * j + 3] + b4.w), hi[2 * j + 1], lo[2 * j + 1]);
-        }
-        if (cc < 32) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            a4[(cc & 16) / 4 + j] = add ? __ldg(reinterpret_cast<const float4*>(add + c0 + cc + 32 + j * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         tc::tmem_st8_u(trow + TM_AHI + (uint32_t)((c0 + cc) / 2), hi);
         tc::tmem_st8_u(trow + TM_ALO + (uint32_t)((c0 + cc) / 2), lo);
