@@ -370,13 +370,15 @@ template <int K>
 __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy, float qz, TopK<K>& best,
                                            const float bound = FLT_MAX) {
   constexpr int STACK = 12 * FAN;
-  unsigned stk_node[STACK];
-  float stk_d[STACK];
+  unsigned long long stk[STACK];   // (distance bits << 32) | level << 28 | node: one 8-byte local-memory access per push / pop
   int sp = 0;
   const int top = t.n_levels - 1;
   // push the top level (<= FAN nodes unless the level cap was hit), farthest first
   for (int n = t.level_count[top] - 1; n >= 0; --n) {
-    if (sp < STACK) { stk_node[sp] = ((unsigned)top << 28) | (unsigned)n; stk_d[sp] = node_d2(qx, qy, qz, t.boxes + t.level_off[top] + NODE_F4 * n); ++sp; }
+    if (sp < STACK) {
+      const float d0 = node_d2(qx, qy, qz, t.boxes + t.level_off[top] + NODE_F4 * n);
+      stk[sp++] = ((unsigned long long)__float_as_uint(d0) << 32) | (((unsigned)top << 28) | (unsigned)n);
+    }
   }
   // The nearest child of a node is visited next without a round trip through the stack (which lives in local memory): `cur`
   // holds it; the visiting order is the one of a stack that had it on top.
@@ -389,8 +391,8 @@ __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy,
     if (have_cur) {
       nd = cur_d; code = cur; have_cur = false;
     } else {
-      --sp;
-      nd = stk_d[sp]; code = stk_node[sp];
+      const unsigned long long e = stk[--sp];
+      nd = __uint_as_float((unsigned)(e >> 32)); code = (unsigned)e;
     }
     if (nd > fminf(best.worst(), bound)) continue;  // strict: equal distance may still hide a smaller index
     const int lvl = code >> 28;
@@ -424,7 +426,7 @@ __device__ __forceinline__ void knn_search(const KnnTree& t, float qx, float qy,
 #pragma unroll
       for (int k = 0; k < FAN; ++k) {
         if (k < nc && k != nearest && cd[k] <= w && sp < STACK) {
-          stk_node[sp] = ((unsigned)cl << 28) | (unsigned)(c0 + k); stk_d[sp] = cd[k]; ++sp;
+          stk[sp++] = ((unsigned long long)__float_as_uint(cd[k]) << 32) | (((unsigned)cl << 28) | (unsigned)(c0 + k));
         }
       }
       if (nearest >= 0 && nearest_d <= w) {

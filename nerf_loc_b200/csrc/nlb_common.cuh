@@ -44,6 +44,15 @@ __device__ __forceinline__ void fma2_v(float& c0, float& c1, const float a0, con
       "fma.rn.f32x2 rc, ra, rb, rc;\nmov.b64 {%0, %1}, rc;\n}" : "+f"(c0), "+f"(c1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
 
+// packed fp32 pairs (one issue slot for two FMAs): operands are 64-bit registers holding two floats
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float2 up2(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
+__device__ __forceinline__ f32x2 fma2p(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ f32x2 mul2p(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 add2p(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+
 // LeakyReLU(0.01) as max(x, 0.01 x): the same value for every finite x (signed zeros included) in two instructions instead of three
 __device__ __forceinline__ float leaky(float x) { return fmaxf(x, 0.01f * x); }
 // ELU(alpha=1).  exp(x) - 1 with the hardware exponential: absolute error ~1e-7 for x < 0 (the library expm1f costs ~40

@@ -146,14 +146,6 @@ __device__ __forceinline__ void mean_var_rows(const float* __restrict__ f0, cons
   }
 }
 
-// packed fp32 pairs (one issue slot for two FMAs): the gather keeps channel pairs in 64-bit registers end to end
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float a, float b) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ float2 up2(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
-__device__ __forceinline__ f32x2 fma2p(f32x2 a, f32x2 b, f32x2 c) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ f32x2 mul2p(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ f32x2 add2p(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-
 // EXT: visibility and depth difference per (sample, view) come from visibility_kernel (`visdd_in`, [N][V] float2) - the NeuRay
 // projection, the visibility-feature gather and the decoder are compiled out.
 // GOUT (with FUSED and EXT): the per-sample statistics vector (mean | variance | 3 extras, the input of out_fc) goes to global
