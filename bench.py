@@ -27,8 +27,16 @@ import torch
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"          # no "NCCL version ..." banner on stdout: rank 0 prints JSON lines only
+# stdout carries the JSON line(s) and nothing else: native libraries that write to file descriptor 1 (the "NCCL version ..."
+# banner, for one) are sent to stderr, the result lines go through a private copy of the original descriptor
+_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
 
 CONFIGS = {
     # name: (H, W, V, S, workload)
@@ -296,7 +304,7 @@ def run_reference(args):
                          "faithful_knn": faithful_knn_probe(sc, sup, ro, rd, S)},
         "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 class Runner:
@@ -598,7 +606,7 @@ def run_b200(args):
                 line = r.measure(f"ray-count sweep (configs[4]): 2^{e} rays x {S} samples/ray, 8 ref views 640x480", {"sweep_point": [2 ** e, S]})
                 if rank == 0:
                     line["cpu_baseline"] = None
-                    print(json.dumps(line), flush=True)
+                    emit(line)
             del r
             torch.cuda.empty_cache()
     else:
@@ -644,7 +652,7 @@ def run_b200(args):
                                         "note": "sum of the three stages measured back to back on one GPU; PnP parity unpinned (COLMAP absent)"}
             else:
                 line["cpu_baseline"] = None
-            print(json.dumps(line), flush=True)
+            emit(line)
     if world > 1:
         dist.destroy_process_group()
 
