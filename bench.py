@@ -29,13 +29,22 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # stdout carries the JSON line(s) and nothing else: native libraries that write to file descriptor 1 (the "NCCL version ..."
 # banner, for one) are sent to stderr, the result lines go through a private copy of the original descriptor
-_OUT = os.fdopen(os.dup(1), "w")
-os.dup2(2, 1)
+_OUT = None
+
+
+def claim_stdout():
+    """Called once by main(): from here on file descriptor 1 is stderr for everybody but emit()."""
+    global _OUT
+    if _OUT is None:
+        sys.stdout.flush()
+        _OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
 
 
 def emit(line):
-    _OUT.write(json.dumps(line) + "\n")
-    _OUT.flush()
+    out = _OUT if _OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 CONFIGS = {
@@ -673,6 +682,7 @@ def main():
                     help="rays in the CPU sample: b200 arm default 4096 (about 15 s of host time), 0 = skip; reference arm default: "
                          "a multiple of 2048 sized from --steps")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         args.cpu_rays = max(args.cpu_rays, 0)
         run_reference(args)
