@@ -52,6 +52,30 @@ def test_knn_points_signature_and_surface_cloud():
     assert torch.equal(out.knn[0].cpu(), xyz[i_ref])
 
 
+@pytest.mark.parametrize("K", [1, 3, 5, 8, 11])
+def test_knn_points_ragged_batches_and_any_k(K):
+    """knn_utils.py:97-222 with lengths1 / lengths2 and neighbour counts the kernel is not instantiated for: indices and squared
+    distances bit for bit against the C oracle per cloud, zeros beyond the lengths and where a cloud has fewer than K points."""
+    from nerf_loc_b200.knn import knn_gather
+    g = torch.Generator().manual_seed(100 + K)
+    p1 = torch.rand(3, 200, 3, generator=g) * 4 - 2
+    p2 = torch.rand(3, 500, 3, generator=g) * 4 - 2
+    p2[1, 10:20] = p2[1, 0:10]                                  # exact ties
+    l1 = torch.tensor([200, 57, 1]); l2 = torch.tensor([500, 123, 4])
+    out = knn_points(p1.cuda(), p2.cuda(), lengths1=l1.cuda(), lengths2=l2.cuda(), K=K, return_nn=True)
+    assert tuple(out.idx.shape) == (3, 200, K) and out.idx.dtype == torch.int64
+    for b in range(3):
+        n1, n2 = int(l1[b]), int(l2[b])
+        kk = min(K, n2)
+        d_ref, i_ref = KO.knn_c(p1[b, :n1].contiguous(), p2[b, :n2].contiguous(), kk)
+        assert torch.equal(out.idx[b, :n1, :kk].cpu(), i_ref) and torch.equal(out.dists[b, :n1, :kk].cpu(), d_ref)
+        assert int(out.idx[b, :n1, kk:].abs().sum()) == 0 and float(out.dists[b, :n1, kk:].abs().sum()) == 0.0
+        assert int(out.idx[b, n1:].abs().sum()) == 0 and float(out.dists[b, n1:].abs().sum()) == 0.0
+    want = knn_gather(p2.cuda(), out.idx, l2.cuda())
+    assert torch.equal(out.knn, want)
+    assert float(out.knn[2, :, 4:].abs().sum()) == 0.0 if K > 4 else True
+
+
 @pytest.mark.parametrize("S,per_ray", [(128, False), (64, True), (24, False)])
 def test_knn_ray_samples_bit_exact(S, per_ray):
     """The render path's own search (8 lanes per query, warm start along the ray; csrc/knn.cu) against the C oracle: indices and

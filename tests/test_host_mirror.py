@@ -120,3 +120,21 @@ def test_top_level_front_end_matches_reference_modules():
     assert torch.allclose(e_r, e_m, atol=1e-6)
     xf = torch.randn(3, 4, 5, 192)
     assert torch.allclose(r_ad(xf, e_r, e_r[:1]), m_ad(xf, e_m, e_m[:1]), atol=1e-6)
+
+
+def test_knn_gather_masks_short_clouds_and_knn_points_validates_arguments():
+    """knn_utils.py:171-222 (gather with `lengths`) and the argument checks of knn_points (no search: the search needs a GPU)."""
+    from nerf_loc_b200.knn import knn_gather, knn_points
+    x = torch.arange(2 * 5 * 2, dtype=torch.float32).reshape(2, 5, 2)
+    idx = torch.tensor([[[0, 1, 4]], [[2, 0, 0]]])
+    out = knn_gather(x, idx, torch.tensor([5, 1]))
+    assert torch.equal(out[0, 0], x[0, [0, 1, 4]])
+    assert torch.equal(out[1, 0, 0], x[1, 2]) and float(out[1, 0, 1:].abs().sum()) == 0.0
+    assert torch.equal(knn_gather(x, idx), torch.stack([x[0, [0, 1, 4]][None], x[1, [2, 0, 0]][None]]))
+    for bad in (dict(K=0), dict(K=17), dict(lengths1=torch.tensor([3])), dict(lengths2=torch.tensor([-1]))):
+        with pytest.raises(ValueError):
+            knn_points(torch.zeros(1, 2, 3), torch.zeros(1, 2, 3), **bad)
+    with pytest.raises(ValueError):
+        knn_points(torch.zeros(1, 2, 2), torch.zeros(1, 2, 2))
+    with pytest.raises(ValueError):
+        knn_points(torch.zeros(2, 2, 3), torch.zeros(1, 2, 3))
